@@ -1,0 +1,200 @@
+/*
+ * pesr_b200 C-ABI: the drop-in boundary of the B200-native PESR hot path.
+ *
+ * The reference (thangvubk/PESR) has no FFI of its own: its hot path is a set of torch.nn modules
+ * (model/basic.py, model/pesr.py, model/vgg.py, model/focal_loss.py) driven by the step bodies in
+ * train.py:164-176, train.py:202-259 and test.py:101-112.  Every torch/cuDNN/cuBLAS/ATen call those
+ * modules make on the GPU is replaced by one of the entry points below.  The Python host side
+ * (pesr_b200/) binds them with ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - plain C: raw device pointers, sizes, a cudaStream_t (passed as void*) last; no torch types.
+ *  - every function returns 0 on success, a positive cudaError_t, or a negative PESR_E_* argument error;
+ *    pesr_last_error() returns a human-readable message for the calling thread's last failure.
+ *  - launches are asynchronous on the given stream; the library never allocates user-visible memory,
+ *    workspaces are caller-provided.
+ *  - activations are NHWC, 16-bit (dtype 0 = fp16, 1 = bf16) with fp32 accumulation; parameters and
+ *    parameter gradients stay fp32 in the reference's own layouts (OIHW conv weights, [out,in] linear).
+ */
+#ifndef PESR_B200_H
+#define PESR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PESR_E_ARG (-1)      /* bad argument / unsupported shape */
+#define PESR_E_DRIVER (-2)   /* cuTensorMapEncodeTiled unavailable or failed */
+#define PESR_E_WORKSPACE (-3) /* workspace too small */
+
+#define PESR_DT_F16 0
+#define PESR_DT_BF16 1
+
+#define PESR_ACT_NONE 0
+#define PESR_ACT_RELU 1   /* nn.ReLU, model/pesr.py:11, torchvision vgg19 */
+#define PESR_ACT_LRELU 2  /* nn.LeakyReLU(0.2), model/pesr.py:47 */
+
+#define PESR_OUT_NORMAL 0     /* out pixel (n, h*sy+oy, w*sx+ox), channel coff+q */
+#define PESR_OUT_SHUFFLE2 1   /* nn.PixelShuffle(2) fused (model/basic.py:57,59), packed channel order (i,j,c) */
+#define PESR_OUT_UNSHUFFLE2 2 /* inverse of PixelShuffle(2): the backward of the above */
+
+#define PESR_MAX_TAPS 9
+#define PESR_MAX_SRC 4
+
+const char* pesr_last_error(void);
+int pesr_version(void);
+/* Number of kernels this library has launched since the last reset (bench.py's gpu_launches). */
+long long pesr_launch_count(int reset);
+/* sizeof(pesr_conv_desc) for which == 0, sizeof(pesr_wgrad_desc) for 1 (binding self-check). */
+int pesr_sizeof(int which);
+
+/* ------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution, forward and backward-data.  Replaces nn.Conv2d forward/dgrad
+ * (model/basic.py:4-7 `Conv`; call sites model/pesr.py:20,23, model/basic.py:41,56-60,
+ * model/pesr.py:54,63 and torchvision vgg19.features used by model/vgg.py:8-10).
+ *
+ * GEMM view: M = nb*h*w output pixels (tiles of tile_h x tile_w = 128 pixels), N = cout (tiles of
+ * block_n), K = ntaps * cin.  For tap t the A operand is the activation box whose top-left input
+ * pixel is (h0 + tap_dh[t], w0 + tap_dw[t]) of source tensor tap_src[t]; out-of-bounds pixels read
+ * as zero (TMA OOB fill == the conv's zero padding).  The B operand is rows
+ * [tap_widx[t]*cout + n0, +block_n) of the packed K-major weight matrix [w_rows][cin].
+ * Backward-data is the same kernel with flipped/transposed packed weights (pesr_pack_weights).
+ * Stride-2 convolutions pass the four parity planes of the input as sources 0..3.
+ *
+ * Epilogue (per output element, in this order):
+ *   v = alpha * [alpha_dev] * (acc + bias[q]);  v += res32;  v += res16;  v = act(v);
+ *   v *= act'(mask16)   (mask_mode 1: relu', 2: lrelu'(0.2));
+ *   out32 = v (normal addressing);  out16 = cvt(v) (out_mode addressing).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct pesr_conv_desc {
+  int32_t dtype;            /* PESR_DT_* for src / weights / out16 / res16 / mask16 */
+  int32_t nb, h, w;         /* GEMM-M pixel grid */
+  int32_t cin, cout;        /* cin multiple of 64 (per tap), cout multiple of block_n */
+  int32_t block_n;          /* 32, 64, 128 or 256 */
+  int32_t tile_h, tile_w;   /* tile_h * tile_w == 128 */
+  int32_t ntaps;
+  int8_t tap_dh[PESR_MAX_TAPS], tap_dw[PESR_MAX_TAPS], tap_src[PESR_MAX_TAPS], tap_widx[PESR_MAX_TAPS];
+  /* sources: NHWC views; strides in elements, channel stride 1 */
+  const void* src[PESR_MAX_SRC];
+  int32_t src_h[PESR_MAX_SRC], src_w[PESR_MAX_SRC];
+  int64_t src_sn[PESR_MAX_SRC], src_sh[PESR_MAX_SRC], src_sw[PESR_MAX_SRC];
+  int32_t nsrc;
+  const void* wpacked;      /* [w_rows][cin], 16-bit, K-major */
+  int32_t w_rows;
+  /* epilogue */
+  const float* bias;        /* [cout] or NULL */
+  float alpha;
+  const float* alpha_dev;   /* optional device scalar multiplied into alpha */
+  const float* res32; int32_t ld_res32;
+  const void* res16;  int32_t ld_res16;
+  int32_t act;
+  const void* mask16; int32_t ld_mask16; int32_t mask_mode;
+  float* out32; int32_t ld_out32;
+  void* out16;  int32_t ld_out16;  /* channels per pixel of the out16 tensor */
+  int32_t out_mode;
+  int32_t out_h, out_w;     /* out16 pixel grid (NORMAL mode; 0 = same as h, w) */
+  int32_t out_sy, out_sx, out_oy, out_ox, out_coff;
+  int32_t ps_c;             /* SHUFFLE2: channels of the shuffled tensor (cout/4) */
+} pesr_conv_desc;
+
+int pesr_conv_igemm(const pesr_conv_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward-filter as a split-K GEMM with both operands MN-major (pixels are K).
+ *   part[split][tap][m][n] = sum over the split's pixels p of  a[p][m0+m] * b[p (+) tap][n0+n]
+ * a = dy (M = cout), b = x (N = cin, shifted by the tap with zero fill).  Replaces cuDNN
+ * backward-filter for the call sites listed above.  pesr_wgrad_reduce sums the splits, applies
+ * `scale` (and 1/scale_dev) and writes/accumulates the fp32 OIHW gradient.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct pesr_wgrad_desc {
+  int32_t dtype;
+  int32_t nb, h, w;         /* pixel grid of `a` */
+  int32_t m_total, n_total; /* channels of a / b used; m_total multiple of 64 (tiles of 128, zero-filled past the end); n_total multiple of block_n */
+  int32_t block_m;          /* 128 */
+  int32_t block_n;          /* 64, 128 or 256 */
+  int32_t ntaps;
+  int8_t tap_dh[PESR_MAX_TAPS], tap_dw[PESR_MAX_TAPS], tap_src[PESR_MAX_TAPS];
+  const void* a; int32_t a_c;   /* NHWC [nb][h][w][a_c] */
+  const void* b[PESR_MAX_SRC];
+  int32_t b_h[PESR_MAX_SRC], b_w[PESR_MAX_SRC];
+  int64_t b_sn[PESR_MAX_SRC], b_sh[PESR_MAX_SRC], b_sw[PESR_MAX_SRC];
+  int32_t nsrc;
+  int32_t splits;           /* split-K factor (0 = choose) */
+  float* partials;          /* [splits][ntaps][m_total][n_total] fp32 workspace */
+  int64_t partials_elems;   /* capacity of `partials` in floats */
+} pesr_wgrad_desc;
+
+/* Returns the number of splits actually used in *splits_out (may be NULL). */
+int pesr_conv_wgrad(const pesr_wgrad_desc* d, int32_t* splits_out, void* stream);
+
+#define PESR_WMAP_OIHW 0      /* partial (tap, m=o, n=i)        -> grad[o][i][tap]                         */
+#define PESR_WMAP_OIHW_PS 1   /* packed shuffle order m=(i,j,c) -> grad[c*4+i*2+j][n][tap]                */
+#define PESR_WMAP_COL_IN 2    /* Cin<=7 im2col conv: (m=o, n=tap*ci_n+ci) -> grad[o][ci][tap]             */
+#define PESR_WMAP_COL_OUT 3   /* Cout<=3 col2im conv: (m=i, n=tap*co_n+o) -> grad[o][i][tap]              */
+/* grad = scale / (*div_dev if given) * sum_splits(partials), scattered per map_mode. */
+int pesr_wgrad_reduce(const float* partials, int32_t splits, int32_t ntaps, int32_t m_total, int32_t n_total,
+                      int32_t map_mode, int32_t co, int32_t ci, float scale, const float* div_dev,
+                      int32_t accumulate, float* grad_oihw, void* stream);
+/* Bring-up hook: override the MN-major smem descriptor strides of pesr_conv_wgrad (0 = built-in). */
+void pesr_debug_wgrad_desc(int lbo_bytes, int sbo_bytes);
+
+/* Weight packing: fp32 OIHW parameter -> 16-bit K-major GEMM operand (tap = ky*3+kx; tapf = 8-tap).
+ *  mode 0 fprop     : out[tap][o][i]                        (rows = 9*co, K = ci)
+ *  mode 1 dgrad     : out[tap][i][o] = w[o][i][tapf]        (rows = 9*ci, K = co)
+ *  mode 2 fprop, PixelShuffle(2) output order: row o' = (i*2+j)*C + c  <- o = c*4 + i*2 + j
+ *  mode 3 dgrad of mode 2: out[tap][i][o'] = w[o][i][tapf], K index o' permuted as in mode 2
+ *  mode 4 im2col fprop for tiny Cin : out[o][tap*ci + i], K zero-padded to pad_to      (rows = co)
+ *  mode 5 col2im fprop for tiny Cout: out[tap*co + o][i], rows zero-padded to pad_to   (K = ci)
+ *  mode 6 dgrad of mode 4 (a col2im GEMM): out[tap*ci + i][o], rows zero-padded to pad_to (K = co)
+ *  mode 7 dgrad of mode 5 (an im2col GEMM): out[i][tap*co + o], K zero-padded to pad_to   (rows = ci)
+ * ksize 1 is accepted for modes 0/1 (tap == 0).
+ */
+int pesr_pack_weights(const float* w_oihw, int32_t co, int32_t ci, int32_t ksize, int32_t mode, int32_t pad_to,
+                      int32_t dtype, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout / edge kernels.  These are HBM-bound; each is a single coalesced pass.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* 3-channel NCHW fp32 image -> im2col matrix [nb*h*w][64] (16-bit), column tap*3+c holds
+ * affine(src)[c] at pixel p + sgn*(ky-1, kx-1), zero outside the image; columns 27..63 are zero.
+ * affine: v = A(3x3, row-major [out][in]) * src + b, applied to in-bounds pixels only (this is how
+ * MeanShift, model/basic.py:9-17, composes with the zero padding of the following conv); A/b NULL =
+ * identity.  mul_dev: optional device scalar multiplied into the result (gradient scaling).
+ * Feeds the Cin=3 convs (model/pesr.py:23,54; vgg19.features[0]) and, with sgn=-1, the backward of
+ * the Cout=3 conv (model/basic.py:60). */
+int pesr_im2col3(const float* src_nchw, int32_t nb, int32_t h, int32_t w, const float* affine_a,
+                 const float* affine_b, const float* mul_dev, int32_t sgn, int32_t dtype, void* col, void* stream);
+
+/* col2im for a 3-channel output: out[n][c][h][w] = affine( sum_tap z[p + sgn*(ky-1,kx-1)][tap*3+c] * mul + bias[c] ).
+ * z is fp32 [nb*h*w][ldz].  pre (optional) receives the value before the affine (needed by the
+ * MeanShift weight gradient).  mul = mul_host / (*div_dev if given). */
+int pesr_col2im3(const float* z, int32_t ldz, int32_t nb, int32_t h, int32_t w, const float* bias,
+                 const float* affine_a, const float* affine_b, float mul_host, const float* div_dev, int32_t sgn,
+                 float* pre_nchw, float* out_nchw, void* stream);
+
+/* NCHW fp32 <-> NHWC 16-bit (generic; used at module boundaries and by the tests). */
+int pesr_nchw32_to_nhwc16(const float* src, int32_t nb, int32_t c, int32_t h, int32_t w, int32_t ldc,
+                          const float* mul_dev, int32_t dtype, void* dst, void* stream);
+int pesr_nhwc16_to_nchw32(const void* src, int32_t nb, int32_t c, int32_t h, int32_t w, int32_t ldc, float mul_host,
+                          const float* div_dev, int32_t dtype, float* dst, void* stream);
+
+/* out[c] (+)= mul * sum over pixels of x[p][c]   (bias gradients; x is 16-bit [npix][ldc]) */
+int pesr_colsum16(const void* x, int64_t npix, int32_t c, int32_t ldc, float mul_host, const float* div_dev,
+                  int32_t accumulate, int32_t dtype, float* out, void* stream);
+
+/* Dynamic power-of-two gradient scale: ws[0] = running max|x| (as uint bits), ws[1] = scale,
+ * ws[2] = 1/scale, with scale = 2^k chosen so that max|x|*scale lies in (target/2, target].
+ * Two launches (max-reduce, finalize); no host sync. */
+int pesr_amax_scale(const float* x, int64_t n, float target, float* ws3, void* stream);
+
+/* sums[0..8] = sum_p a[o][p]*b[i][p] (row-major [o][i]), sums[9..11] = sum_p a[o][p]; a, b are
+ * [nb][3][hw] fp32.  The MeanShift weight/bias gradients (model/basic.py:17 leaves them trainable). */
+int pesr_moments3(const float* a, const float* b, int32_t nb, int64_t hw, float* sums12, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PESR_B200_H */

@@ -1,0 +1,370 @@
+// Implicit-GEMM convolution for sm_100a: forward and backward-data of every 3x3 / 1x1 conv on the
+// PESR hot path (reference: model/basic.py:4-7 `Conv` -> nn.Conv2d -> cuDNN fprop/dgrad).
+//
+//   D[pixel, cout] = sum_tap sum_cin  X[pixel (+) tap, cin] * Wp[tap][cout][cin]
+//
+// One persistent CTA per SM, 6 warps:
+//   warp 0      TMA producer: per k-block one 4-D activation box (64 ch x tile_w x tile_h x 1 image; conv
+//               padding and ragged edges come from TMA's out-of-bounds zero fill) + one 2-D weight box.
+//   warp 1      tcgen05.mma issuer (single thread), fp32 accumulators in TMEM, two accumulator buffers
+//               so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warps 2..5  epilogue: tcgen05.ld -> bias / scale / residual / activation / ReLU-mask -> global
+//               (NHWC 16-bit, optional fp32 copy, optional PixelShuffle(2) / inverse addressing).
+#include "common.cuh"
+#include "host_util.cuh"
+
+namespace pesr {
+
+static constexpr int kTileM = 128;        // pixels per tile == TMEM lanes
+static constexpr int kKBlock = 64;        // K elements per pipeline stage (one 128B swizzle row)
+static constexpr int kABytes = kTileM * kKBlock * 2;  // 16 KB
+static constexpr int kAccStride = 256;    // TMEM columns reserved per accumulator buffer
+static constexpr int kNumThreads = 192;
+static constexpr int kMaxStages = 8;
+
+struct ConvMaps {
+  CUtensorMap a[PESR_MAX_SRC];
+  CUtensorMap b;
+};
+
+struct ConvK {
+  int dtype;
+  int nb, h, w, cin, cout, block_n, tile_h, tile_w, ntaps;
+  int tiles_h, tiles_w, n_tiles, num_tiles, kblocks_per_tap;
+  int stages, stage_bytes;
+  int8_t tap_dh[PESR_MAX_TAPS], tap_dw[PESR_MAX_TAPS], tap_src[PESR_MAX_TAPS], tap_widx[PESR_MAX_TAPS];
+  const float* bias;
+  float alpha;
+  const float* alpha_dev;
+  const float* res32; int ld_res32;
+  const uint16_t* res16; int ld_res16;
+  int act;
+  const uint16_t* mask16; int ld_mask16; int mask_mode;
+  float* out32; int ld_out32;
+  uint16_t* out16; int ld_out16;
+  int out_mode, out_h, out_w, out_sy, out_sx, out_oy, out_ox, out_coff, ps_c;
+};
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvK p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  uint8_t* tail = smem + (size_t)p.stages * p.stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(tail + 256);  // [2][256]
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; i++) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+    for (int s = 0; s < p.stages; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int total_kb = p.ntaps * p.kblocks_per_tap;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int img = m_tile / (p.tiles_w * p.tiles_h);
+        const int h0 = th * p.tile_h, w0 = tw * p.tile_w, n0 = n_tile * p.block_n;
+        for (int t = 0; t < p.ntaps; t++) {
+          const CUtensorMap* ma = &maps.a[p.tap_src[t]];
+          const int hh = h0 + p.tap_dh[t], ww = w0 + p.tap_dw[t];
+          const int wrow = p.tap_widx[t] * p.cout + n0;
+          for (int cb = 0; cb < p.kblocks_per_tap; cb++) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes);
+            tma_load_4d(sa, ma, &full_bar[stage], cb * kKBlock, ww, hh, img);
+            tma_load_2d(sa + kABytes, &maps.b, &full_bar[stage], cb * kKBlock, wrow);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc(kTileM, p.block_n, p.dtype, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
+      for (int kb = 0; kb < total_kb; kb++) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < kKBlock / 16; k++) {
+            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == total_kb - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const int et = threadIdx.x - 64;  // 0..127
+    const int ty = row / p.tile_w, tx = row % p.tile_w;
+    const int bf = p.dtype;
+    float alpha = p.alpha;
+    if (p.alpha_dev) alpha *= __ldg(p.alpha_dev);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int tw = m_tile % p.tiles_w;
+      const int th = (m_tile / p.tiles_w) % p.tiles_h;
+      const int img = m_tile / (p.tiles_w * p.tiles_h);
+      const int h = th * p.tile_h + ty, w = tw * p.tile_w + tx, n0 = n_tile * p.block_n;
+      const bool valid = (h < p.h) && (w < p.w);
+      const long long pix = ((long long)img * p.h + h) * p.w + w;
+
+      float* bs = bias_s + acc * 256;
+      for (int i = et; i < p.block_n; i += 128) bs[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccStride);
+
+      for (int ch = 0; ch < p.block_n / 32; ch++) {
+        uint32_t v[32];
+        tmem_ld32(taddr + ch * 32, v);
+        tmem_ld_wait();
+        if (ch == p.block_n / 32 - 1) {
+          // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+        if (!valid) continue;
+        const int q0 = n0 + ch * 32;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) f[j] = alpha * (__uint_as_float(v[j]) + bs[ch * 32 + j]);
+        if (p.res32) {
+          const float4* r = reinterpret_cast<const float4*>(p.res32 + pix * p.ld_res32 + q0);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            float4 t = r[j];
+            f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+          }
+        }
+        if (p.res16) {
+          const uint4* r = reinterpret_cast<const uint4*>(p.res16 + pix * p.ld_res16 + q0);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            uint4 t = r[j];
+            float2 a = unpack2(t.x, bf), b = unpack2(t.y, bf), c = unpack2(t.z, bf), d = unpack2(t.w, bf);
+            f[8 * j] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
+            f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
+          }
+        }
+        if (p.act == PESR_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) f[j] = fmaxf(f[j], 0.f);
+        } else if (p.act == PESR_ACT_LRELU) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) f[j] = f[j] > 0.f ? f[j] : 0.2f * f[j];
+        }
+        if (p.mask16) {
+          const uint4* r = reinterpret_cast<const uint4*>(p.mask16 + pix * p.ld_mask16 + q0);
+          const float neg = p.mask_mode == 2 ? 0.2f : 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            uint4 t = r[j];
+            float2 a = unpack2(t.x, bf), b = unpack2(t.y, bf), c = unpack2(t.z, bf), d = unpack2(t.w, bf);
+            f[8 * j] *= a.x > 0.f ? 1.f : neg; f[8 * j + 1] *= a.y > 0.f ? 1.f : neg;
+            f[8 * j + 2] *= b.x > 0.f ? 1.f : neg; f[8 * j + 3] *= b.y > 0.f ? 1.f : neg;
+            f[8 * j + 4] *= c.x > 0.f ? 1.f : neg; f[8 * j + 5] *= c.y > 0.f ? 1.f : neg;
+            f[8 * j + 6] *= d.x > 0.f ? 1.f : neg; f[8 * j + 7] *= d.y > 0.f ? 1.f : neg;
+          }
+        }
+        if (p.out32) {
+          float4* o = reinterpret_cast<float4*>(p.out32 + pix * p.ld_out32 + q0);
+#pragma unroll
+          for (int j = 0; j < 8; j++) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+        if (p.out16) {
+          long long off;
+          if (p.out_mode == PESR_OUT_SHUFFLE2) {
+            const int ij = q0 / p.ps_c, c0 = q0 % p.ps_c;
+            const long long op = ((long long)img * (2 * p.h) + (2 * h + (ij >> 1))) * (2 * p.w) + (2 * w + (ij & 1));
+            off = op * p.ld_out16 + p.out_coff + c0;
+          } else if (p.out_mode == PESR_OUT_UNSHUFFLE2) {
+            const long long op = ((long long)img * (p.h >> 1) + (h >> 1)) * (p.w >> 1) + (w >> 1);
+            off = op * p.ld_out16 + p.out_coff + ((h & 1) * 2 + (w & 1)) * p.cout + q0;
+          } else {
+            const long long op =
+                ((long long)img * p.out_h + (h * p.out_sy + p.out_oy)) * p.out_w + (w * p.out_sx + p.out_ox);
+            off = op * p.ld_out16 + p.out_coff + q0;
+          }
+          uint4* o = reinterpret_cast<uint4*>(p.out16 + off);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            uint4 t;
+            t.x = pack2(f[8 * j], f[8 * j + 1], bf);
+            t.y = pack2(f[8 * j + 2], f[8 * j + 3], bf);
+            t.z = pack2(f[8 * j + 4], f[8 * j + 5], bf);
+            t.w = pack2(f[8 * j + 6], f[8 * j + 7], bf);
+            o[j] = t;
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace pesr
+
+using namespace pesr;
+
+extern "C" int pesr_conv_igemm(const pesr_conv_desc* d, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(d != nullptr, "conv_igemm: null descriptor");
+  PESR_CHECK_ARG(d->dtype == PESR_DT_F16 || d->dtype == PESR_DT_BF16, "conv_igemm: bad dtype %d", d->dtype);
+  PESR_CHECK_ARG(d->nb > 0 && d->h > 0 && d->w > 0, "conv_igemm: empty pixel grid %dx%dx%d", d->nb, d->h, d->w);
+  PESR_CHECK_ARG(d->cin > 0 && d->cin % kKBlock == 0, "conv_igemm: cin %d must be a multiple of 64", d->cin);
+  PESR_CHECK_ARG(d->block_n == 32 || d->block_n == 64 || d->block_n == 128 || d->block_n == 256,
+                 "conv_igemm: block_n %d not in {32,64,128,256}", d->block_n);
+  PESR_CHECK_ARG(d->cout > 0 && d->cout % d->block_n == 0, "conv_igemm: cout %d not a multiple of block_n %d",
+                 d->cout, d->block_n);
+  PESR_CHECK_ARG(d->tile_h > 0 && d->tile_w > 0 && d->tile_h * d->tile_w == kTileM,
+                 "conv_igemm: tile %dx%d must cover 128 pixels", d->tile_h, d->tile_w);
+  PESR_CHECK_ARG(d->tile_w <= 256 && d->tile_h <= 256, "conv_igemm: tile too large for a TMA box");
+  PESR_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= PESR_MAX_TAPS, "conv_igemm: ntaps %d", d->ntaps);
+  PESR_CHECK_ARG(d->nsrc >= 1 && d->nsrc <= PESR_MAX_SRC, "conv_igemm: nsrc %d", d->nsrc);
+  PESR_CHECK_ARG(d->wpacked != nullptr && d->w_rows > 0, "conv_igemm: missing packed weights");
+  PESR_CHECK_ARG(d->out16 != nullptr || d->out32 != nullptr, "conv_igemm: no output");
+  for (int t = 0; t < d->ntaps; t++) {
+    PESR_CHECK_ARG(d->tap_src[t] >= 0 && d->tap_src[t] < d->nsrc, "conv_igemm: tap %d reads source %d", t,
+                   d->tap_src[t]);
+    PESR_CHECK_ARG((d->tap_widx[t] + 1) * d->cout <= d->w_rows, "conv_igemm: tap %d weight rows out of range", t);
+  }
+  if (d->out_mode == PESR_OUT_SHUFFLE2)
+    PESR_CHECK_ARG(d->ps_c > 0 && d->ps_c % 32 == 0 && d->cout == 4 * d->ps_c, "conv_igemm: bad ps_c %d", d->ps_c);
+  if (d->out_mode == PESR_OUT_UNSHUFFLE2)
+    PESR_CHECK_ARG(d->h % 2 == 0 && d->w % 2 == 0, "conv_igemm: unshuffle needs even h, w");
+
+  ConvMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int s = 0; s < PESR_MAX_SRC; s++) {
+    const int ss = s < d->nsrc ? s : 0;  // unused slots alias source 0 so every descriptor is valid
+    PESR_CHECK_ARG(d->src[ss] != nullptr, "conv_igemm: source %d is null", ss);
+    uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->src_w[ss], (uint64_t)d->src_h[ss], (uint64_t)d->nb};
+    uint64_t str[3] = {(uint64_t)d->src_sw[ss] * 2, (uint64_t)d->src_sh[ss] * 2, (uint64_t)d->src_sn[ss] * 2};
+    uint32_t box[4] = {(uint32_t)kKBlock, (uint32_t)d->tile_w, (uint32_t)d->tile_h, 1};
+    int r = get_tensor_map(&maps.a[s], d->src[ss], d->dtype, 4, dims, str, box);
+    if (r) return r;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)d->cin, (uint64_t)d->w_rows};
+    uint64_t str[1] = {(uint64_t)d->cin * 2};
+    uint32_t box[2] = {(uint32_t)kKBlock, (uint32_t)d->block_n};
+    int r = get_tensor_map(&maps.b, d->wpacked, d->dtype, 2, dims, str, box);
+    if (r) return r;
+  }
+
+  ConvK k;
+  memset(&k, 0, sizeof(k));
+  k.dtype = d->dtype;
+  k.nb = d->nb; k.h = d->h; k.w = d->w; k.cin = d->cin; k.cout = d->cout; k.block_n = d->block_n;
+  k.tile_h = d->tile_h; k.tile_w = d->tile_w; k.ntaps = d->ntaps;
+  k.tiles_h = (d->h + d->tile_h - 1) / d->tile_h;
+  k.tiles_w = (d->w + d->tile_w - 1) / d->tile_w;
+  k.n_tiles = d->cout / d->block_n;
+  k.num_tiles = d->nb * k.tiles_h * k.tiles_w * k.n_tiles;
+  k.kblocks_per_tap = d->cin / kKBlock;
+  k.stage_bytes = kABytes + d->block_n * kKBlock * 2;
+  const int smem_budget = 227 * 1024 - 4096;
+  k.stages = smem_budget / k.stage_bytes;
+  if (k.stages > kMaxStages) k.stages = kMaxStages;
+  for (int t = 0; t < PESR_MAX_TAPS; t++) {
+    k.tap_dh[t] = d->tap_dh[t]; k.tap_dw[t] = d->tap_dw[t]; k.tap_src[t] = d->tap_src[t]; k.tap_widx[t] = d->tap_widx[t];
+  }
+  k.bias = d->bias; k.alpha = d->alpha; k.alpha_dev = d->alpha_dev;
+  k.res32 = d->res32; k.ld_res32 = d->ld_res32;
+  k.res16 = reinterpret_cast<const uint16_t*>(d->res16); k.ld_res16 = d->ld_res16;
+  k.act = d->act;
+  k.mask16 = reinterpret_cast<const uint16_t*>(d->mask16); k.ld_mask16 = d->ld_mask16; k.mask_mode = d->mask_mode;
+  k.out32 = d->out32; k.ld_out32 = d->ld_out32;
+  k.out16 = reinterpret_cast<uint16_t*>(d->out16); k.ld_out16 = d->ld_out16;
+  k.out_mode = d->out_mode;
+  k.out_h = d->out_h > 0 ? d->out_h : d->h;
+  k.out_w = d->out_w > 0 ? d->out_w : d->w;
+  k.out_sy = d->out_sy > 0 ? d->out_sy : 1;
+  k.out_sx = d->out_sx > 0 ? d->out_sx : 1;
+  k.out_oy = d->out_oy; k.out_ox = d->out_ox; k.out_coff = d->out_coff; k.ps_c = d->ps_c;
+
+  // >= 120 KB of dynamic smem also guarantees one CTA per SM, so the 512-column TMEM allocation never contends.
+  size_t smem = (size_t)k.stages * k.stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + 2 * 256 * sizeof(float);
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("conv_igemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  int grid = k.num_tiles < num_sms() ? k.num_tiles : num_sms();
+  conv_igemm_kernel<<<grid, kNumThreads, smem, stream>>>(maps, k);
+  count_launch();
+  PESR_CHECK_LAUNCH("conv_igemm");
+  return 0;
+}

@@ -1,0 +1,385 @@
+// Backward-filter (wgrad) for sm_100a as a split-K tcgen05 GEMM whose K dimension is the pixel index
+// (reference: nn.Conv2d backward-filter via cuDNN, model/basic.py:4-7).
+//
+//   part[split][tap][m][n] = sum_{p in split}  A[p][m] * B[p (+) tap][n]
+//
+// A = dy (NHWC, M = output channels), B = x (NHWC, N = input channels) shifted by the tap with TMA
+// zero fill.  Both operands are "MN-major" for the tensor core: a TMA box of 64 channels x 64 pixels
+// lands in smem as 64 rows (one per pixel = K index) of 128 swizzled bytes (64 channels = MN index),
+// which is exactly the canonical SWIZZLE_128B MN-major layout; no transpose copy is ever made.
+// The fp32 partial sums of each split are written to a workspace; pesr_wgrad_reduce sums them and
+// scatters into the reference's OIHW gradient layout.
+#include "common.cuh"
+#include "host_util.cuh"
+
+namespace pesr {
+
+static constexpr int kWgKBlock = 64;               // pixels per pipeline stage
+static constexpr int kWgBoxBytes = kWgKBlock * 128;  // one 64-channel x 64-pixel box = 8 KB
+static constexpr int kWgThreads = 192;
+static constexpr int kWgMaxStages = 8;
+static constexpr int kWgAccStride = 256;
+
+struct WgMaps {
+  CUtensorMap a;
+  CUtensorMap b[PESR_MAX_SRC];
+};
+
+struct WgK {
+  int dtype;
+  int nb, h, w, m_total, n_total, block_n, ntaps;
+  int tile_h, tile_w, tiles_h, tiles_w, patches;
+  int m_tiles, n_tiles, splits, num_items;
+  int stages, stage_bytes, a_boxes, b_boxes;
+  int lbo, sbo;  // MN-major descriptor strides (bytes)
+  int8_t tap_dh[PESR_MAX_TAPS], tap_dw[PESR_MAX_TAPS], tap_src[PESR_MAX_TAPS];
+  float* partials;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgK p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  uint8_t* tail = smem + (size_t)p.stages * p.stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + kWgMaxStages;
+  uint64_t* tmem_full = empty_bar + kWgMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&maps.a);
+    for (int i = 0; i < 4; i++) tma_prefetch_desc(&maps.b[i]);
+    for (int s = 0; s < p.stages; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // item -> (split, tap, m_tile, n_tile); split slowest so that concurrently running CTAs share pixels in L2
+  auto decode = [&](int item, int& split, int& tap, int& mt, int& nt) {
+    nt = item % p.n_tiles;
+    int r = item / p.n_tiles;
+    mt = r % p.m_tiles;
+    r /= p.m_tiles;
+    tap = r % p.ntaps;
+    split = r / p.ntaps;
+  };
+  auto patch_range = [&](int split, int& p0, int& p1) {
+    p0 = (int)(((long long)split * p.patches) / p.splits);
+    p1 = (int)(((long long)(split + 1) * p.patches) / p.splits);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        int split, tap, mt, nt, p0, p1;
+        decode(item, split, tap, mt, nt);
+        patch_range(split, p0, p1);
+        const CUtensorMap* mb = &maps.b[p.tap_src[tap]];
+        const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+        for (int pt = p0; pt < p1; pt++) {
+          const int tw = pt % p.tiles_w;
+          const int th = (pt / p.tiles_w) % p.tiles_h;
+          const int img = pt / (p.tiles_w * p.tiles_h);
+          const int h0 = th * p.tile_h, w0 = tw * p.tile_w;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+          uint8_t* sb = sa + p.a_boxes * kWgBoxBytes;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes);
+          for (int i = 0; i < p.a_boxes; i++)
+            tma_load_4d(sa + i * kWgBoxBytes, &maps.a, &full_bar[stage], mt * 128 + i * 64, w0, h0, img);
+          for (int i = 0; i < p.b_boxes; i++)
+            tma_load_4d(sb + i * kWgBoxBytes, mb, &full_bar[stage], nt * p.block_n + i * 64, w0 + dw, h0 + dh, img);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(128, p.block_n, p.dtype, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int split, tap, mt, nt, p0, p1;
+      decode(item, split, tap, mt, nt);
+      patch_range(split, p0, p1);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kWgAccStride);
+      for (int pt = p0; pt < p1; pt++) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint32_t b_addr = a_addr + p.a_boxes * kWgBoxBytes;
+#pragma unroll
+          for (int k = 0; k < kWgKBlock / 16; k++) {
+            const uint64_t da = make_smem_desc(a_addr + k * 2048, p.lbo, p.sbo);
+            const uint64_t db = make_smem_desc(b_addr + k * 2048, p.lbo, p.sbo);
+            umma_f16(d_tmem, da, db, idesc, (pt > p0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (pt == p1 - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      if (p1 > p0) {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int split, tap, mt, nt, p0, p1;
+      decode(item, split, tap, mt, nt);
+      patch_range(split, p0, p1);
+      const int m = mt * 128 + row;
+      float* dst = p.partials + (((long long)split * p.ntaps + tap) * p.m_total + m) * p.n_total + nt * p.block_n;
+      if (p1 <= p0) {  // empty split: its partial is all zeros
+        if (m < p.m_total)
+          for (int j = 0; j < p.block_n; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(0, 0, 0, 0);
+        continue;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kWgAccStride);
+      for (int ch = 0; ch < p.block_n / 32; ch++) {
+        uint32_t v[32];
+        tmem_ld32(taddr + ch * 32, v);
+        tmem_ld_wait();
+        if (ch == p.block_n / 32 - 1) {
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+        if (m < p.m_total) {
+          float4* o = reinterpret_cast<float4*>(dst + ch * 32);
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// split-K reduction + scatter into the fp32 OIHW gradient
+// ------------------------------------------------------------------------------------------
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int ntaps, int m_total, int n_total,
+                                    int map_mode, int co, int ci, float scale, const float* __restrict__ inv_scale_dev,
+                                    int accumulate, float* __restrict__ grad) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)co * ci;
+  if (idx >= total) return;
+  if (inv_scale_dev) scale /= __ldg(inv_scale_dev);
+  const long long tap_stride = (long long)m_total * n_total;
+  const long long split_stride = tap_stride * ntaps;
+  if (map_mode == PESR_WMAP_OIHW || map_mode == PESR_WMAP_OIHW_PS) {
+    // thread <-> (m, n): n fastest => coalesced partial reads
+    const int n = (int)(idx % ci), m = (int)(idx / ci);
+    int o = m;
+    if (map_mode == PESR_WMAP_OIHW_PS) {
+      const int c_ps = co / 4;
+      o = (m % c_ps) * 4 + (m / c_ps);
+    }
+    float* g = grad + ((long long)o * ci + n) * ntaps;
+    for (int t = 0; t < ntaps; t++) {
+      float s = 0.f;
+      const float* src = part + t * tap_stride + (long long)m * n_total + n;
+      for (int k = 0; k < splits; k++) s += src[k * split_stride];
+      s *= scale;
+      g[t] = accumulate ? g[t] + s : s;
+    }
+  } else if (map_mode == PESR_WMAP_COL_IN) {
+    // partial [m = o][n = tap*ci + i], 9 taps folded into n
+    const int i = (int)(idx % ci), o = (int)(idx / ci);
+    float* g = grad + ((long long)o * ci + i) * 9;
+    for (int t = 0; t < 9; t++) {
+      float s = 0.f;
+      const float* src = part + (long long)o * n_total + (t * ci + i);
+      for (int k = 0; k < splits; k++) s += src[k * split_stride];
+      s *= scale;
+      g[t] = accumulate ? g[t] + s : s;
+    }
+  } else {
+    // PESR_WMAP_COL_OUT: partial [m = i][n = tap*co + o]
+    const int i = (int)(idx % ci), o = (int)(idx / ci);
+    float* g = grad + ((long long)o * ci + i) * 9;
+    for (int t = 0; t < 9; t++) {
+      float s = 0.f;
+      const float* src = part + (long long)i * n_total + (t * co + o);
+      for (int k = 0; k < splits; k++) s += src[k * split_stride];
+      s *= scale;
+      g[t] = accumulate ? g[t] + s : s;
+    }
+  }
+}
+
+static int g_dbg_lbo = 0, g_dbg_sbo = 0;
+
+}  // namespace pesr
+
+using namespace pesr;
+
+// Debug hook used by the bring-up tests only: override the MN-major descriptor strides (0 = default).
+extern "C" void pesr_debug_wgrad_desc(int lbo_bytes, int sbo_bytes) {
+  g_dbg_lbo = lbo_bytes;
+  g_dbg_sbo = sbo_bytes;
+}
+
+extern "C" int pesr_conv_wgrad(const pesr_wgrad_desc* d, int32_t* splits_out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(d != nullptr, "conv_wgrad: null descriptor");
+  PESR_CHECK_ARG(d->dtype == PESR_DT_F16 || d->dtype == PESR_DT_BF16, "conv_wgrad: bad dtype %d", d->dtype);
+  PESR_CHECK_ARG(d->nb > 0 && d->h > 0 && d->w > 0, "conv_wgrad: empty pixel grid");
+  PESR_CHECK_ARG(d->block_m == 128, "conv_wgrad: block_m must be 128 (got %d)", d->block_m);
+  PESR_CHECK_ARG(d->block_n == 64 || d->block_n == 128 || d->block_n == 256, "conv_wgrad: block_n %d", d->block_n);
+  PESR_CHECK_ARG(d->m_total > 0 && d->n_total > 0 && d->n_total % d->block_n == 0,
+                 "conv_wgrad: n_total %d not a multiple of block_n %d", d->n_total, d->block_n);
+  PESR_CHECK_ARG(d->m_total % 64 == 0, "conv_wgrad: m_total %d must be a multiple of 64", d->m_total);
+  PESR_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= PESR_MAX_TAPS, "conv_wgrad: ntaps %d", d->ntaps);
+  PESR_CHECK_ARG(d->nsrc >= 1 && d->nsrc <= PESR_MAX_SRC, "conv_wgrad: nsrc %d", d->nsrc);
+  PESR_CHECK_ARG(d->a != nullptr && d->partials != nullptr, "conv_wgrad: null operand");
+  PESR_CHECK_ARG(d->a_c % 8 == 0, "conv_wgrad: a_c %d must be a multiple of 8", d->a_c);
+
+  WgK k;
+  memset(&k, 0, sizeof(k));
+  k.dtype = d->dtype;
+  k.nb = d->nb; k.h = d->h; k.w = d->w; k.m_total = d->m_total; k.n_total = d->n_total;
+  k.block_n = d->block_n; k.ntaps = d->ntaps;
+  // 64-pixel patches: wide images use 4x16, narrow ones 8x8
+  if (d->w % 16 == 0 || d->w > 24) { k.tile_h = 4; k.tile_w = 16; } else { k.tile_h = 8; k.tile_w = 8; }
+  k.tiles_h = (d->h + k.tile_h - 1) / k.tile_h;
+  k.tiles_w = (d->w + k.tile_w - 1) / k.tile_w;
+  k.patches = d->nb * k.tiles_h * k.tiles_w;
+  k.m_tiles = (d->m_total + 127) / 128;
+  k.n_tiles = d->n_total / d->block_n;
+  const int base_items = d->ntaps * k.m_tiles * k.n_tiles;
+  int splits = d->splits;
+  if (splits <= 0) {
+    splits = num_sms() / base_items;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > k.patches) splits = k.patches;
+  const long long need = (long long)splits * d->ntaps * d->m_total * d->n_total;
+  if (need > d->partials_elems) {
+    // shrink to what the workspace can hold
+    long long per = (long long)d->ntaps * d->m_total * d->n_total;
+    splits = (int)(d->partials_elems / per);
+    if (splits < 1) {
+      set_error("conv_wgrad: workspace holds %lld floats, one split needs %lld", (long long)d->partials_elems, per);
+      return PESR_E_WORKSPACE;
+    }
+  }
+  k.splits = splits;
+  k.num_items = base_items * splits;
+  k.a_boxes = 2;
+  k.b_boxes = d->block_n / 64;
+  k.stage_bytes = (k.a_boxes + k.b_boxes) * kWgBoxBytes;
+  k.stages = (227 * 1024 - 4096) / k.stage_bytes;
+  if (k.stages > kWgMaxStages) k.stages = kWgMaxStages;
+  k.lbo = g_dbg_lbo ? g_dbg_lbo : kWgBoxBytes;
+  k.sbo = g_dbg_sbo ? g_dbg_sbo : 1024;
+  for (int t = 0; t < PESR_MAX_TAPS; t++) {
+    k.tap_dh[t] = d->tap_dh[t]; k.tap_dw[t] = d->tap_dw[t]; k.tap_src[t] = d->tap_src[t];
+  }
+  for (int t = 0; t < d->ntaps; t++)
+    PESR_CHECK_ARG(d->tap_src[t] >= 0 && d->tap_src[t] < d->nsrc, "conv_wgrad: tap %d reads source %d", t, d->tap_src[t]);
+  k.partials = d->partials;
+
+  WgMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  {
+    uint64_t dims[4] = {(uint64_t)d->m_total, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nb};
+    uint64_t str[3] = {(uint64_t)d->a_c * 2, (uint64_t)d->w * d->a_c * 2, (uint64_t)d->h * d->w * d->a_c * 2};
+    uint32_t box[4] = {64, (uint32_t)k.tile_w, (uint32_t)k.tile_h, 1};
+    int r = get_tensor_map(&maps.a, d->a, d->dtype, 4, dims, str, box);
+    if (r) return r;
+  }
+  for (int s = 0; s < PESR_MAX_SRC; s++) {
+    const int ss = s < d->nsrc ? s : 0;
+    PESR_CHECK_ARG(d->b[ss] != nullptr, "conv_wgrad: b source %d is null", ss);
+    uint64_t dims[4] = {(uint64_t)d->n_total, (uint64_t)d->b_w[ss], (uint64_t)d->b_h[ss], (uint64_t)d->nb};
+    uint64_t str[3] = {(uint64_t)d->b_sw[ss] * 2, (uint64_t)d->b_sh[ss] * 2, (uint64_t)d->b_sn[ss] * 2};
+    uint32_t box[4] = {64, (uint32_t)k.tile_w, (uint32_t)k.tile_h, 1};
+    int r = get_tensor_map(&maps.b[s], d->b[ss], d->dtype, 4, dims, str, box);
+    if (r) return r;
+  }
+
+  size_t smem = (size_t)k.stages * k.stage_bytes + 1024 + 256;
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("conv_wgrad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  int grid = k.num_items < num_sms() ? k.num_items : num_sms();
+  conv_wgrad_kernel<<<grid, kWgThreads, smem, stream>>>(maps, k);
+  count_launch();
+  PESR_CHECK_LAUNCH("conv_wgrad");
+  if (splits_out) *splits_out = splits;
+  return 0;
+}
+
+extern "C" int pesr_wgrad_reduce(const float* partials, int32_t splits, int32_t ntaps, int32_t m_total,
+                                 int32_t n_total, int32_t map_mode, int32_t co, int32_t ci, float scale,
+                                 const float* inv_scale_dev, int32_t accumulate, float* grad_oihw, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(partials && grad_oihw, "wgrad_reduce: null pointer");
+  PESR_CHECK_ARG(splits >= 1 && ntaps >= 1, "wgrad_reduce: bad splits/ntaps");
+  PESR_CHECK_ARG(map_mode >= 0 && map_mode <= 3, "wgrad_reduce: bad map_mode %d", map_mode);
+  if (map_mode == PESR_WMAP_OIHW || map_mode == PESR_WMAP_OIHW_PS)
+    PESR_CHECK_ARG(co <= m_total && ci <= n_total, "wgrad_reduce: %dx%d does not fit partial %dx%d", co, ci, m_total,
+                   n_total);
+  if (map_mode == PESR_WMAP_COL_IN)
+    PESR_CHECK_ARG(co <= m_total && 9 * ci <= n_total && ntaps == 1, "wgrad_reduce: COL_IN shape mismatch");
+  if (map_mode == PESR_WMAP_COL_OUT)
+    PESR_CHECK_ARG(ci <= m_total && 9 * co <= n_total && ntaps == 1, "wgrad_reduce: COL_OUT shape mismatch");
+  const long long total = (long long)co * ci;
+  const int threads = 256;
+  const int blocks = (int)((total + threads - 1) / threads);
+  wgrad_reduce_kernel<<<blocks, threads, 0, stream>>>(partials, splits, ntaps, m_total, n_total, map_mode, co, ci,
+                                                     scale, inv_scale_dev, accumulate, grad_oihw);
+  count_launch();
+  PESR_CHECK_LAUNCH("wgrad_reduce");
+  return 0;
+}

@@ -1,0 +1,130 @@
+// Error reporting, launch counter, device query and the TMA tensor-map cache.
+#include "host_util.cuh"
+
+#include <stdarg.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace pesr {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
+  }
+  return cached[dev];
+}
+
+// ------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver symbol; resolve it through the runtime so the library
+// links without libcuda (this container has no GPU driver; the GPU box does).
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  uint64_t v[14];
+  bool operator<(const MapKey& o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
+};
+
+int get_tensor_map(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box) {
+  static std::mutex mu;
+  static std::map<MapKey, CUtensorMap> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  MapKey k;
+  memset(&k, 0, sizeof(k));
+  k.v[0] = (uint64_t)(uintptr_t)base;
+  k.v[1] = ((uint64_t)dtype << 8) | (uint64_t)rank | ((uint64_t)dev << 16);
+  for (int i = 0; i < rank; i++) k.v[2 + i] = dims[i];
+  for (int i = 0; i < rank - 1; i++) k.v[6 + i] = strides_bytes[i];
+  for (int i = 0; i < rank; i++) k.v[10 + i] = box[i];
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(k);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled could not be resolved (no CUDA driver?)");
+    return PESR_E_DRIVER;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; i++) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; i++) gstr[i] = strides_bytes[i];
+  CUtensorMap m;
+  CUresult r = fn(&m, dtype == PESR_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                  (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): base %p rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]",
+              (int)r, base, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+              rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return PESR_E_DRIVER;
+  }
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 65536) cache.clear();
+    cache[k] = m;
+  }
+  *out = m;
+  return 0;
+}
+
+}  // namespace pesr
+
+extern "C" const char* pesr_last_error(void) { return pesr::g_err; }
+extern "C" int pesr_version(void) { return 100; }
+extern "C" long long pesr_launch_count(int reset) {
+  long long v = pesr::g_launches.load();
+  if (reset) pesr::g_launches.store(0);
+  return v;
+}
+extern "C" int pesr_sizeof(int which) {
+  return which == 0 ? (int)sizeof(pesr_conv_desc) : which == 1 ? (int)sizeof(pesr_wgrad_desc) : -1;
+}

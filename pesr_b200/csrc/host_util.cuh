@@ -1,0 +1,40 @@
+// Host-side helpers shared by the launchers: error reporting, launch counting, TMA tensor-map cache.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/pesr_b200.h"
+
+namespace pesr {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int num_sms();
+
+// Encodes (or fetches from the cache) a tiled, 128B-swizzled tensor map over a 16-bit tensor.
+// dims/strides are innermost-first; strides_bytes has rank-1 entries (dims 1..rank-1).
+// Returns 0 or a PESR_E_* code.
+int get_tensor_map(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box);
+
+#define PESR_CHECK_ARG(cond, ...)      \
+  do {                                 \
+    if (!(cond)) {                     \
+      pesr::set_error(__VA_ARGS__);    \
+      return PESR_E_ARG;               \
+    }                                  \
+  } while (0)
+
+#define PESR_CHECK_LAUNCH(name)                                                 \
+  do {                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                       \
+    if (e__ != cudaSuccess) {                                                   \
+      pesr::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return (int)e__;                                                          \
+    }                                                                           \
+  } while (0)
+
+}  // namespace pesr

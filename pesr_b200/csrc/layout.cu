@@ -1,0 +1,430 @@
+// HBM-bound layout / edge kernels: weight packing, im2col / col2im for the 3-channel convolutions
+// (with the MeanShift affine of model/basic.py:9-17 fused), NCHW<->NHWC conversion, column sums
+// (bias gradients), the dynamic gradient scale and the MeanShift parameter gradients.
+#include "common.cuh"
+#include "host_util.cuh"
+
+namespace pesr {
+
+static inline int blocks_for(long long n, int threads, int cap = 148 * 16) {
+  long long b = (n + threads - 1) / threads;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing
+// ------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ w, int co, int ci, int taps, int mode, int pad_to,
+                                    int bf, uint16_t* __restrict__ out, long long total, int rows, int kdim) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % kdim);
+    const int r = (int)(idx / kdim);
+    float v = 0.f;
+    const int c_ps = co / 4;
+    switch (mode) {
+      case 0: {  // out[tap][o][i]
+        const int tap = r / co, o = r % co;
+        v = w[((long long)o * ci + k) * taps + tap];
+      } break;
+      case 1: {  // out[tap][i][o] = w[o][i][tapf]
+        const int tap = r / ci, i = r % ci;
+        v = w[((long long)k * ci + i) * taps + (taps - 1 - tap)];
+      } break;
+      case 2: {  // out[tap][o'][i], o' = ij*C + c <- o = c*4 + ij
+        const int tap = r / co, op = r % co;
+        const int o = (op % c_ps) * 4 + (op / c_ps);
+        v = w[((long long)o * ci + k) * taps + tap];
+      } break;
+      case 3: {  // out[tap][i][o'] = w[o][i][tapf]
+        const int tap = r / ci, i = r % ci;
+        const int o = (k % c_ps) * 4 + (k / c_ps);
+        v = w[((long long)o * ci + i) * taps + (taps - 1 - tap)];
+      } break;
+      case 4: {  // out[o][tap*ci + i], K padded
+        if (k < taps * ci) {
+          const int tap = k / ci, i = k % ci;
+          v = w[((long long)r * ci + i) * taps + tap];
+        }
+      } break;
+      case 5: {  // out[tap*co + o][i], rows padded
+        if (r < taps * co) {
+          const int tap = r / co, o = r % co;
+          v = w[((long long)o * ci + k) * taps + tap];
+        }
+      } break;
+      case 6: {  // out[tap*ci + i][o], rows padded
+        if (r < taps * ci) {
+          const int tap = r / ci, i = r % ci;
+          v = w[((long long)k * ci + i) * taps + tap];
+        }
+      } break;
+      case 7: {  // out[i][tap*co + o], K padded
+        if (k < taps * co) {
+          const int tap = k / co, o = k % co;
+          v = w[((long long)o * ci + r) * taps + tap];
+        }
+      } break;
+    }
+    out[idx] = from_f32(v, bf);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// im2col for 3-channel images: one thread per (pixel, 8-column chunk) -> one 16-byte store
+// ------------------------------------------------------------------------------------------
+__global__ void im2col3_kernel(const float* __restrict__ src, int nb, int h, int w, const float* __restrict__ aff_a,
+                               const float* __restrict__ aff_b, const float* __restrict__ mul_dev, int sgn, int bf,
+                               uint4* __restrict__ col) {
+  const long long total = (long long)nb * h * w * 8;
+  float A[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  float B[3] = {0, 0, 0};
+  if (aff_a)
+    for (int i = 0; i < 9; i++) A[i] = __ldg(aff_a + i);
+  if (aff_b)
+    for (int i = 0; i < 3; i++) B[i] = __ldg(aff_b + i);
+  const float mul = mul_dev ? __ldg(mul_dev) : 1.f;
+  const long long plane = (long long)h * w;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int chunk = (int)(idx & 7);
+    const long long p = idx >> 3;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (chunk < 4) {
+      const int x = (int)(p % w);
+      const int y = (int)((p / w) % h);
+      const int n = (int)(p / plane);
+      const float* base = src + (long long)n * 3 * plane;
+      float vals[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int k = chunk * 8 + j;
+        float v = 0.f;
+        if (k < 27) {
+          const int tap = k / 3, c = k % 3;
+          const int yy = y + sgn * (tap / 3 - 1), xx = x + sgn * (tap % 3 - 1);
+          if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+            const long long off = (long long)yy * w + xx;
+            const float s0 = __ldg(base + off), s1 = __ldg(base + plane + off), s2 = __ldg(base + 2 * plane + off);
+            v = (A[c * 3] * s0 + A[c * 3 + 1] * s1 + A[c * 3 + 2] * s2 + B[c]) * mul;
+          }
+        }
+        vals[j] = v;
+      }
+      o.x = pack2(vals[0], vals[1], bf);
+      o.y = pack2(vals[2], vals[3], bf);
+      o.z = pack2(vals[4], vals[5], bf);
+      o.w = pack2(vals[6], vals[7], bf);
+    }
+    col[idx] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// col2im for 3-channel outputs: one thread per pixel, writes 3 NCHW planes
+// ------------------------------------------------------------------------------------------
+__global__ void col2im3_kernel(const float* __restrict__ z, int ldz, int nb, int h, int w,
+                               const float* __restrict__ bias, const float* __restrict__ aff_a,
+                               const float* __restrict__ aff_b, float mul, const float* __restrict__ div_dev, int sgn,
+                               float* __restrict__ pre, float* __restrict__ out) {
+  const long long total = (long long)nb * h * w;
+  const long long plane = (long long)h * w;
+  float A[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  float B[3] = {0, 0, 0};
+  if (aff_a)
+    for (int i = 0; i < 9; i++) A[i] = __ldg(aff_a + i);
+  if (aff_b)
+    for (int i = 0; i < 3; i++) B[i] = __ldg(aff_b + i);
+  if (div_dev) mul /= __ldg(div_dev);
+  float b0 = 0, b1 = 0, b2 = 0;
+  if (bias) { b0 = __ldg(bias); b1 = __ldg(bias + 1); b2 = __ldg(bias + 2); }
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(p % w);
+    const int y = (int)((p / w) % h);
+    const int n = (int)(p / plane);
+    float s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+    for (int tap = 0; tap < 9; tap++) {
+      const int yy = y + sgn * (tap / 3 - 1), xx = x + sgn * (tap % 3 - 1);
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+        const float* zp = z + (((long long)n * h + yy) * w + xx) * ldz + tap * 3;
+        s0 += __ldg(zp); s1 += __ldg(zp + 1); s2 += __ldg(zp + 2);
+      }
+    }
+    s0 = s0 * mul + b0; s1 = s1 * mul + b1; s2 = s2 * mul + b2;
+    const long long o = (long long)n * 3 * plane + (long long)y * w + x;
+    if (pre) { pre[o] = s0; pre[o + plane] = s1; pre[o + 2 * plane] = s2; }
+    out[o] = A[0] * s0 + A[1] * s1 + A[2] * s2 + B[0];
+    out[o + plane] = A[3] * s0 + A[4] * s1 + A[5] * s2 + B[1];
+    out[o + 2 * plane] = A[6] * s0 + A[7] * s1 + A[8] * s2 + B[2];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// NCHW fp32 <-> NHWC 16-bit through a 32x32 smem transpose (coalesced on both sides)
+// ------------------------------------------------------------------------------------------
+__global__ void nchw32_to_nhwc16_kernel(const float* __restrict__ src, int c, long long hw, int ldc,
+                                        const float* __restrict__ mul_dev, int bf, uint16_t* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const float mul = mul_dev ? __ldg(mul_dev) : 1.f;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int cc = c0 + i;
+    const long long pp = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (cc < c && pp < hw) ? src[((long long)n * c + cc) * hw + pp] * mul : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long pp = p0 + i;
+    const int cc = c0 + threadIdx.x;
+    if (pp < hw && cc < ldc) dst[((long long)n * hw + pp) * ldc + cc] = from_f32(cc < c ? tile[threadIdx.x][i] : 0.f, bf);
+  }
+}
+
+__global__ void nhwc16_to_nchw32_kernel(const uint16_t* __restrict__ src, int c, long long hw, int ldc, float mul,
+                                        const float* __restrict__ div_dev, int bf, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  if (div_dev) mul /= __ldg(div_dev);
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long pp = p0 + i;
+    const int cc = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (pp < hw && cc < c) ? to_f32(src[((long long)n * hw + pp) * ldc + cc], bf) * mul : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int cc = c0 + i;
+    const long long pp = p0 + threadIdx.x;
+    if (cc < c && pp < hw) dst[((long long)n * c + cc) * hw + pp] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// column sums of a 16-bit [npix][ldc] matrix (bias gradients)
+// block = 256 threads: 32 channel-pair lanes x 8 pixel rows; grid.y tiles the channels by 64
+// ------------------------------------------------------------------------------------------
+__global__ void colsum16_kernel(const uint16_t* __restrict__ x, long long npix, int c, int ldc, float mul,
+                                const float* __restrict__ div_dev, int bf, float* __restrict__ out) {
+  __shared__ float red[8][64];
+  const int lane = threadIdx.x & 31;
+  const int rowi = threadIdx.x >> 5;
+  const int c0 = blockIdx.y * 64 + lane * 2;
+  float s0 = 0.f, s1 = 0.f;
+  if (c0 < c) {
+    for (long long p = (long long)blockIdx.x * 8 + rowi; p < npix; p += (long long)gridDim.x * 8) {
+      const uint32_t u = *reinterpret_cast<const uint32_t*>(x + p * ldc + c0);
+      const float2 f = unpack2(u, bf);
+      s0 += f.x;
+      s1 += f.y;
+    }
+  }
+  red[rowi][lane * 2] = s0;
+  red[rowi][lane * 2 + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+    for (int i = 0; i < 8; i++) s += red[i][threadIdx.x];
+    const int cc = blockIdx.y * 64 + threadIdx.x;
+    if (div_dev) mul /= __ldg(div_dev);
+    if (cc < c) atomicAdd(out + cc, s * mul);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// dynamic gradient scale
+// ------------------------------------------------------------------------------------------
+__global__ void amax_kernel(const float* __restrict__ x, long long n, unsigned int* __restrict__ ws) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float sm[32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) atomicMax(ws, __float_as_uint(m));  // non-negative floats order like uints
+  }
+}
+__global__ void amax_finalize_kernel(float* ws, float target) {
+  const float m = __uint_as_float(*reinterpret_cast<unsigned int*>(ws));
+  float scale = 1.f;
+  if (m > 0.f && isfinite(m)) {
+    int e;
+    frexpf(m, &e);  // m = f * 2^e, f in [0.5, 1)
+    int et;
+    frexpf(target, &et);
+    scale = ldexpf(1.f, et - e);  // m*scale in [target/2.., target)
+  }
+  ws[1] = scale;
+  ws[2] = 1.f / scale;
+  *reinterpret_cast<unsigned int*>(ws) = 0u;  // re-arm for the next use
+}
+
+// ------------------------------------------------------------------------------------------
+// MeanShift parameter gradients: 9 cross moments + 3 sums
+// ------------------------------------------------------------------------------------------
+__global__ void moments3_kernel(const float* __restrict__ a, const float* __restrict__ b, int nb, long long hw,
+                                float* __restrict__ sums) {
+  float acc[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) acc[i] = 0.f;
+  const long long total = (long long)nb * hw;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long n = idx / hw, p = idx % hw;
+    const long long o = n * 3 * hw + p;
+    const float a0 = a[o], a1 = a[o + hw], a2 = a[o + 2 * hw];
+    const float b0 = b[o], b1 = b[o + hw], b2 = b[o + 2 * hw];
+    acc[0] += a0 * b0; acc[1] += a0 * b1; acc[2] += a0 * b2;
+    acc[3] += a1 * b0; acc[4] += a1 * b1; acc[5] += a1 * b2;
+    acc[6] += a2 * b0; acc[7] += a2 * b1; acc[8] += a2 * b2;
+    acc[9] += a0; acc[10] += a1; acc[11] += a2;
+  }
+  __shared__ float sm[12][8];
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    float v = acc[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[i][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    float v = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) v += sm[threadIdx.x][i];
+    atomicAdd(sums + threadIdx.x, v);
+  }
+}
+
+}  // namespace pesr
+
+using namespace pesr;
+
+extern "C" int pesr_pack_weights(const float* w, int32_t co, int32_t ci, int32_t ksize, int32_t mode, int32_t pad_to,
+                                 int32_t dtype, void* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(w && out, "pack_weights: null pointer");
+  PESR_CHECK_ARG(ksize == 3 || (ksize == 1 && (mode == 0 || mode == 1)), "pack_weights: ksize %d mode %d", ksize, mode);
+  PESR_CHECK_ARG(mode >= 0 && mode <= 7, "pack_weights: mode %d", mode);
+  const int taps = ksize * ksize;
+  int rows = 0, kdim = 0;
+  switch (mode) {
+    case 0: case 2: rows = taps * co; kdim = ci; break;
+    case 1: case 3: rows = taps * ci; kdim = co; break;
+    case 4: rows = co; kdim = pad_to; PESR_CHECK_ARG(pad_to >= taps * ci, "pack_weights: pad_to %d < %d", pad_to, taps * ci); break;
+    case 5: rows = pad_to; kdim = ci; PESR_CHECK_ARG(pad_to >= taps * co, "pack_weights: pad_to %d < %d", pad_to, taps * co); break;
+    case 6: rows = pad_to; kdim = co; PESR_CHECK_ARG(pad_to >= taps * ci, "pack_weights: pad_to %d < %d", pad_to, taps * ci); break;
+    case 7: rows = ci; kdim = pad_to; PESR_CHECK_ARG(pad_to >= taps * co, "pack_weights: pad_to %d < %d", pad_to, taps * co); break;
+  }
+  if (mode == 2 || mode == 3) PESR_CHECK_ARG(co % 4 == 0, "pack_weights: pixel-shuffle needs co %% 4 == 0");
+  const long long total = (long long)rows * kdim;
+  pack_weights_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(w, co, ci, taps, mode, pad_to, dtype,
+                                                                  reinterpret_cast<uint16_t*>(out), total, rows, kdim);
+  count_launch();
+  PESR_CHECK_LAUNCH("pack_weights");
+  return 0;
+}
+
+extern "C" int pesr_im2col3(const float* src, int32_t nb, int32_t h, int32_t w, const float* aff_a,
+                            const float* aff_b, const float* mul_dev, int32_t sgn, int32_t dtype, void* col,
+                            void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(src && col && nb > 0 && h > 0 && w > 0, "im2col3: bad arguments");
+  PESR_CHECK_ARG(sgn == 1 || sgn == -1, "im2col3: sgn must be +-1");
+  const long long total = (long long)nb * h * w * 8;
+  im2col3_kernel<<<blocks_for(total, 256, 148 * 32), 256, 0, stream>>>(src, nb, h, w, aff_a, aff_b, mul_dev, sgn, dtype,
+                                                                      reinterpret_cast<uint4*>(col));
+  count_launch();
+  PESR_CHECK_LAUNCH("im2col3");
+  return 0;
+}
+
+extern "C" int pesr_col2im3(const float* z, int32_t ldz, int32_t nb, int32_t h, int32_t w, const float* bias,
+                            const float* aff_a, const float* aff_b, float mul_host, const float* div_dev, int32_t sgn,
+                            float* pre, float* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(z && out && nb > 0 && h > 0 && w > 0 && ldz >= 27, "col2im3: bad arguments");
+  PESR_CHECK_ARG(sgn == 1 || sgn == -1, "col2im3: sgn must be +-1");
+  const long long total = (long long)nb * h * w;
+  col2im3_kernel<<<blocks_for(total, 256, 148 * 32), 256, 0, stream>>>(z, ldz, nb, h, w, bias, aff_a, aff_b, mul_host,
+                                                                      div_dev, sgn, pre, out);
+  count_launch();
+  PESR_CHECK_LAUNCH("col2im3");
+  return 0;
+}
+
+extern "C" int pesr_nchw32_to_nhwc16(const float* src, int32_t nb, int32_t c, int32_t h, int32_t w, int32_t ldc,
+                                     const float* mul_dev, int32_t dtype, void* dst, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(src && dst && nb > 0 && c > 0 && ldc >= c, "nchw32_to_nhwc16: bad arguments");
+  PESR_CHECK_ARG(nb <= 65535, "nchw32_to_nhwc16: nb too large");
+  const long long hw = (long long)h * w;
+  dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((ldc + 31) / 32), (unsigned)nb);
+  nchw32_to_nhwc16_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, c, hw, ldc, mul_dev, dtype,
+                                                           reinterpret_cast<uint16_t*>(dst));
+  count_launch();
+  PESR_CHECK_LAUNCH("nchw32_to_nhwc16");
+  return 0;
+}
+
+extern "C" int pesr_nhwc16_to_nchw32(const void* src, int32_t nb, int32_t c, int32_t h, int32_t w, int32_t ldc,
+                                     float mul_host, const float* div_dev, int32_t dtype, float* dst, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(src && dst && nb > 0 && c > 0 && ldc >= c, "nhwc16_to_nchw32: bad arguments");
+  PESR_CHECK_ARG(nb <= 65535, "nhwc16_to_nchw32: nb too large");
+  const long long hw = (long long)h * w;
+  dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)nb);
+  nhwc16_to_nchw32_kernel<<<grid, dim3(32, 8), 0, stream>>>(reinterpret_cast<const uint16_t*>(src), c, hw, ldc,
+                                                           mul_host, div_dev, dtype, dst);
+  count_launch();
+  PESR_CHECK_LAUNCH("nhwc16_to_nchw32");
+  return 0;
+}
+
+extern "C" int pesr_colsum16(const void* x, int64_t npix, int32_t c, int32_t ldc, float mul_host,
+                             const float* div_dev, int32_t accumulate, int32_t dtype, float* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(x && out && npix > 0 && c > 0 && c % 2 == 0 && ldc % 2 == 0, "colsum16: bad arguments");
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * c, stream);
+    if (e != cudaSuccess) { set_error("colsum16: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  long long bx = (npix + 8 * 64 - 1) / (8 * 64);
+  if (bx > 1024) bx = 1024;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)((c + 63) / 64));
+  colsum16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(x), npix, c, ldc, mul_host, div_dev,
+                                           dtype, out);
+  count_launch();
+  PESR_CHECK_LAUNCH("colsum16");
+  return 0;
+}
+
+extern "C" int pesr_amax_scale(const float* x, int64_t n, float target, float* ws3, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(x && ws3 && n > 0 && target > 0.f, "amax_scale: bad arguments");
+  amax_kernel<<<blocks_for(n, 256, 148 * 4), 256, 0, stream>>>(x, n, reinterpret_cast<unsigned int*>(ws3));
+  amax_finalize_kernel<<<1, 1, 0, stream>>>(ws3, target);
+  count_launch(2);
+  PESR_CHECK_LAUNCH("amax_scale");
+  return 0;
+}
+
+extern "C" int pesr_moments3(const float* a, const float* b, int32_t nb, int64_t hw, float* sums12, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(a && b && sums12 && nb > 0 && hw > 0, "moments3: bad arguments");
+  cudaError_t e = cudaMemsetAsync(sums12, 0, sizeof(float) * 12, stream);
+  if (e != cudaSuccess) { set_error("moments3: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+  moments3_kernel<<<blocks_for((long long)nb * hw, 256, 148 * 4), 256, 0, stream>>>(a, b, nb, hw, sums12);
+  count_launch();
+  PESR_CHECK_LAUNCH("moments3");
+  return 0;
+}

@@ -1,0 +1,210 @@
+"""Python-side wrappers over the C-ABI: one function per entry point, taking torch tensors.
+
+Torch is used here for device memory and streams only; all arithmetic happens inside
+``libpesr_b200.so``.  Tensors are passed as raw device pointers plus shapes, on torch's current stream.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, DT_BF16, DT_F16, OUT_NORMAL, OUT_SHUFFLE2, OUT_UNSHUFFLE2,
+                   WMAP_COL_IN, WMAP_COL_OUT, WMAP_OIHW, WMAP_OIHW_PS, ConvDesc, WgradDesc, check, lib)
+
+_DT = {torch.float16: DT_F16, torch.bfloat16: DT_BF16}
+
+
+def dt_code(dtype):
+    try:
+        return _DT[dtype]
+    except KeyError:
+        raise TypeError(f"pesr_b200: activations must be float16 or bfloat16, got {dtype}")
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.PesrError("pesr_b200 has no CPU path: tensors must live on a CUDA device")
+
+
+def pick_tile(h, w):
+    """128-pixel spatial tile (tile_h, tile_w) for an h x w pixel grid."""
+    if w % 16 == 0 or w > 24:
+        return 8, 16
+    return 16, 8
+
+
+TAPS_3X3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+
+
+def make_conv_desc(*, dtype, nb, h, w, cin, cout, block_n=None, taps=TAPS_3X3, tap_src=None, tap_widx=None,
+                   srcs, wpacked, bias=None, alpha=1.0, alpha_dev=None, res32=None, ld_res32=0, res16=None,
+                   ld_res16=0, act=ACT_NONE, mask16=None, ld_mask16=0, mask_mode=0, out32=None, ld_out32=0,
+                   out16=None, ld_out16=0, out_mode=OUT_NORMAL, out_h=0, out_w=0, out_sy=1, out_sx=1, out_oy=0,
+                   out_ox=0, out_coff=0, ps_c=0, tile=None):
+    """Build a ``pesr_conv_desc``.
+
+    ``srcs`` is a list of (tensor_or_ptr, src_h, src_w, stride_n, stride_h, stride_w) NHWC views (element
+    strides); the descriptor keeps raw pointers, the caller keeps the tensors alive.
+    """
+    d = ConvDesc()
+    d.dtype = dtype
+    d.nb, d.h, d.w, d.cin, d.cout = nb, h, w, cin, cout
+    d.block_n = block_n or min(cout, 256)
+    th, tw = tile or pick_tile(h, w)
+    d.tile_h, d.tile_w = th, tw
+    d.ntaps = len(taps)
+    for t, (dh, dw) in enumerate(taps):
+        d.tap_dh[t], d.tap_dw[t] = dh, dw
+        d.tap_src[t] = tap_src[t] if tap_src is not None else 0
+        d.tap_widx[t] = tap_widx[t] if tap_widx is not None else t
+    d.nsrc = len(srcs)
+    for i, (t, sh_, sw_, sn, sh, sw) in enumerate(srcs):
+        d.src[i] = t if isinstance(t, int) else t.data_ptr()
+        d.src_h[i], d.src_w[i] = sh_, sw_
+        d.src_sn[i], d.src_sh[i], d.src_sw[i] = sn, sh, sw
+    d.wpacked = _ptr(wpacked)
+    d.w_rows = wpacked.shape[0]
+    d.bias = _ptr(bias)
+    d.alpha = alpha
+    d.alpha_dev = _ptr(alpha_dev)
+    d.res32, d.ld_res32 = _ptr(res32), ld_res32
+    d.res16, d.ld_res16 = _ptr(res16), ld_res16
+    d.act = act
+    d.mask16, d.ld_mask16, d.mask_mode = _ptr(mask16), ld_mask16, mask_mode
+    d.out32, d.ld_out32 = _ptr(out32), ld_out32
+    d.out16, d.ld_out16 = _ptr(out16), ld_out16
+    d.out_mode, d.out_h, d.out_w = out_mode, out_h, out_w
+    d.out_sy, d.out_sx, d.out_oy, d.out_ox, d.out_coff, d.ps_c = out_sy, out_sx, out_oy, out_ox, out_coff, ps_c
+    return d
+
+
+def nhwc_src(t, nb, h, w, c):
+    """(tensor, h, w, sn, sh, sw) for a dense NHWC tensor of c channels per pixel."""
+    return (t, h, w, h * w * c, w * c, c)
+
+
+def conv_igemm(desc):
+    check(lib.pesr_conv_igemm(C.byref(desc), _stream()), "pesr_conv_igemm")
+
+
+def make_wgrad_desc(*, dtype, nb, h, w, a, a_c, m_total, b_srcs, n_total, block_n=None, taps=TAPS_3X3, tap_src=None,
+                    partials, splits=0):
+    d = WgradDesc()
+    d.dtype = dtype
+    d.nb, d.h, d.w = nb, h, w
+    d.m_total, d.n_total = m_total, n_total
+    d.block_m = 128
+    d.block_n = block_n or min(n_total, 256)
+    d.ntaps = len(taps)
+    for t, (dh, dw) in enumerate(taps):
+        d.tap_dh[t], d.tap_dw[t] = dh, dw
+        d.tap_src[t] = tap_src[t] if tap_src is not None else 0
+    d.a, d.a_c = _ptr(a), a_c
+    d.nsrc = len(b_srcs)
+    for i, (t, bh, bw, sn, sh, sw) in enumerate(b_srcs):
+        d.b[i] = t if isinstance(t, int) else t.data_ptr()
+        d.b_h[i], d.b_w[i] = bh, bw
+        d.b_sn[i], d.b_sh[i], d.b_sw[i] = sn, sh, sw
+    d.splits = splits
+    d.partials = _ptr(partials)
+    d.partials_elems = partials.numel()
+    return d
+
+
+def conv_wgrad(desc):
+    s = C.c_int32(0)
+    check(lib.pesr_conv_wgrad(C.byref(desc), C.byref(s), _stream()), "pesr_conv_wgrad")
+    return s.value
+
+
+def wgrad_reduce(partials, splits, ntaps, m_total, n_total, map_mode, co, ci, grad, scale=1.0, div_dev=None,
+                 accumulate=False):
+    check(lib.pesr_wgrad_reduce(_ptr(partials), splits, ntaps, m_total, n_total, map_mode, co, ci, scale,
+                                _ptr(div_dev), 1 if accumulate else 0, _ptr(grad), _stream()), "pesr_wgrad_reduce")
+
+
+def pack_weights(w, mode, out, pad_to=0):
+    """fp32 OIHW -> packed 16-bit GEMM operand (see include/pesr_b200.h for the modes)."""
+    _need_cuda(w, out)
+    co, ci, k = w.shape[0], w.shape[1], w.shape[2]
+    check(lib.pesr_pack_weights(_ptr(w), co, ci, k, mode, pad_to, dt_code(out.dtype), _ptr(out), _stream()),
+          "pesr_pack_weights")
+    return out
+
+
+def packed_shape(co, ci, ksize, mode, pad_to=0):
+    taps = ksize * ksize
+    if mode in (0, 2):
+        return (taps * co, ci)
+    if mode in (1, 3):
+        return (taps * ci, co)
+    if mode == 4:
+        return (co, pad_to)
+    if mode == 5:
+        return (pad_to, ci)
+    if mode == 6:
+        return (pad_to, co)
+    if mode == 7:
+        return (ci, pad_to)
+    raise ValueError(mode)
+
+
+def im2col3(src, col, affine_a=None, affine_b=None, mul_dev=None, sgn=1):
+    _need_cuda(src, col)
+    nb, c, h, w = src.shape
+    assert c == 3 and src.dtype == torch.float32 and src.is_contiguous()
+    check(lib.pesr_im2col3(_ptr(src), nb, h, w, _ptr(affine_a), _ptr(affine_b), _ptr(mul_dev), sgn,
+                           dt_code(col.dtype), _ptr(col), _stream()), "pesr_im2col3")
+    return col
+
+
+def col2im3(z, ldz, nb, h, w, out, bias=None, affine_a=None, affine_b=None, mul=1.0, div_dev=None, sgn=1, pre=None):
+    _need_cuda(z, out)
+    check(lib.pesr_col2im3(_ptr(z), ldz, nb, h, w, _ptr(bias), _ptr(affine_a), _ptr(affine_b), mul, _ptr(div_dev),
+                           sgn, _ptr(pre), _ptr(out), _stream()), "pesr_col2im3")
+    return out
+
+
+def nchw32_to_nhwc16(src, dst, ldc=None, mul_dev=None):
+    _need_cuda(src, dst)
+    nb, c, h, w = src.shape
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    check(lib.pesr_nchw32_to_nhwc16(_ptr(src), nb, c, h, w, ldc or c, _ptr(mul_dev), dt_code(dst.dtype), _ptr(dst),
+                                    _stream()), "pesr_nchw32_to_nhwc16")
+    return dst
+
+
+def nhwc16_to_nchw32(src, dst, ldc=None, mul=1.0, div_dev=None):
+    _need_cuda(src, dst)
+    nb, c, h, w = dst.shape
+    assert dst.dtype == torch.float32 and dst.is_contiguous()
+    check(lib.pesr_nhwc16_to_nchw32(_ptr(src), nb, c, h, w, ldc or c, mul, _ptr(div_dev), dt_code(src.dtype),
+                                    _ptr(dst), _stream()), "pesr_nhwc16_to_nchw32")
+    return dst
+
+
+def colsum16(x, npix, c, ldc, out, mul=1.0, div_dev=None, accumulate=False):
+    check(lib.pesr_colsum16(_ptr(x), npix, c, ldc, mul, _ptr(div_dev), 1 if accumulate else 0, dt_code(x.dtype),
+                            _ptr(out), _stream()), "pesr_colsum16")
+    return out
+
+
+def amax_scale(x, ws3, target=16.0):
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    check(lib.pesr_amax_scale(_ptr(x), x.numel(), target, _ptr(ws3), _stream()), "pesr_amax_scale")
+
+
+def moments3(a, b, sums12):
+    nb, c, h, w = a.shape
+    assert c == 3 and a.is_contiguous() and b.is_contiguous()
+    check(lib.pesr_moments3(_ptr(a), _ptr(b), nb, h * w, _ptr(sums12), _stream()), "pesr_moments3")
+    return sums12

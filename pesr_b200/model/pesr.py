@@ -1,0 +1,69 @@
+"""Generator and Discriminator with the reference's constructor, call and state_dict surface
+(model/pesr.py:3-81), executed by the sm_100a kernel schedules in pesr_b200.engine_g / engine_d."""
+import torch
+import torch.nn as nn
+
+from .basic import BasicBlock, Conv, MeanShift, ResBlock, Upsampler  # noqa: F401
+
+
+def _require_cuda(x, who):
+    if not x.is_cuda:
+        raise RuntimeError(f"pesr_b200.{who}: input is on {x.device}; the B200 path has no CPU fallback "
+                           "(use the oracle under oracle/ for CPU reference results)")
+
+
+class _GeneratorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, x, *params):
+        need = any(ctx.needs_input_grad)
+        sr, state = engine.forward(x, train=need)
+        ctx.engine, ctx.state = engine, state
+        return sr
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dsr):
+        eng = ctx.engine
+        grads, dlr = eng.backward(ctx.state, dsr, need_input_grad=ctx.needs_input_grad[1])
+        out = [None, dlr]
+        for i, p in enumerate(eng.param_list):
+            out.append(grads.get(p) if ctx.needs_input_grad[2 + i] else None)
+        return tuple(out)
+
+
+class Generator(nn.Module):
+    """EDSR-style x4 SR network (model/pesr.py:3-38): sub_mean, embed, `depth` ResBlocks + conv with a
+    global skip, Upsampler, add_mean.  ``opt`` keys: depth, num_channels, res_scale."""
+
+    def __init__(self, opt, dtype=torch.float16):
+        nn.Module.__init__(self)
+        self.n_resblock = opt['depth']
+        self.n_feats = opt['num_channels']
+        self.res_scale = opt['res_scale']
+        if self.n_feats % 64 != 0:
+            raise ValueError("pesr_b200.Generator: num_channels must be a multiple of 64 (tensor-core K block)")
+        rgb_mean = (0.4488, 0.4371, 0.4040)  # DIV2K800, model/pesr.py:13
+        rgb_std = (1.0, 1.0, 1.0)
+        act = nn.ReLU(True)
+        # construction order == the reference's, so a given torch seed yields the same initial weights
+        blocks = [ResBlock(self.n_feats, 3, act=act, res_scale=self.res_scale) for _ in range(self.n_resblock)]
+        blocks.append(Conv(self.n_feats, self.n_feats, 3))
+        self.sub_mean = MeanShift(255, rgb_mean, rgb_std)
+        self.embed = Conv(3, self.n_feats, 3)
+        self.body = nn.Sequential(*blocks)
+        self.upsample = Upsampler(self.n_feats)
+        self.add_mean = MeanShift(255, rgb_mean, rgb_std, 1)
+        self._compute_dtype = dtype
+        self._engine = None
+
+    def engine(self):
+        if self._engine is None:
+            from ..engine_g import GeneratorEngine
+            self._engine = GeneratorEngine(self, self._compute_dtype)
+            self._engine.param_list = list(self.parameters())
+        return self._engine
+
+    def forward(self, x):
+        _require_cuda(x, "Generator")
+        eng = self.engine()
+        return _GeneratorFn.apply(eng, x, *eng.param_list)

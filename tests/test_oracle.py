@@ -1,0 +1,165 @@
+"""CPU tests: the oracle (oracle/pesr_oracle.py) against the golden vectors produced by the unmodified
+reference (tests/golden/make_golden.py), and -- when /root/reference is mounted -- against the live
+reference modules."""
+import os
+import sys
+
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_l2
+from oracle import pesr_oracle as O
+
+REF = "/root/reference"
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def _checksum(sd):
+    return float(sum(v.double().abs().sum() for v in sd.values() if v.is_floating_point()))
+
+
+@pytest.mark.parametrize("name", ["gen_small.pt", "gen_full.pt"])
+def test_generator_matches_reference_golden(name):
+    gd = _load(name)
+    opt = gd["opt"]
+    sd = O.init_generator(opt, gd["seed"])
+    assert list(sd.keys()) == gd["keys"]                       # state_dict key order of model/pesr.py
+    assert {k: tuple(v.shape) for k, v in sd.items()} == gd["shapes"]
+    assert abs(_checksum(sd) - gd["weight_checksum"]) <= 1e-9 * gd["weight_checksum"]  # same init stream
+    g = torch.Generator().manual_seed(gd["seed"] + 1)
+    shape = gd["shape"]
+    lr = torch.rand(*shape, generator=g) * 255
+    hr = torch.rand(shape[0], 3, shape[2] * 4, shape[3] * 4, generator=g) * 255
+    loss, sr, grads = O.pretrain_step(sd, lr, hr, opt)
+    assert rel_l2(sr, gd["sr"]) < 1e-5
+    assert abs(float(loss) - float(gd["loss"])) < 1e-4 * float(gd["loss"])
+    for k, ref in gd["grads"].items():
+        assert rel_l2(grads[k], ref) < 2e-3, k   # fp32 summation-order noise only (8.7e-4 vs fp64)
+    for k, n in gd["grad_norms"].items():
+        assert abs(float(grads[k].norm()) - n) <= 2e-3 * n + 1e-12, k
+
+
+def test_discriminator_matches_reference_golden():
+    gd = _load("disc_p12.pt")
+    sd = O.init_discriminator(gd["opt"], gd["seed"])
+    assert sorted(sd.keys()) == sorted(gd["keys"])
+    assert {k: tuple(v.shape) for k, v in sd.items()} == gd["shapes"]
+    assert abs(_checksum(sd) - gd["weight_checksum"]) <= 1e-9 * gd["weight_checksum"]
+    g = torch.Generator().manual_seed(gd["seed"] + 1)
+    p = gd["opt"]["patch_size"] * 4
+    x = (torch.rand(gd["nb"], 3, p, p, generator=g) * 255).requires_grad_(True)
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+            for k, v in sd.items()}
+    stats = []
+    y = O.discriminator_forward(leaf, x, stats_out=stats)
+    assert rel_l2(y, gd["logits"]) < 1e-4
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(y, torch.ones_like(y))
+    assert abs(float(loss) - float(gd["loss"])) < 1e-5
+    names = [k for k in leaf if leaf[k].is_floating_point() and leaf[k].requires_grad]
+    all_grads = torch.autograd.grad(loss, [leaf[k] for k in names] + [x])
+    grads, dx = dict(zip(names, all_grads[:-1])), all_grads[-1]
+    assert rel_l2(dx, gd["dx"]) < 5e-3
+    for k, ref in gd["grads"].items():
+        assert rel_l2(grads[k], ref) < 5e-3, k
+    # BatchNorm running statistics after one train-mode forward (momentum 0.1, unbiased var), model/basic.py:29
+    for layer, key in ((0, "0"), (7, "7")):
+        mean, var, n = stats[layer]
+        assert rel_l2(0.1 * mean, gd[f"running_mean_{key}"]) < 1e-4
+        assert rel_l2(0.9 + 0.1 * var * n / (n - 1), gd[f"running_var_{key}"]) < 1e-4
+
+
+def test_vgg_matches_reference_golden():
+    gd = _load("vgg_64.pt")
+    sd = O.init_vgg(gd["seed"])
+    assert sorted(sd.keys()) == sorted(gd["keys"])
+    assert abs(_checksum(sd) - gd["weight_checksum"]) <= 1e-9 * gd["weight_checksum"]
+    g = torch.Generator().manual_seed(gd["seed"] + 1)
+    sr = (torch.rand(gd["nb"], 3, gd["side"], gd["side"], generator=g) * 255).requires_grad_(True)
+    hr = torch.rand(gd["nb"], 3, gd["side"], gd["side"], generator=g) * 255
+    f_sr, f_hr = O.vgg_forward(sd, sr, hr)
+    assert not f_hr.requires_grad and gd["hr_requires_grad"] is False
+    assert rel_l2(f_sr, gd["f_sr"]) < 1e-5 and rel_l2(f_hr, gd["f_hr"]) < 1e-5
+    loss = O.mse_loss(f_sr, f_hr)
+    assert abs(float(loss) - float(gd["loss"])) < 1e-4 * float(gd["loss"])
+    dsr, = torch.autograd.grad(loss, sr)
+    assert rel_l2(dsr, gd["dsr"]) < 1e-3
+
+
+def test_focal_loss_values_and_torch04_gradient():
+    gd = _load("focal.pt")
+    for (gamma, tval), rec in gd.items():
+        x = rec["x"]
+        t = torch.full_like(x, tval)
+        assert abs(float(O.focal_loss(x, t, gamma)) - float(rec["value"])) < 1e-6
+        assert abs(float(O.focal_loss(x, t, gamma, detach_weight=True)) - float(rec["value"])) < 1e-6
+    # closed form for t=1, gamma=1: L = mean(sig(-x)*softplus(-x)),
+    # dL/dx = [-sig(x)sig(-x)softplus(-x) - sig(-x)^2]/N  (torch-0.4 semantics: gradient through the weight)
+    x = (torch.randn(16, 1, dtype=torch.float64) * 3).requires_grad_(True)
+    loss = O.focal_loss(x, torch.ones_like(x), 1)
+    g, = torch.autograd.grad(loss, x)
+    sp = torch.nn.functional.softplus(-x)
+    ref = (-torch.sigmoid(x) * torch.sigmoid(-x) * sp - torch.sigmoid(-x) ** 2) / x.numel()
+    assert rel_l2(g, ref.detach()) < 1e-10
+
+
+def test_x8_and_rounding_match_reference_golden():
+    gd = _load("x8_round.pt")
+    wt = gd["wt"]
+
+    def model(t):
+        return torch.nn.functional.conv2d(torch.nn.functional.interpolate(t, scale_factor=2), wt, padding=1)
+
+    out = O.x8_forward(model, gd["img"])
+    assert rel_l2(out, gd["out"]) < 1e-6
+    assert O.infer(model, gd["img"], 1.0) is not None
+    blend = O.infer(model, gd["img"], 0.5, model)
+    assert rel_l2(blend, 0.5 * model(gd["img"]) + 0.5 * gd["out"]) < 1e-6
+    img = O.tensors_to_img_u8(gd["round_in"])
+    assert (torch.from_numpy(img.copy()) == gd["round_out"]).all()
+
+
+def test_tv_is_a_sum_and_adam_matches_torch():
+    y = torch.arange(24, dtype=torch.float32).reshape(1, 2, 3, 4)
+    assert float(O.tv_loss(y)) == 2 * (3 * 3 * 1 + 2 * 4 * 4)
+    p = torch.randn(50)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=5e-5, betas=(0.9, 0.999))
+    m, v, mine = torch.zeros(50), torch.zeros(50), p.clone()
+    for step in range(1, 4):
+        g = torch.randn(50)
+        ref.grad = g.clone()
+        opt.step()
+        O.adam_update(mine, g, m, v, step, 5e-5)
+    assert rel_l2(mine, ref.detach()) < 1e-6
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not mounted (GPU box)")
+def test_oracle_against_live_reference_modules():
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REF)
+    try:
+        import torchvision.models as tvm
+        orig = tvm.vgg19
+        tvm.vgg19 = lambda pretrained=True, **kw: orig(weights=None)
+        import importlib
+        ref_model = importlib.import_module("model")
+    finally:
+        sys.path.remove(REF)
+    opt = {'depth': 3, 'num_channels': 64, 'res_scale': 0.1, 'patch_size': 8, 'spectral_norm': False}
+    torch.manual_seed(7)
+    G = ref_model.Generator(opt)
+    sd = O.init_generator(opt, 7)
+    for k, v in G.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    x = torch.rand(2, 3, 9, 11) * 255
+    assert rel_l2(O.generator_forward(sd, x, 3, 0.1), G(x).detach()) < 1e-5
+    torch.manual_seed(8)
+    D = ref_model.Discriminator(opt).train()
+    dsd = O.init_discriminator(opt, 8)
+    for k, v in D.state_dict().items():
+        assert torch.equal(v, dsd[k]), k
+    xi = torch.rand(3, 3, 32, 32) * 255
+    assert rel_l2(O.discriminator_forward(dsd, xi), D(xi).detach()) < 1e-4

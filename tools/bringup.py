@@ -105,8 +105,48 @@ def wgrad_case(nb, cin, cout, h, w, dtype=torch.float16, lbo=0, sbo=0, seed=0, s
     return e
 
 
+def gen_case(opt, shape, dtype=torch.float16, seed=0, qmatch=True):
+    from oracle import pesr_oracle as O
+    from pesr_b200.model import Generator
+    sd = O.init_generator(opt, seed)
+    G = Generator(opt, dtype=dtype)
+    G.load_state_dict(sd)
+    G = G.cuda()
+    g = torch.Generator().manual_seed(seed + 1)
+    lr = torch.rand(*shape, generator=g) * 255
+    hr = torch.rand(shape[0], 3, shape[2] * 4, shape[3] * 4, generator=g) * 255
+    with torch.no_grad():
+        sr_inf = G(lr.cuda())
+    sr = G(lr.cuda())
+    loss = (sr - hr.cuda()).abs().mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    print(f"gen {opt} {shape} {str(dtype)[6:]}: train/infer sr diff {rel(sr_inf, sr.detach()):.2e}")
+    for name, kw in (("fp64", dict(dtype=torch.float64)), ("qmatch", dict(dtype=torch.float64, qdtype=dtype))):
+        if name == "qmatch" and not qmatch:
+            continue
+        ol, osr, og = O.pretrain_step(sd, lr, hr, opt, **kw)
+        errs = {k: rel(p.grad.cpu(), og[k]) for k, p in G.named_parameters()}
+        vals = sorted(errs.values())
+        worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+        print(f"  vs {name}: sr rel {rel(sr.detach().cpu(), osr):.3e}  loss rel {abs(loss.item() - ol.item()) / ol.item():.3e}  "
+              f"grad rel median {vals[len(vals) // 2]:.3e} max {vals[-1]:.3e}")
+        print("   worst:", ", ".join(f"{k}={v:.2e}" for k, v in worst))
+        for k in ("sub_mean.weight", "sub_mean.bias", "embed.weight", "embed.bias", "upsample.0.weight",
+                  "upsample.0.bias", "upsample.2.weight", "upsample.4.weight", "upsample.4.bias", "add_mean.weight",
+                  "add_mean.bias", f"body.{opt['depth']}.weight", "body.0.body.0.weight", "body.0.body.2.weight"):
+            print(f"     {k}: {errs[k]:.2e}", end="")
+        print(flush=True)
+
+
 def main():
     what = sys.argv[1]
+    if what == "gen":
+        gen_case({'depth': 2, 'num_channels': 64, 'res_scale': 0.1}, (2, 3, 10, 12))
+        gen_case({'depth': 2, 'num_channels': 64, 'res_scale': 0.1}, (2, 3, 10, 12), dtype=torch.bfloat16)
+        gen_case({'depth': 4, 'num_channels': 128, 'res_scale': 0.1}, (1, 3, 24, 24))
+        gen_case({'depth': 32, 'num_channels': 256, 'res_scale': 0.1}, (1, 3, 16, 16), qmatch=False)
+        return
     if what == "layout":
         x = torch.randn(2, 40, 10, 12, device="cuda")
         y = from_nhwc16(to_nhwc16(x, torch.float16), 2, 40, 10, 12)

@@ -1,0 +1,118 @@
+"""Kernel timing probe (CUDA events, warm-up, L2 flush between iterations). Prints TFLOP/s per kernel."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.nn.functional as F
+
+from pesr_b200 import ops
+
+FLUSH = None
+
+
+def timeit(fn, iters=10, warm=3, flush=True):
+    global FLUSH
+    if FLUSH is None:
+        FLUSH = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        if flush:
+            FLUSH.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        tot += s.elapsed_time(e)
+    return tot / iters
+
+
+def conv_case(nb, cin, cout, h, w, dtype=torch.float16, **epi):
+    x16 = torch.randn(nb, h, w, cin, device="cuda").to(dtype)
+    wp = (torch.randn(9 * cout, cin, device="cuda") / (3 * cin ** 0.5)).to(dtype)
+    out16 = torch.empty(nb, h, w, cout, device="cuda", dtype=dtype)
+    bias = torch.randn(cout, device="cuda")
+    d = ops.make_conv_desc(dtype=ops.dt_code(dtype), nb=nb, h=h, w=w, cin=cin, cout=cout,
+                           srcs=[ops.nhwc_src(x16, nb, h, w, cin)], wpacked=wp, bias=bias, act=1, out16=out16,
+                           ld_out16=cout)
+    ms = timeit(lambda: ops.conv_igemm(d))
+    fl = 2.0 * nb * h * w * cout * cin * 9
+    # cuDNN comparator (channels_last fp16)
+    xc = torch.randn(nb, cin, h, w, device="cuda", dtype=dtype).contiguous(memory_format=torch.channels_last)
+    wc = torch.randn(cout, cin, 3, 3, device="cuda", dtype=dtype).contiguous(memory_format=torch.channels_last)
+    ms_c = timeit(lambda: F.conv2d(xc, wc, None, padding=1))
+    print(f"fprop nb={nb} {cin}->{cout} {h}x{w}: {ms*1e3:.1f} us  {fl/ms/1e9:.0f} TFLOP/s | cudnn {ms_c*1e3:.1f} us "
+          f"{fl/ms_c/1e9:.0f} TFLOP/s", flush=True)
+
+
+def wgrad_case(nb, cin, cout, h, w, dtype=torch.float16):
+    x16 = torch.randn(nb, h, w, cin, device="cuda").to(dtype)
+    dy16 = torch.randn(nb, h, w, cout, device="cuda").to(dtype)
+    part = torch.empty(16 * 9 * cout * cin, device="cuda", dtype=torch.float32)
+    grad = torch.empty(cout, cin, 3, 3, device="cuda")
+    d = ops.make_wgrad_desc(dtype=ops.dt_code(dtype), nb=nb, h=h, w=w, a=dy16, a_c=cout, m_total=cout,
+                            b_srcs=[ops.nhwc_src(x16, nb, h, w, cin)], n_total=cin, partials=part)
+    sp = [0]
+
+    def run():
+        sp[0] = ops.conv_wgrad(d)
+    ms = timeit(run)
+    ms_r = timeit(lambda: ops.wgrad_reduce(part, sp[0], 9, cout, cin, ops.WMAP_OIHW, cout, cin, grad))
+    fl = 2.0 * nb * h * w * cout * cin * 9
+    xc = torch.randn(nb, cin, h, w, device="cuda", dtype=dtype).contiguous(memory_format=torch.channels_last)
+    dyc = torch.randn(nb, cout, h, w, device="cuda", dtype=dtype).contiguous(memory_format=torch.channels_last)
+    ms_c = timeit(lambda: torch.nn.grad.conv2d_weight(xc, (cout, cin, 3, 3), dyc, padding=1))
+    print(f"wgrad nb={nb} {cin}->{cout} {h}x{w}: {ms*1e3:.1f} us (splits {sp[0]}) {fl/ms/1e9:.0f} TFLOP/s, reduce "
+          f"{ms_r*1e3:.1f} us | cudnn {ms_c*1e3:.1f} us {fl/ms_c/1e9:.0f} TFLOP/s", flush=True)
+
+
+def gen_step(nb=16, dtype=torch.float16):
+    from pesr_b200.model import Generator
+    opt = {'depth': 32, 'num_channels': 256, 'res_scale': 0.1}
+    torch.manual_seed(0)
+    G = Generator(opt, dtype=dtype).cuda()
+    lr = torch.rand(nb, 3, 48, 48, device="cuda") * 255
+    hr = torch.rand(nb, 3, 192, 192, device="cuda") * 255
+
+    def fwd():
+        with torch.no_grad():
+            G(lr)
+
+    def step():
+        for p in G.parameters():
+            p.grad = None
+        sr = G(lr)
+        loss = (sr - hr).abs().mean()
+        loss.backward()
+    ms_f = timeit(fwd, iters=5, flush=False)
+    ms_s = timeit(step, iters=5, flush=False)
+    print(f"G fwd nb={nb}: {ms_f:.2f} ms = {nb*231.564/ms_f:.0f} TFLOP/s ; fwd+bwd: {ms_s:.2f} ms = "
+          f"{nb*3*231.564/ms_s:.0f} TFLOP/s ({nb/ms_s*1e3:.0f} samples/s)", flush=True)
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        step()
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"   host launch time per step {1e3*(t1-t0)/3:.2f} ms, total wall {1e3*(t2-t0)/3:.2f} ms")
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("all", "conv"):
+        conv_case(16, 256, 256, 48, 48)
+        conv_case(16, 256, 1024, 48, 48)
+        conv_case(16, 256, 1024, 96, 96)
+        conv_case(16, 1024, 256, 96, 96)
+        conv_case(16, 64, 64, 192, 192)
+        conv_case(16, 512, 512, 24, 24)
+        wgrad_case(16, 256, 256, 48, 48)
+        wgrad_case(16, 256, 1024, 96, 96)
+    if what in ("all", "gen"):
+        gen_step()

@@ -47,6 +47,12 @@ const char* pesr_last_error(void);
 int pesr_version(void);
 /* Number of kernels this library has launched since the last reset (bench.py's gpu_launches). */
 long long pesr_launch_count(int reset);
+/* Per-launch profiling of the tensor-core kernels: when enabled every pesr_conv_igemm (kind 0) and
+ * pesr_conv_wgrad (kind 1) launch is bracketed by CUDA events on its stream.  pesr_profile_read
+ * synchronises the device and returns the summed kernel time, launch count and algorithmic FLOPs
+ * (dense convention 2*M*N*K, padding taps counted), then clears the records of that kind. */
+void pesr_profile_enable(int on);
+int pesr_profile_read(int kind, double* total_ms, long long* launches, double* flops);
 /* sizeof(pesr_conv_desc) for which == 0, sizeof(pesr_wgrad_desc) for 1 (binding self-check). */
 int pesr_sizeof(int which);
 
@@ -193,6 +199,27 @@ int pesr_amax_scale(const float* x, int64_t n, float target, float* ws3, void* s
 /* sums[0..8] = sum_p a[o][p]*b[i][p] (row-major [o][i]), sums[9..11] = sum_p a[o][p]; a, b are
  * [nb][3][hw] fp32.  The MeanShift weight/bias gradients (model/basic.py:17 leaves them trainable). */
 int pesr_moments3(const float* a, const float* b, int32_t nb, int64_t hw, float* sums12, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Loss reductions with the gradient produced in the same pass (train.py:131-140), all fp32.
+ *   *loss receives the scalar (it is zeroed by the call); grad (optional) receives d loss / d a.
+ * ------------------------------------------------------------------------------------------------ */
+int pesr_loss_l1(const float* a, const float* b, int64_t n, float* loss, float* grad, void* stream);  /* nn.L1Loss, train.py:131 */
+int pesr_loss_mse(const float* a, const float* b, int64_t n, float* loss, float* grad, void* stream); /* F.mse_loss, train.py:136 */
+/* TV (train.py:137-140): SUM of |dx| + |dy| over y viewed as [planes][h][w]. */
+int pesr_loss_tv(const float* y, int64_t planes, int32_t h, int32_t w, float* loss, float* grad, void* stream);
+/* GAN losses on n logits: x = sign_a*a + sign_b*b (b may be NULL), target t in {0,1}.
+ *   mode 0: BCE-with-logits mean (nn.BCEWithLogitsLoss, train.py:132,211,213)
+ *   mode 1: FocalLoss(gamma) (model/focal_loss.py:9-13) with torch-0.4 gradient semantics (through the weight)
+ *   mode 2: FocalLoss(gamma) with the weight detached (what torch >= 1.0 would compute)
+ * grad_a / grad_b (optional) receive d loss / d a, d loss / d b. */
+int pesr_loss_gan(const float* a, const float* b, int32_t n, float sign_a, float sign_b, float target, int32_t mode,
+                  float gamma, float* loss, float* grad_a, float* grad_b, void* stream);
+
+/* Multi-tensor Adam (torch.optim.Adam semantics, train.py:124-126; no weight decay, no amsgrad).
+ * table_dev: nchunks rows of {p, g, m, v (device addresses), n} as int64; g is multiplied by grad_mul first. */
+int pesr_adam_multi(const int64_t* table_dev, int32_t nchunks, float lr, float beta1, float beta2, float eps,
+                    int32_t step, float grad_mul, void* stream);
 
 #ifdef __cplusplus
 }

@@ -83,6 +83,8 @@ SIGNATURES = {
     "pesr_version": (C.c_int, []),
     "pesr_launch_count": (C.c_longlong, [C.c_int]),
     "pesr_sizeof": (C.c_int, [C.c_int]),
+    "pesr_profile_enable": (None, [C.c_int]),
+    "pesr_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
     "pesr_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), _vp]),
     "pesr_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), C.POINTER(_i32), _vp]),
     "pesr_debug_wgrad_desc": (None, [C.c_int, C.c_int]),
@@ -95,6 +97,11 @@ SIGNATURES = {
     "pesr_colsum16": (C.c_int, [_vp, _i64, _i32, _i32, _f32, _vp, _i32, _i32, _vp, _vp]),
     "pesr_amax_scale": (C.c_int, [_vp, _i64, _f32, _vp, _vp]),
     "pesr_moments3": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp]),
+    "pesr_loss_l1": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "pesr_loss_mse": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "pesr_loss_tv": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "pesr_loss_gan": (C.c_int, [_vp, _vp, _i32, _f32, _f32, _f32, _i32, _f32, _vp, _vp, _vp, _vp]),
+    "pesr_adam_multi": (C.c_int, [_vp, _i32, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():
@@ -111,6 +118,17 @@ def check(rc, what=""):
     if rc != 0:
         msg = lib.pesr_last_error().decode("utf-8", "replace")
         raise PesrError(f"{what or 'pesr_b200'} failed (rc={rc}): {msg}")
+
+
+def profile_enable(on=True):
+    lib.pesr_profile_enable(1 if on else 0)
+
+
+def profile_read(kind):
+    """-> (total kernel ms, launches, algorithmic FLOPs) of the tensor-core launches recorded since the last read."""
+    ms, n, fl = C.c_double(0), C.c_longlong(0), C.c_double(0)
+    check(lib.pesr_profile_read(kind, C.byref(ms), C.byref(n), C.byref(fl)), "pesr_profile_read")
+    return ms.value, n.value, fl.value
 
 
 def launch_count(reset=False):

@@ -363,7 +363,10 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d, void* stream_) {
     attr_set = true;
   }
   int grid = k.num_tiles < num_sms() ? k.num_tiles : num_sms();
+  const bool prof = profiling_enabled();
+  if (prof) profile_begin(0, 2.0 * d->nb * d->h * d->w * (double)d->cout * d->cin * d->ntaps, stream);
   conv_igemm_kernel<<<grid, kNumThreads, smem, stream>>>(maps, k);
+  if (prof) profile_end(0, stream);
   count_launch();
   PESR_CHECK_LAUNCH("conv_igemm");
   return 0;

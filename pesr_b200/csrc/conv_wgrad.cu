@@ -353,7 +353,10 @@ extern "C" int pesr_conv_wgrad(const pesr_wgrad_desc* d, int32_t* splits_out, vo
     attr_set = true;
   }
   int grid = k.num_items < num_sms() ? k.num_items : num_sms();
+  const bool prof = profiling_enabled();
+  if (prof) profile_begin(1, 2.0 * d->nb * d->h * d->w * (double)d->m_total * d->n_total * d->ntaps, stream);
   conv_wgrad_kernel<<<grid, kWgThreads, smem, stream>>>(maps, k);
+  if (prof) profile_end(1, stream);
   count_launch();
   PESR_CHECK_LAUNCH("conv_wgrad");
   if (splits_out) *splits_out = splits;

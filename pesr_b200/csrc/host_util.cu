@@ -116,7 +116,83 @@ int get_tensor_map(CUtensorMap* out, const void* base, int dtype, int rank, cons
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// per-launch profiling
+// ------------------------------------------------------------------------------------------
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  int kind;
+  double flops;
+};
+static bool g_prof = false;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_event_pool;
+
+bool profiling_enabled() { return g_prof; }
+
+static cudaEvent_t get_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+void profile_begin(int kind, double flops, cudaStream_t stream) {
+  ProfRec r;
+  r.e0 = get_event();
+  r.e1 = get_event();
+  r.kind = kind;
+  r.flops = flops;
+  cudaEventRecord(r.e0, stream);
+  g_prof_recs.push_back(r);
+}
+
+void profile_end(int kind, cudaStream_t stream) {
+  (void)kind;
+  if (!g_prof_recs.empty()) cudaEventRecord(g_prof_recs.back().e1, stream);
+}
+
 }  // namespace pesr
+
+extern "C" void pesr_profile_enable(int on) {
+  pesr::g_prof = on != 0;
+}
+
+// Synchronises, sums the recorded launches of `kind`, returns them and clears the records of that kind.
+extern "C" int pesr_profile_read(int kind, double* total_ms, long long* launches, double* flops) {
+  using namespace pesr;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    set_error("profile_read: sync failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  double ms = 0, fl = 0;
+  long long n = 0;
+  std::vector<ProfRec> keep;
+  for (auto& r : g_prof_recs) {
+    if (r.kind != kind) {
+      keep.push_back(r);
+      continue;
+    }
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) {
+      ms += t;
+      fl += r.flops;
+      n++;
+    }
+    g_event_pool.push_back(r.e0);
+    g_event_pool.push_back(r.e1);
+  }
+  g_prof_recs.swap(keep);
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = n;
+  if (flops) *flops = fl;
+  return 0;
+}
 
 extern "C" const char* pesr_last_error(void) { return pesr::g_err; }
 extern "C" int pesr_version(void) { return 100; }

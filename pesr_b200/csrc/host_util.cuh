@@ -14,6 +14,13 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int num_sms();
 
+// Optional per-launch profiling of the tensor-core kernels (bench.py's roofline leg): when enabled, the
+// launchers bracket each launch with CUDA events on the launch stream and record its algorithmic FLOPs.
+// kind 0 = conv_igemm (fprop/dgrad), 1 = conv_wgrad.
+bool profiling_enabled();
+void profile_begin(int kind, double flops, cudaStream_t stream);
+void profile_end(int kind, cudaStream_t stream);
+
 // Encodes (or fetches from the cache) a tiled, 128B-swizzled tensor map over a 16-bit tensor.
 // dims/strides are innermost-first; strides_bytes has rank-1 entries (dims 1..rank-1).
 // Returns 0 or a PESR_E_* code.

@@ -10,12 +10,21 @@ Forward (all activations NHWC 16-bit, fp32 residual stream kept beside them):
     Z  = U2 x W4 (1x1 GEMM, 27 columns) --col2im3(+bias, +add_mean)--> sr (NCHW fp32)
 
 Backward mirrors it with the same implicit-GEMM kernel on flipped weights (dgrad) and the split-K
-MN-major kernel (wgrad); the fp32 gradients land in the reference's OIHW layouts.
+MN-major kernel (wgrad).  Parameter gradients are fp32, in the reference's layouts, and are views of
+ONE flat buffer in parameter order; they complete from the end of that buffer towards its start, and
+``grad_hook(lo, hi, flat)`` is called as each range completes so that a data-parallel wrapper can start
+the NCCL all-reduce of a bucket while the rest of backward is still running.
+
+Launch descriptors are built once per (batch, height, width) plan and replayed; per step the host only
+re-packs changed weights and issues the launches.
 """
+import ctypes as C
+
 import torch
 
 from . import ops
-from .ops import ACT_NONE, ACT_RELU, OUT_SHUFFLE2, OUT_UNSHUFFLE2
+from ._lib import check, lib
+from .ops import ACT_RELU, OUT_SHUFFLE2, OUT_UNSHUFFLE2
 
 
 class PackedWeight:
@@ -37,7 +46,7 @@ class PackedWeight:
 
 
 def _unshuffle_perm(vec, c):
-    """packed PixelShuffle order (i, j, c) -> reference order c*4 + i*2 + j."""
+    """packed PixelShuffle order (ij, c) -> reference order c*4 + ij."""
     return vec.view(4, c).t().reshape(-1)
 
 
@@ -47,8 +56,11 @@ def _shuffle_perm(vec, c):
 
 
 class _Plan:
-    """Buffers + prebuilt launch descriptors for one (nb, h, w, training) configuration."""
     pass
+
+
+def _run_conv(desc, stream):
+    check(lib.pesr_conv_igemm(C.byref(desc), stream), "pesr_conv_igemm")
 
 
 class GeneratorEngine:
@@ -59,21 +71,25 @@ class GeneratorEngine:
         self.plans = {}
         self.packed = None
         self.device = None
-        self.wg_ws = None
+        self.grad_hook = None      # callable(lo, hi, flat) -> None
+        self.grad_hook_finish = None
+        self.param_list = None
+        self.last_flat_grad = None
 
     # ------------------------------------------------------------------ parameters
     def _convs(self):
         g = self.gen
-        trunk = []
-        for blk in g.body[:-1]:
-            trunk.append((blk.body[0], blk.body[2]))
+        trunk = [(blk.body[0], blk.body[2]) for blk in list(g.body)[:-1]]
         return trunk, g.body[-1]
 
     def _ensure_packed(self, device):
-        if self.packed is not None and self.device == device:
+        sentinel = (self.gen.embed.weight.data_ptr(), self.gen.add_mean.bias.data_ptr())
+        if self.packed is not None and self.device == device and self.sentinel == sentinel:
             return
+        self.sentinel = sentinel
         g, dt = self.gen, self.dtype
         self.device = device
+        self.plans = {}
         trunk, tail = self._convs()
         pk = {}
         pk["embed_f"] = PackedWeight(g.embed.weight, 4, dt, pad_to=64)
@@ -92,7 +108,18 @@ class GeneratorEngine:
         pk["up4_f"] = PackedWeight(g.upsample[4].weight, 5, dt, pad_to=32)
         pk["up4_d"] = PackedWeight(g.upsample[4].weight, 7, dt, pad_to=64)
         self.packed = pk
+        self.fwd_packs = [v for k, v in pk.items() if k.endswith("_f")]
+        self.bwd_packs = [v for k, v in pk.items() if k.endswith("_d")]
         self.scale_ws = torch.zeros(4, device=device, dtype=torch.float32)
+        C_ = g.n_feats
+        self.bias_up0 = torch.empty(4 * C_, device=device, dtype=torch.float32)
+        self.bias_up2 = torch.empty(4 * C_, device=device, dtype=torch.float32)
+        # flat gradient layout: parameter order, each tensor starting on a 16-byte boundary
+        self.offsets, off = {}, 0
+        for p in self.param_list:
+            self.offsets[p] = off
+            off += (p.numel() + 3) // 4 * 4
+        self.flat_numel = off
 
     # ------------------------------------------------------------------ plans
     def _plan(self, nb, h, w, train):
@@ -101,200 +128,240 @@ class GeneratorEngine:
         if pl is not None:
             return pl
         g = self.gen
-        C, depth = g.n_feats, g.n_resblock
-        dev, dt = self.device, self.dtype
+        Cn, depth, rs = g.n_feats, g.n_resblock, float(g.res_scale)
+        dev, tdt, dt = self.device, self.dtype, self.dt
+        pk = self.packed
         P = nb * h * w
         pl = _Plan()
         pl.nb, pl.h, pl.w, pl.P, pl.train = nb, h, w, P, train
-        e16 = lambda *s: torch.empty(*s, device=dev, dtype=dt)
-        e32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        e16 = lambda *s: torch.empty(*s, device=dev, dtype=tdt)  # noqa: E731
+        e32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
         pl.col_in = e16(P, 64)
-        pl.F0 = e32(P, C)
-        pl.S = e32(P, C)
-        nx = depth + 1 if train else 2
-        pl.X = [e16(P, C) for _ in range(nx)]
-        pl.T = [e16(P, C) for _ in range(depth if train else 1)]
-        pl.U0 = e16(P, C)
-        pl.U1 = e16(4 * P, C)
-        pl.U2 = e16(16 * P, C)
+        pl.F0 = e32(P, Cn)
+        pl.S = e32(P, Cn)
+        pl.X = [e16(P, Cn) for _ in range(depth + 1 if train else 2)]
+        pl.T = [e16(P, Cn) for _ in range(depth if train else 1)]
+        pl.U0 = e16(P, Cn)
+        pl.U1 = e16(4 * P, Cn)
+        pl.U2 = e16(16 * P, Cn)
         pl.Z = e32(16 * P, 32)
         pl.ypre = e32(nb, 3, 4 * h, 4 * w) if train else None
         pl.generation = 0
-        if train:
-            pl.dcol = e16(16 * P, 64)
-            pl.dZ2 = e16(4 * P, 4 * C)
-            pl.dZ1 = e16(P, 4 * C)
-            pl.dR16 = e16(P, C)
-            pl.gS32 = e32(P, C)
-            pl.gS16 = e16(P, C)
-            pl.dT16 = e16(P, C)
-            pl.dF0 = e16(P, C)
-            pl.Zd = e32(P, 32)
-            pl.dx_sm = e32(nb, 3, h, w)
-            pl.sums = torch.zeros(24, device=dev, dtype=torch.float32)
-            wg_elems = max(9 * 4 * C * C * 2, 9 * C * C * 8, 148 * C * 64)
-            pl.wg = e32(wg_elems)
+        X = (lambda i: pl.X[i]) if train else (lambda i: pl.X[i % 2])
+        T = (lambda i: pl.T[i]) if train else (lambda i: pl.T[0])
+        trunk, tail = self._convs()
+        up0, up2, up4 = g.upsample[0], g.upsample[2], g.upsample[4]
+        bn = min(Cn, 256)
+
+        def src(t, hh, ww, c):
+            return [ops.nhwc_src(t, nb, hh, ww, c)]
+
+        # ---------------- forward launch list
+        f = []
+        f.append(ops.make_conv_desc(dtype=dt, nb=nb, h=h, w=w, cin=64, cout=Cn, taps=[(0, 0)],
+                                    srcs=src(pl.col_in, h, w, 64), wpacked=pk["embed_f"].buf,
+                                    bias=g.embed.bias, out32=pl.F0, ld_out32=Cn, out16=X(0), ld_out16=Cn))
+        for i, (c1, c2) in enumerate(trunk):
+            f.append(ops.make_conv_desc(dtype=dt, nb=nb, h=h, w=w, cin=Cn, cout=Cn, srcs=src(X(i), h, w, Cn),
+                                        wpacked=pk[f"b{i}c1_f"].buf, bias=c1.bias, act=ACT_RELU, out16=T(i),
+                                        ld_out16=Cn))
+            f.append(ops.make_conv_desc(dtype=dt, nb=nb, h=h, w=w, cin=Cn, cout=Cn, srcs=src(T(i), h, w, Cn),
+                                        wpacked=pk[f"b{i}c2_f"].buf, bias=c2.bias, alpha=rs,
+                                        res32=pl.F0 if i == 0 else pl.S, ld_res32=Cn, out32=pl.S, ld_out32=Cn,
+                                        out16=X(i + 1), ld_out16=Cn))
+        f.append(ops.make_conv_desc(dtype=dt, nb=nb, h=h, w=w, cin=Cn, cout=Cn, srcs=src(X(depth), h, w, Cn),
+                                    wpacked=pk["tail_f"].buf, bias=tail.bias, res32=pl.F0, ld_res32=Cn,
+                                    out16=pl.U0, ld_out16=Cn))
+        f.append(ops.make_conv_desc(dtype=dt, nb=nb, h=h, w=w, cin=Cn, cout=4 * Cn, block_n=bn,
+                                    srcs=src(pl.U0, h, w, Cn), wpacked=pk["up0_f"].buf, bias=self.bias_up0,
+                                    out16=pl.U1, ld_out16=Cn, out_mode=OUT_SHUFFLE2, ps_c=Cn))
+        f.append(ops.make_conv_desc(dtype=dt, nb=nb, h=2 * h, w=2 * w, cin=Cn, cout=4 * Cn, block_n=bn,
+                                    srcs=src(pl.U1, 2 * h, 2 * w, Cn), wpacked=pk["up2_f"].buf, bias=self.bias_up2,
+                                    out16=pl.U2, ld_out16=Cn, out_mode=OUT_SHUFFLE2, ps_c=Cn))
+        f.append(ops.make_conv_desc(dtype=dt, nb=nb, h=4 * h, w=4 * w, cin=Cn, cout=32, taps=[(0, 0)],
+                                    srcs=src(pl.U2, 4 * h, 4 * w, Cn), wpacked=pk["up4_f"].buf, out32=pl.Z,
+                                    ld_out32=32))
+        pl.fwd = f
+        if not train:
+            self.plans[key] = pl
+            return pl
+
+        # ---------------- backward buffers and launch list
+        pl.dcol = e16(16 * P, 64)
+        pl.dZ2 = e16(4 * P, 4 * Cn)
+        pl.dZ1 = e16(P, 4 * Cn)
+        pl.dR16 = e16(P, Cn)
+        pl.gS32 = e32(P, Cn)
+        pl.gS16 = e16(P, Cn)
+        pl.dT16 = e16(P, Cn)
+        pl.dF0 = e16(P, Cn)
+        pl.Zd = e32(P, 32)
+        pl.dx_sm = e32(nb, 3, h, w)
+        pl.sums = torch.zeros(24, device=dev, dtype=torch.float32)
+        pl.bias_tmp = e32(8 * Cn)
+        pl.wg = e32(max(9 * 4 * Cn * Cn * 2, 9 * Cn * Cn * 8, 148 * max(Cn, 128) * 64))
+        scale = self.scale_ws[1:2]
+        b = []   # entries: ("conv", desc) | ("wgrad", desc, reduce-args) | ("bias", args) | ("mark", param) | ("call", fn)
+
+        def wgrad(a, a_c, m_total, bt, b_c, n_total, gh, gw, param, map_mode, co, ci, taps=ops.TAPS_3X3, mul=1.0):
+            d = ops.make_wgrad_desc(dtype=dt, nb=nb, h=gh, w=gw, a=a, a_c=a_c, m_total=m_total,
+                                    b_srcs=[ops.nhwc_src(bt, nb, gh, gw, b_c)], n_total=n_total, taps=taps,
+                                    partials=pl.wg)
+            b.append(("wgrad", d, (len(taps), m_total, n_total, map_mode, co, ci, mul), param))
+
+        def bgrad(x16, npix, c, ldc, param, mul=1.0, perm_c=0):
+            b.append(("bias", (x16, npix, c, ldc, mul, perm_c), param))
+
+        def conv(**kw):
+            b.append(("conv", ops.make_conv_desc(dtype=dt, nb=nb, **kw)))
+
+        # upsample.4 (Cout = 3): dgrad = 1x1 GEMM over the flipped im2col of dy, stored un-shuffled
+        conv(h=4 * h, w=4 * w, cin=64, cout=Cn, taps=[(0, 0)], srcs=src(pl.dcol, 4 * h, 4 * w, 64),
+             wpacked=pk["up4_d"].buf, out16=pl.dZ2, ld_out16=4 * Cn, out_mode=OUT_UNSHUFFLE2)
+        wgrad(pl.U2, Cn, Cn, pl.dcol, 64, 64, 4 * h, 4 * w, up4.weight, ops.WMAP_COL_OUT, 3, Cn, taps=[(0, 0)])
+        b.append(("mark", up4.weight))
+        # upsample.2
+        conv(h=2 * h, w=2 * w, cin=4 * Cn, cout=Cn, srcs=src(pl.dZ2, 2 * h, 2 * w, 4 * Cn), wpacked=pk["up2_d"].buf,
+             out16=pl.dZ1, ld_out16=4 * Cn, out_mode=OUT_UNSHUFFLE2)
+        bgrad(pl.dZ2, 4 * P, 4 * Cn, 4 * Cn, up2.bias, perm_c=Cn)
+        wgrad(pl.dZ2, 4 * Cn, 4 * Cn, pl.U1, Cn, Cn, 2 * h, 2 * w, up2.weight, ops.WMAP_OIHW_PS, 4 * Cn, Cn)
+        b.append(("mark", up2.weight))
+        # upsample.0: its dgrad is dR, the gradient of (tail(X_depth) + F0)
+        conv(h=h, w=w, cin=4 * Cn, cout=Cn, srcs=src(pl.dZ1, h, w, 4 * Cn), wpacked=pk["up0_d"].buf, out16=pl.dR16,
+             ld_out16=Cn)
+        bgrad(pl.dZ1, P, 4 * Cn, 4 * Cn, up0.bias, perm_c=Cn)
+        wgrad(pl.dZ1, 4 * Cn, 4 * Cn, pl.U0, Cn, Cn, h, w, up0.weight, ops.WMAP_OIHW_PS, 4 * Cn, Cn)
+        b.append(("mark", up0.weight))
+        # tail conv
+        bgrad(pl.dR16, P, Cn, Cn, tail.bias)
+        wgrad(pl.dR16, Cn, Cn, pl.X[depth], Cn, Cn, h, w, tail.weight, ops.WMAP_OIHW, Cn, Cn)
+        b.append(("mark", tail.weight))
+        conv(h=h, w=w, cin=Cn, cout=Cn, srcs=src(pl.dR16, h, w, Cn), wpacked=pk["tail_d"].buf, out32=pl.gS32,
+             ld_out32=Cn, out16=pl.gS16, ld_out16=Cn)
+        for i in range(depth - 1, -1, -1):
+            c1, c2 = trunk[i]
+            bgrad(pl.gS16, P, Cn, Cn, c2.bias, mul=rs)
+            wgrad(pl.gS16, Cn, Cn, pl.T[i], Cn, Cn, h, w, c2.weight, ops.WMAP_OIHW, Cn, Cn, mul=rs)
+            conv(h=h, w=w, cin=Cn, cout=Cn, srcs=src(pl.gS16, h, w, Cn), wpacked=pk[f"b{i}c2_d"].buf, alpha=rs,
+                 mask16=pl.T[i], ld_mask16=Cn, mask_mode=1, out16=pl.dT16, ld_out16=Cn)
+            bgrad(pl.dT16, P, Cn, Cn, c1.bias)
+            wgrad(pl.dT16, Cn, Cn, pl.X[i], Cn, Cn, h, w, c1.weight, ops.WMAP_OIHW, Cn, Cn)
+            b.append(("mark", c1.weight))
+            last = i == 0
+            conv(h=h, w=w, cin=Cn, cout=Cn, srcs=src(pl.dT16, h, w, Cn), wpacked=pk[f"b{i}c1_d"].buf,
+                 res32=pl.gS32, ld_res32=Cn, res16=pl.dR16 if last else None, ld_res16=Cn,
+                 out32=None if last else pl.gS32, ld_out32=Cn, out16=pl.dF0 if last else pl.gS16, ld_out16=Cn)
+        # embed (Cin = 3): wgrad against the saved im2col matrix; dgrad as a col2im GEMM (for sub_mean's gradients)
+        bgrad(pl.dF0, P, Cn, Cn, g.embed.bias)
+        wgrad(pl.dF0, Cn, Cn, pl.col_in, 64, 64, h, w, g.embed.weight, ops.WMAP_COL_IN, Cn, 3, taps=[(0, 0)])
+        conv(h=h, w=w, cin=Cn, cout=32, taps=[(0, 0)], srcs=src(pl.dF0, h, w, Cn), wpacked=pk["embed_d"].buf,
+             out32=pl.Zd, ld_out32=32)
+        pl.bwd = b
+        pl.scale = scale
         self.plans[key] = pl
         return pl
-
-    def _x(self, pl, i):
-        return pl.X[i] if pl.train else pl.X[i % 2]
-
-    def _t(self, pl, i):
-        return pl.T[i] if pl.train else pl.T[0]
 
     # ------------------------------------------------------------------ forward
     def forward(self, lr, train):
         g = self.gen
-        assert lr.dim() == 4 and lr.shape[1] == 3, "Generator expects [N,3,H,W]"
+        if lr.dim() != 4 or lr.shape[1] != 3:
+            raise ValueError(f"Generator expects [N,3,H,W], got {tuple(lr.shape)}")
+        if g.n_resblock < 1:
+            raise NotImplementedError("pesr_b200.Generator needs depth >= 1")
         lr = lr.contiguous().float()
         nb, _, h, w = lr.shape
         self._ensure_packed(lr.device)
         pl = self._plan(nb, h, w, train)
         pl.generation += 1
-        pk, dt = self.packed, self.dt
-        C, depth, rs = g.n_feats, g.n_resblock, float(g.res_scale)
-        trunk, tail = self._convs()
-        P = pl.P
-        sm_w = g.sub_mean.weight.detach().reshape(3, 3).contiguous()
-        sm_b = g.sub_mean.bias.detach()
-        am_w = g.add_mean.weight.detach().reshape(3, 3).contiguous()
-        am_b = g.add_mean.bias.detach()
-
-        ops.im2col3(lr, pl.col_in, affine_a=sm_w, affine_b=sm_b)
-        # embed: 1x1 GEMM over the im2col matrix
-        ops.conv_igemm(ops.make_conv_desc(
-            dtype=dt, nb=nb, h=h, w=w, cin=64, cout=C, taps=[(0, 0)], srcs=[ops.nhwc_src(pl.col_in, nb, h, w, 64)],
-            wpacked=pk["embed_f"].get(), bias=g.embed.bias.detach(), out32=pl.F0, ld_out32=C,
-            out16=self._x(pl, 0), ld_out16=C))
-        for i, (c1, c2) in enumerate(trunk):
-            xin, t, xout = self._x(pl, i), self._t(pl, i), self._x(pl, i + 1)
-            ops.conv_igemm(ops.make_conv_desc(
-                dtype=dt, nb=nb, h=h, w=w, cin=C, cout=C, srcs=[ops.nhwc_src(xin, nb, h, w, C)],
-                wpacked=pk[f"b{i}c1_f"].get(), bias=c1.bias.detach(), act=ACT_RELU, out16=t, ld_out16=C))
-            ops.conv_igemm(ops.make_conv_desc(
-                dtype=dt, nb=nb, h=h, w=w, cin=C, cout=C, srcs=[ops.nhwc_src(t, nb, h, w, C)],
-                wpacked=pk[f"b{i}c2_f"].get(), bias=c2.bias.detach(), alpha=rs,
-                res32=pl.F0 if i == 0 else pl.S, ld_res32=C, out32=pl.S, ld_out32=C, out16=xout, ld_out16=C))
-        ops.conv_igemm(ops.make_conv_desc(
-            dtype=dt, nb=nb, h=h, w=w, cin=C, cout=C, srcs=[ops.nhwc_src(self._x(pl, depth), nb, h, w, C)],
-            wpacked=pk["tail_f"].get(), bias=tail.bias.detach(), res32=pl.F0, ld_res32=C, out16=pl.U0, ld_out16=C))
+        Cn = g.n_feats
+        for pw in self.fwd_packs:
+            pw.get()
         up0, up2, up4 = g.upsample[0], g.upsample[2], g.upsample[4]
-        ops.conv_igemm(ops.make_conv_desc(
-            dtype=dt, nb=nb, h=h, w=w, cin=C, cout=4 * C, block_n=min(C, 256),
-            srcs=[ops.nhwc_src(pl.U0, nb, h, w, C)], wpacked=pk["up0_f"].get(),
-            bias=_shuffle_perm(up0.bias.detach(), C).contiguous(), out16=pl.U1, ld_out16=C, out_mode=OUT_SHUFFLE2,
-            ps_c=C))
-        ops.conv_igemm(ops.make_conv_desc(
-            dtype=dt, nb=nb, h=2 * h, w=2 * w, cin=C, cout=4 * C, block_n=min(C, 256),
-            srcs=[ops.nhwc_src(pl.U1, nb, 2 * h, 2 * w, C)], wpacked=pk["up2_f"].get(),
-            bias=_shuffle_perm(up2.bias.detach(), C).contiguous(), out16=pl.U2, ld_out16=C, out_mode=OUT_SHUFFLE2,
-            ps_c=C))
-        ops.conv_igemm(ops.make_conv_desc(
-            dtype=dt, nb=nb, h=4 * h, w=4 * w, cin=C, cout=32, taps=[(0, 0)],
-            srcs=[ops.nhwc_src(pl.U2, nb, 4 * h, 4 * w, C)], wpacked=pk["up4_f"].get(), out32=pl.Z, ld_out32=32))
+        self.bias_up0.copy_(_shuffle_perm(up0.bias.detach(), Cn))
+        self.bias_up2.copy_(_shuffle_perm(up2.bias.detach(), Cn))
+        sm_w = g.sub_mean.weight.detach().reshape(3, 3)
+        am_w = g.add_mean.weight.detach().reshape(3, 3)
+        ops.im2col3(lr, pl.col_in, affine_a=sm_w, affine_b=g.sub_mean.bias.detach())
+        stream = torch.cuda.current_stream().cuda_stream
+        for d in pl.fwd:
+            _run_conv(d, stream)
         sr = torch.empty(nb, 3, 4 * h, 4 * w, device=lr.device, dtype=torch.float32)
-        ops.col2im3(pl.Z, 32, nb, 4 * h, 4 * w, sr, bias=up4.bias.detach(), affine_a=am_w, affine_b=am_b, sgn=1,
-                    pre=pl.ypre)
+        ops.col2im3(pl.Z, 32, nb, 4 * h, 4 * w, sr, bias=up4.bias.detach(), affine_a=am_w,
+                    affine_b=g.add_mean.bias.detach(), sgn=1, pre=pl.ypre)
         return sr, (pl, pl.generation, lr)
 
     # ------------------------------------------------------------------ backward
     def backward(self, state, dsr, need_input_grad=False):
-        """Returns (grads: dict param -> fp32 gradient in the reference layout, dlr or None)."""
+        """Returns (grads: dict param -> fp32 gradient view in the reference layout, dlr or None)."""
         pl, generation, lr = state
         if generation != pl.generation:
             raise RuntimeError("pesr_b200.Generator: backward through a forward whose activations were overwritten "
-                               "by a later forward of the same shape (keep one live graph per shape)")
+                               "by a later forward of the same shape (keep one live graph per input shape)")
         g = self.gen
-        pk, dt = self.packed, self.dt
-        C, depth, rs = g.n_feats, g.n_resblock, float(g.res_scale)
-        nb, h, w, P = pl.nb, pl.h, pl.w, pl.P
-        trunk, tail = self._convs()
-        up0, up2, up4 = g.upsample[0], g.upsample[2], g.upsample[4]
+        Cn = g.n_feats
+        nb, h, w = pl.nb, pl.h, pl.w
+        up4 = g.upsample[4]
         dsr = dsr.contiguous().float()
         dev = dsr.device
-        grads = {}
+        for pw in self.bwd_packs:
+            pw.get()
+        flat = torch.empty(self.flat_numel, device=dev, dtype=torch.float32)
+        self.last_flat_grad = flat
+        off = self.offsets
+        grads = {p: flat[off[p]:off[p] + p.numel()].view(p.shape) for p in self.param_list}
+        hook = self.grad_hook
+        mark_hi = [self.flat_numel]
+
+        def mark(param):
+            lo = off[param]
+            if hook is not None and lo < mark_hi[0]:
+                hook(lo, mark_hi[0], flat)
+            mark_hi[0] = lo
+
         ws = self.scale_ws
-        scale, wg = ws[1:2], pl.wg
-
-        def wgrad(a, a_c, m_total, b, b_c, n_total, gh, gw, param, map_mode, co, ci, taps=ops.TAPS_3X3, mul=1.0):
-            d = ops.make_wgrad_desc(dtype=dt, nb=nb, h=gh, w=gw, a=a, a_c=a_c, m_total=m_total,
-                                    b_srcs=[ops.nhwc_src(b, nb, gh, gw, b_c)], n_total=n_total, taps=taps,
-                                    partials=wg)
-            splits = ops.conv_wgrad(d)
-            gr = torch.empty_like(param)
-            ops.wgrad_reduce(wg, splits, len(taps), m_total, n_total, map_mode, co, ci, gr, scale=mul, div_dev=scale)
-            grads[param] = gr
-
-        def bgrad(x16, npix, c, ldc, mul=1.0):
-            out = torch.empty(c, device=dev, dtype=torch.float32)
-            ops.colsum16(x16, npix, c, ldc, out, mul=mul, div_dev=scale)
-            return out
-
-        # --- add_mean (1x1, trainable in the reference) and the gradient scale
+        scale = pl.scale
+        stream = torch.cuda.current_stream().cuda_stream
+        # add_mean (1x1, trainable in the reference, model/basic.py:17) and the dynamic gradient scale
         am_w = g.add_mean.weight.detach().reshape(3, 3)
-        ops.moments3(dsr, pl.ypre, pl.sums[:12])
-        ops.amax_scale(dsr, ws, target=16.0)
         am_wt = am_w.t().contiguous()
+        ops.moments3(dsr, pl.ypre, pl.sums[:12])
+        s = pl.sums
+        grads[g.add_mean.weight].view(-1).copy_(s[0:9])
+        grads[g.add_mean.bias].copy_(s[9:12])
+        torch.mv(am_wt, s[9:12], out=grads[up4.bias])
+        mark(up4.bias)
+        ops.amax_scale(dsr, ws, target=16.0)
         ops.im2col3(dsr, pl.dcol, affine_a=am_wt, mul_dev=scale, sgn=-1)
-        # --- upsample.4 (Cout = 3): dgrad is a 1x1 GEMM over the flipped im2col of dy, stored un-shuffled
-        ops.conv_igemm(ops.make_conv_desc(
-            dtype=dt, nb=nb, h=4 * h, w=4 * w, cin=64, cout=C, taps=[(0, 0)],
-            srcs=[ops.nhwc_src(pl.dcol, nb, 4 * h, 4 * w, 64)], wpacked=pk["up4_d"].get(),
-            out16=pl.dZ2, ld_out16=4 * C, out_mode=OUT_UNSHUFFLE2))
-        wgrad(pl.U2, C, C, pl.dcol, 64, 64, 4 * h, 4 * w, up4.weight, ops.WMAP_COL_OUT, 3, C, taps=[(0, 0)])
-        # --- upsample.2
-        ops.conv_igemm(ops.make_conv_desc(
-            dtype=dt, nb=nb, h=2 * h, w=2 * w, cin=4 * C, cout=C, srcs=[ops.nhwc_src(pl.dZ2, nb, 2 * h, 2 * w, 4 * C)],
-            wpacked=pk["up2_d"].get(), out16=pl.dZ1, ld_out16=4 * C, out_mode=OUT_UNSHUFFLE2))
-        wgrad(pl.dZ2, 4 * C, 4 * C, pl.U1, C, C, 2 * h, 2 * w, up2.weight, ops.WMAP_OIHW_PS, 4 * C, C)
-        grads[up2.bias] = _unshuffle_perm(bgrad(pl.dZ2, 4 * P, 4 * C, 4 * C), C).contiguous()
-        # --- upsample.0 ; its dgrad is dR, the gradient of (tail(X_depth) + F0)
-        ops.conv_igemm(ops.make_conv_desc(
-            dtype=dt, nb=nb, h=h, w=w, cin=4 * C, cout=C, srcs=[ops.nhwc_src(pl.dZ1, nb, h, w, 4 * C)],
-            wpacked=pk["up0_d"].get(), out16=pl.dR16, ld_out16=C))
-        wgrad(pl.dZ1, 4 * C, 4 * C, pl.U0, C, C, h, w, up0.weight, ops.WMAP_OIHW_PS, 4 * C, C)
-        grads[up0.bias] = _unshuffle_perm(bgrad(pl.dZ1, P, 4 * C, 4 * C), C).contiguous()
-        # --- tail conv
-        wgrad(pl.dR16, C, C, pl.X[depth], C, C, h, w, tail.weight, ops.WMAP_OIHW, C, C)
-        grads[tail.bias] = bgrad(pl.dR16, P, C, C)
-        ops.conv_igemm(ops.make_conv_desc(
-            dtype=dt, nb=nb, h=h, w=w, cin=C, cout=C, srcs=[ops.nhwc_src(pl.dR16, nb, h, w, C)],
-            wpacked=pk["tail_d"].get(), out32=pl.gS32, ld_out32=C, out16=pl.gS16, ld_out16=C))
-        # --- residual blocks, last to first
-        for i in range(depth - 1, -1, -1):
-            c1, c2 = trunk[i]
-            wgrad(pl.gS16, C, C, pl.T[i], C, C, h, w, c2.weight, ops.WMAP_OIHW, C, C, mul=rs)
-            grads[c2.bias] = bgrad(pl.gS16, P, C, C, mul=rs)
-            ops.conv_igemm(ops.make_conv_desc(
-                dtype=dt, nb=nb, h=h, w=w, cin=C, cout=C, srcs=[ops.nhwc_src(pl.gS16, nb, h, w, C)],
-                wpacked=pk[f"b{i}c2_d"].get(), alpha=rs, mask16=pl.T[i], ld_mask16=C, mask_mode=1,
-                out16=pl.dT16, ld_out16=C))
-            wgrad(pl.dT16, C, C, pl.X[i], C, C, h, w, c1.weight, ops.WMAP_OIHW, C, C)
-            grads[c1.bias] = bgrad(pl.dT16, P, C, C)
-            last = i == 0
-            ops.conv_igemm(ops.make_conv_desc(
-                dtype=dt, nb=nb, h=h, w=w, cin=C, cout=C, srcs=[ops.nhwc_src(pl.dT16, nb, h, w, C)],
-                wpacked=pk[f"b{i}c1_d"].get(), res32=pl.gS32, ld_res32=C,
-                res16=pl.dR16 if last else None, ld_res16=C,
-                out32=None if last else pl.gS32, ld_out32=C, out16=pl.dF0 if last else pl.gS16, ld_out16=C))
-        if depth == 0:
-            raise NotImplementedError("Generator with depth 0")
-        # --- embed (Cin = 3): wgrad against the saved im2col matrix; dgrad as a col2im GEMM
-        wgrad(pl.dF0, C, C, pl.col_in, 64, 64, h, w, g.embed.weight, ops.WMAP_COL_IN, C, 3, taps=[(0, 0)])
-        grads[g.embed.bias] = bgrad(pl.dF0, P, C, C)
-        ops.conv_igemm(ops.make_conv_desc(
-            dtype=dt, nb=nb, h=h, w=w, cin=C, cout=32, taps=[(0, 0)], srcs=[ops.nhwc_src(pl.dF0, nb, h, w, C)],
-            wpacked=pk["embed_d"].get(), out32=pl.Zd, ld_out32=32))
+        splits_out = C.c_int32(0)
+        for op in pl.bwd:
+            kind = op[0]
+            if kind == "conv":
+                _run_conv(op[1], stream)
+            elif kind == "wgrad":
+                _, d, (ntaps, m_total, n_total, map_mode, co, ci, mul), param = op
+                check(lib.pesr_conv_wgrad(C.byref(d), C.byref(splits_out), stream), "pesr_conv_wgrad")
+                check(lib.pesr_wgrad_reduce(pl.wg.data_ptr(), splits_out.value, ntaps, m_total, n_total, map_mode, co,
+                                            ci, mul, scale.data_ptr(), 0, grads[param].data_ptr(), stream),
+                      "pesr_wgrad_reduce")
+            elif kind == "bias":
+                _, (x16, npix, c, ldc, mul, perm_c), param = op
+                if perm_c:
+                    ops.colsum16(x16, npix, c, ldc, pl.bias_tmp[:c], mul=mul, div_dev=scale)
+                    grads[param].copy_(_unshuffle_perm(pl.bias_tmp[:c], perm_c))
+                else:
+                    ops.colsum16(x16, npix, c, ldc, grads[param], mul=mul, div_dev=scale)
+            else:
+                mark(op[1])
         ops.col2im3(pl.Zd, 32, nb, h, w, pl.dx_sm, mul=1.0, div_dev=scale, sgn=-1)
         ops.moments3(pl.dx_sm, lr, pl.sums[12:])
-        # --- tiny host-side (torch) assembly of the 1x1 MeanShift gradients
-        s = pl.sums
-        grads[g.add_mean.weight] = s[0:9].reshape(3, 3, 1, 1).clone()
-        grads[g.add_mean.bias] = s[9:12].clone()
-        grads[up4.bias] = am_wt @ s[9:12]
-        grads[g.sub_mean.weight] = s[12:21].reshape(3, 3, 1, 1).clone()
-        grads[g.sub_mean.bias] = s[21:24].clone()
+        grads[g.sub_mean.weight].view(-1).copy_(s[12:21])
+        grads[g.sub_mean.bias].copy_(s[21:24])
+        mark(self.param_list[0])
+        if mark_hi[0] != 0:
+            raise AssertionError("generator backward: gradient ranges did not cover the flat buffer")
+        if hook is not None and self.grad_hook_finish is not None:
+            # autograd may copy the gradient views when it accumulates them: the reduced values must be in place
+            self.grad_hook_finish()
         dlr = None
         if need_input_grad:
             sm_w = g.sub_mean.weight.detach().reshape(3, 3)

@@ -208,3 +208,26 @@ def moments3(a, b, sums12):
     assert c == 3 and a.is_contiguous() and b.is_contiguous()
     check(lib.pesr_moments3(_ptr(a), _ptr(b), nb, h * w, _ptr(sums12), _stream()), "pesr_moments3")
     return sums12
+
+
+def loss_l1(a, b, loss, grad=None):
+    check(lib.pesr_loss_l1(_ptr(a), _ptr(b), a.numel(), _ptr(loss), _ptr(grad), _stream()), "pesr_loss_l1")
+
+
+def loss_mse(a, b, loss, grad=None):
+    check(lib.pesr_loss_mse(_ptr(a), _ptr(b), a.numel(), _ptr(loss), _ptr(grad), _stream()), "pesr_loss_mse")
+
+
+def loss_tv(y, loss, grad=None):
+    h, w = y.shape[-2], y.shape[-1]
+    check(lib.pesr_loss_tv(_ptr(y), y.numel() // (h * w), h, w, _ptr(loss), _ptr(grad), _stream()), "pesr_loss_tv")
+
+
+def loss_gan(a, b, loss, sign_a=1.0, sign_b=-1.0, target=1.0, mode=0, gamma=1.0, grad_a=None, grad_b=None):
+    check(lib.pesr_loss_gan(_ptr(a), _ptr(b), a.numel(), sign_a, sign_b, target, mode, gamma, _ptr(loss),
+                            _ptr(grad_a), _ptr(grad_b), _stream()), "pesr_loss_gan")
+
+
+def adam_multi(table, nchunks, lr, beta1, beta2, eps, step, grad_mul=1.0):
+    check(lib.pesr_adam_multi(_ptr(table), nchunks, lr, beta1, beta2, eps, step, grad_mul, _stream()),
+          "pesr_adam_multi")

@@ -1,0 +1,99 @@
+"""Data parallelism: one process per GPU + NCCL gradient all-reduce over NVLink, replacing the
+reference's single-process nn.DataParallel (train.py:114-118).
+
+Semantics kept from nn.DataParallel: every replica sees an equal shard of the batch, BatchNorm
+statistics are per replica, and the optimiser sees the gradient of the global-batch loss: mean losses
+become the average of the per-rank gradients; the TV term, a batch SUM in the reference
+(train.py:137-140), is multiplied by world_size before averaging (pesr_b200.steps.gan_step).
+
+Overlap: the Generator / Discriminator schedules emit their parameter gradients into one flat fp32
+buffer that completes from its end towards its start; each completed range is handed to
+``_on_range``, which launches ncclAllReduce(AVG) for every full bucket on a side stream while the
+remaining backward kernels keep the SMs busy.  The last (smallest) bucket is the only exposed one.
+"""
+import torch
+import torch.distributed as dist
+
+
+class DataParallel(torch.nn.Module):
+    """Wraps a pesr_b200 network; exposes ``.module`` like nn.DataParallel (train.py:303,309)."""
+
+    def __init__(self, module, process_group=None, bucket_mb=32):
+        super().__init__()
+        self.module = module
+        self.pg = process_group
+        self.world_size = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.bucket_elems = int(bucket_mb * (1 << 20) // 4)
+        self._pending = None      # (lo, hi, flat) accumulated, not yet reduced
+        self._works = []
+        self._comm_stream = None
+        if self.world_size > 1:
+            self._broadcast_parameters()
+            eng = getattr(module, "engine", None)
+            if callable(eng):
+                e = module.engine()
+                e.grad_hook = self._on_range
+                e.grad_hook_finish = self.finish
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    def _broadcast_parameters(self):
+        with torch.no_grad():
+            for t in list(self.module.parameters()) + list(self.module.buffers()):
+                dist.broadcast(t, src=0, group=self.pg)
+
+    # ---- called by the kernel schedules during backward
+    def _on_range(self, lo, hi, flat):
+        if self._pending is None:
+            self._pending = [lo, hi, flat]
+        else:
+            self._pending[0] = lo
+        if self._pending[1] - self._pending[0] >= self.bucket_elems:
+            self._flush()
+
+    def _flush(self):
+        if self._pending is None:
+            return
+        lo, hi, flat = self._pending
+        self._pending = None
+        if self.world_size == 1 or hi <= lo:
+            return
+        if flat.is_cuda:
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream()
+            ev = torch.cuda.Event()
+            ev.record()
+            self._comm_stream.wait_event(ev)
+            with torch.cuda.stream(self._comm_stream):
+                dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.AVG, group=self.pg)
+                done = torch.cuda.Event()
+                done.record()
+            self._works.append(done)
+        else:  # gloo (CPU tests): no AVG op, no streams
+            w = dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            self._works.append((w, flat, lo, hi))
+
+    def finish(self):
+        """Make the current stream wait for every outstanding bucket (call before optimizer.step())."""
+        self._flush()
+        for w in self._works:
+            if isinstance(w, tuple):
+                work, flat, lo, hi = w
+                work.wait()
+                flat[lo:hi].div_(self.world_size)
+            else:
+                torch.cuda.current_stream().wait_event(w)
+        self._works = []
+
+    # ---- fallback for modules without a flat-gradient schedule
+    def allreduce_grads(self):
+        if self.world_size == 1:
+            return
+        grads = [p.grad for p in self.module.parameters() if p.grad is not None]
+        for g in grads:
+            if g.is_cuda:
+                dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.pg)
+            else:
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
+                g.div_(self.world_size)

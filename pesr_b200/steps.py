@@ -1,0 +1,77 @@
+"""The reference's step bodies (train.py:164-176 pretrain, train.py:202-266 GAN) over the B200 modules.
+
+These are what train.py's loops call once per batch; bench.py times exactly these functions.
+Losses stay on the device: callers read them back when they want to log (train.py reads five scalars
+per iteration, train.py:262-266 -- here that is one optional stacked copy)."""
+import torch
+
+from . import losses
+
+
+def pretrain_step(G, optim_G, lr, hr, ddp=None):
+    """train.py:168-173: sr = G(lr); zero_grad; L1; backward; Adam step.  Returns the loss tensor."""
+    sr = G(lr)
+    optim_G.zero_grad(set_to_none=True)
+    loss = losses.l1_loss(sr, hr)
+    loss.backward()
+    if ddp is not None:
+        ddp.finish()
+    optim_G.step()
+    return loss
+
+
+def gan_step(G, D, vgg, optim_G, optim_D, lr, hr, cfg, ddp_g=None, ddp_d=None):
+    """train.py:202-259 with the defaults of train.py:64-76 (RSGAN + focal loss).  ``cfg`` carries
+    alpha_l1, alpha_vgg, alpha_gan, alpha_tv, fl_gamma, gan_type, focal_loss, target_real, target_fake.
+    Returns the five scalars of train.py:262-266 as device tensors."""
+    t_real, t_fake = cfg['target_real'], cfg['target_fake']
+    # ---- Discriminator phase (train.py:202-229)
+    for p in D.parameters():
+        p.requires_grad = True
+    optim_D.zero_grad(set_to_none=True)
+    pred_real = D(hr)
+    sr = G(lr)
+    pred_fake = D(sr.detach())
+    if cfg['gan_type'] == 'SGAN':
+        bce = losses.BCEWithLogitsLoss()
+        total_D_loss = bce(pred_real, t_real) + bce(pred_fake, t_fake)
+    else:
+        total_D_loss = losses.rsgan_bce(pred_real, pred_fake, t_real)
+    total_D_loss.backward()
+    if ddp_d is not None:
+        ddp_d.finish()
+    optim_D.step()
+    # ---- Generator phase (train.py:234-259)
+    for p in D.parameters():
+        p.requires_grad = False
+    optim_G.zero_grad(set_to_none=True)
+    pred_fake = D(sr)
+    pred_real = D(hr)
+    l1_loss = losses.l1_loss(sr, hr) * cfg['alpha_l1']
+    f_sr, f_hr = vgg(sr, hr)
+    vgg_loss = losses.mse_loss(f_sr, f_hr) * cfg['alpha_vgg']
+    tv_scale = cfg['alpha_tv'] * (ddp_g.world_size if ddp_g is not None else 1)  # TV is a batch SUM (train.py:137-140)
+    tv_loss = losses.tv_loss(sr) * tv_scale
+    if cfg['gan_type'] == 'SGAN':
+        if cfg['focal_loss']:
+            G_loss = losses._GanLoss.apply(pred_fake, None, 1.0, 0.0, losses._uniform_target(t_real), 1,
+                                           float(cfg['fl_gamma']))
+        else:
+            G_loss = losses.BCEWithLogitsLoss()(pred_fake, t_real)
+    else:
+        if cfg['focal_loss']:
+            G_loss = losses.rsgan_focal(pred_fake, pred_real, cfg['fl_gamma'], t_real)
+        else:
+            G_loss = losses.rsgan_bce(pred_fake, pred_real, t_real)
+    G_loss = G_loss * cfg['alpha_gan']
+    total_G_loss = l1_loss + vgg_loss + G_loss + tv_loss
+    total_G_loss.backward()
+    if ddp_g is not None:
+        ddp_g.finish()
+    optim_G.step()
+    return torch.stack([l1_loss.detach(), vgg_loss.detach(), G_loss.detach(), tv_loss.detach() / max(1, (ddp_g.world_size if ddp_g is not None else 1)),
+                        total_D_loss.detach()])
+
+
+DEFAULT_GAN_CFG = dict(alpha_l1=0.0, alpha_vgg=50.0, alpha_gan=1.0, alpha_tv=1e-6, fl_gamma=1.0, gan_type='RSGAN',
+                       focal_loss=True)

@@ -103,6 +103,8 @@ typedef struct pesr_conv_desc {
   int32_t out_h, out_w;     /* out16 pixel grid (NORMAL mode; 0 = same as h, w) */
   int32_t out_sy, out_sx, out_oy, out_ox, out_coff;
   int32_t ps_c;             /* SHUFFLE2: channels of the shuffled tensor (cout/4) */
+  int32_t aux_mode;         /* 0: res32/res16/mask16/out32 are indexed by the GEMM pixel; 1: by the NORMAL-mode
+                               output pixel (n, h*sy+oy, w*sx+ox) of the out_h x out_w grid (stride-2 dgrad) */
 } pesr_conv_desc;
 
 int pesr_conv_igemm(const pesr_conv_desc* d, void* stream);
@@ -168,11 +170,14 @@ int pesr_pack_weights(const float* w_oihw, int32_t co, int32_t ci, int32_t ksize
  * affine(src)[c] at pixel p + sgn*(ky-1, kx-1), zero outside the image; columns 27..63 are zero.
  * affine: v = A(3x3, row-major [out][in]) * src + b, applied to in-bounds pixels only (this is how
  * MeanShift, model/basic.py:9-17, composes with the zero padding of the following conv); A/b NULL =
- * identity.  mul_dev: optional device scalar multiplied into the result (gradient scaling).
+ * identity.  pad_affine = 1 instead applies the affine to the padded zeros too (out-of-image taps read b): a
+ * constant shift of the conv input, used to centre the 0..255 image ahead of the Discriminator's first
+ * conv + BatchNorm (which is invariant to it).  mul_dev: optional device scalar multiplied into the result.
  * Feeds the Cin=3 convs (model/pesr.py:23,54; vgg19.features[0]) and, with sgn=-1, the backward of
  * the Cout=3 conv (model/basic.py:60). */
 int pesr_im2col3(const float* src_nchw, int32_t nb, int32_t h, int32_t w, const float* affine_a,
-                 const float* affine_b, const float* mul_dev, int32_t sgn, int32_t dtype, void* col, void* stream);
+                 const float* affine_b, const float* mul_dev, int32_t sgn, int32_t pad_affine, int32_t dtype, void* col,
+                 void* stream);
 
 /* col2im for a 3-channel output: out[n][c][h][w] = affine( sum_tap z[p + sgn*(ky-1,kx-1)][tap*3+c] * mul + bias[c] ).
  * z is fp32 [nb*h*w][ldz].  pre (optional) receives the value before the affine (needed by the
@@ -220,6 +225,48 @@ int pesr_loss_gan(const float* a, const float* b, int32_t n, float sign_a, float
  * table_dev: nchunks rows of {p, g, m, v (device addresses), n} as int64; g is multiplied by grad_mul first. */
 int pesr_adam_multi(const int64_t* table_dev, int32_t nchunks, float lr, float beta1, float beta2, float eps,
                     int32_t step, float grad_mul, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Discriminator / VGG layer kernels (HBM-bound).
+ * ------------------------------------------------------------------------------------------------ */
+/* Train-mode BatchNorm2d statistics (model/basic.py:29): per-channel mean and 1/sqrt(biased var + eps) of the
+ * 16-bit NHWC tensor y[npix][c]; updates running_mean / running_var (unbiased) with `momentum` and increments
+ * num_batches_tracked when given.  running_mean_shift (optional, per channel) is added to the batch mean in the
+ * running_mean update only (y was produced from a constant-shifted input).  sums_ws: 2*c doubles, zero on entry,
+ * zero again on exit. */
+int pesr_bn_stats(const void* y16, int64_t npix, int32_t c, float eps, float momentum, double* sums_ws, float* mean,
+                  float* rstd, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                  const float* running_mean_shift, int32_t dtype, void* stream);
+/* a = LeakyReLU_slope(gamma * (y - mean) * rstd + beta)   (model/basic.py:29-30, model/pesr.py:47) */
+int pesr_bn_lrelu_fwd(const void* y16, int64_t npix, int32_t c, const float* mean, const float* rstd,
+                      const float* gamma, const float* beta, float slope, int32_t dtype, void* a16, void* stream);
+/* BatchNorm backward given dz = dL/d(bn output) (LeakyReLU' already applied by the producer):
+ *   dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)), dgamma = sum(dz*xhat), dbeta = sum(dz),
+ * the parameter gradients multiplied by grad_mul / (*grad_div_dev). */
+int pesr_bn_lrelu_bwd(const void* dz16, const void* y16, int64_t npix, int32_t c, const float* mean, const float* rstd,
+                      const float* gamma, double* sums_ws, float grad_mul, const float* grad_div_dev, int32_t dtype,
+                      void* dy16, float* dgamma, float* dbeta, void* stream);
+/* 2x2/2 max-pool (vgg19.features) on NHWC 16-bit; backward routes to the first maximum in scan order (PyTorch's
+ * tie rule) and, with relu_mask, multiplies by relu'(x). */
+int pesr_maxpool2_fwd(const void* x16, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t dtype, void* y16, void* stream);
+int pesr_maxpool2_bwd(const void* x16, const void* dy16, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t relu_mask,
+                      int32_t dtype, void* dx16, void* stream);
+/* Skinny Linear (nn.Linear, model/pesr.py:71,73) for nb <= 16 rows: weights [o][k] 16-bit streamed once per pass.
+ * fwd: out = act(x w^T + bias) (split-K partials in `workspace`, pesr_linear_workspace_floats floats);
+ * dgrad: dx32[nb][k] = dy w;  wgrad: dw[o][k] (+)= mul/(*div_dev) * dy^T x. */
+int64_t pesr_linear_workspace_floats(int32_t nb, int32_t k, int32_t o);
+int pesr_linear_skinny_fwd(const void* x16, const void* w16, const float* bias, int32_t nb, int32_t k, int32_t o,
+                           int32_t act, int32_t dtype, float* workspace, float* out32, void* out16, void* stream);
+int pesr_linear_skinny_dgrad(const float* dy, const void* w16, int32_t nb, int32_t k, int32_t o, int32_t dtype,
+                             float* dx32, void* stream);
+int pesr_linear_skinny_wgrad(const float* dy, const void* x16, int32_t nb, int32_t k, int32_t o, float mul,
+                             const float* div_dev, int32_t accumulate, int32_t dtype, float* dw, void* stream);
+int pesr_cast16(const float* src, int64_t n, int32_t dtype, void* dst, void* stream);
+/* features.view(N, -1) of model/pesr.py:79: NHWC 16-bit -> NCHW-flattened 16-bit, and its backward
+ * (fp32 NCHW-flat gradient * mul * (*mul_dev) * lrelu'(mask) -> NHWC 16-bit). */
+int pesr_flatten_nchw16(const void* src_nhwc16, int32_t nb, int32_t hw, int32_t c, void* dst, void* stream);
+int pesr_unflatten_nchw16(const float* src32_nchw, const void* mask_nhwc16, int32_t nb, int32_t hw, int32_t c, float mul,
+                          const float* mul_dev, float slope, int32_t dtype, void* dst_nhwc16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -167,7 +167,13 @@ def discriminator_forward(sd, x, eps=1e-5, qdtype=None, stats_out=None):
     """model/pesr.py:77-81 in train mode: BatchNorm uses the batch's own (biased) statistics
     (model/basic.py:29).  stats_out (list) receives per-layer (mean, biased var) for the running-stat update."""
     for i, (_cin, _cout, stride) in enumerate(D_CHANNELS):
-        y = F.conv2d(_qa(x, qdtype), _q(sd[f'features.{i}.0.weight'], qdtype), None, stride=stride, padding=1)
+        if qdtype is not None and i == 0:
+            # the B200 path feeds conv 0 the image minus 127.5 (padding included): BatchNorm cancels the shift
+            xin = F.pad(_qa(x - 127.5, qdtype), (1, 1, 1, 1), value=-127.5)
+            y = F.conv2d(xin, _q(sd['features.0.0.weight'], qdtype), None, stride=stride)
+        else:
+            y = F.conv2d(_qa(x, qdtype), _q(sd[f'features.{i}.0.weight'], qdtype), None, stride=stride, padding=1)
+        y = _qa(y, qdtype)   # the pre-BN tensor is stored in 16 bits by the B200 path
         mean = y.mean(dim=(0, 2, 3))
         var = y.var(dim=(0, 2, 3), unbiased=False)
         if stats_out is not None:

@@ -45,7 +45,7 @@ class ConvDesc(C.Structure):
         ("out16", C.c_void_p), ("ld_out16", C.c_int32),
         ("out_mode", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32),
         ("out_sy", C.c_int32), ("out_sx", C.c_int32), ("out_oy", C.c_int32), ("out_ox", C.c_int32),
-        ("out_coff", C.c_int32), ("ps_c", C.c_int32),
+        ("out_coff", C.c_int32), ("ps_c", C.c_int32), ("aux_mode", C.c_int32),
     ]
 
 
@@ -90,7 +90,7 @@ SIGNATURES = {
     "pesr_debug_wgrad_desc": (None, [C.c_int, C.c_int]),
     "pesr_wgrad_reduce": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp, _vp]),
     "pesr_pack_weights": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
-    "pesr_im2col3": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "pesr_im2col3": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "pesr_col2im3": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _vp]),
     "pesr_nchw32_to_nhwc16": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp]),
     "pesr_nhwc16_to_nchw32": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp, _vp]),
@@ -101,6 +101,18 @@ SIGNATURES = {
     "pesr_loss_mse": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "pesr_loss_tv": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "pesr_loss_gan": (C.c_int, [_vp, _vp, _i32, _f32, _f32, _f32, _i32, _f32, _vp, _vp, _vp, _vp]),
+    "pesr_bn_stats": (C.c_int, [_vp, _i64, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "pesr_bn_lrelu_fwd": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _i32, _vp, _vp]),
+    "pesr_bn_lrelu_bwd": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "pesr_maxpool2_fwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "pesr_maxpool2_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "pesr_linear_workspace_floats": (C.c_int64, [_i32, _i32, _i32]),
+    "pesr_linear_skinny_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "pesr_linear_skinny_dgrad": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "pesr_linear_skinny_wgrad": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _i32, _i32, _vp, _vp]),
+    "pesr_cast16": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "pesr_flatten_nchw16": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "pesr_unflatten_nchw16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _f32, _i32, _vp, _vp]),
     "pesr_adam_multi": (C.c_int, [_vp, _i32, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
 }
 

@@ -42,7 +42,7 @@ struct ConvK {
   const uint16_t* mask16; int ld_mask16; int mask_mode;
   float* out32; int ld_out32;
   uint16_t* out16; int ld_out16;
-  int out_mode, out_h, out_w, out_sy, out_sx, out_oy, out_ox, out_coff, ps_c;
+  int out_mode, out_h, out_w, out_sy, out_sx, out_oy, out_ox, out_coff, ps_c, aux_mode;
 };
 
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -163,7 +163,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       const int img = m_tile / (p.tiles_w * p.tiles_h);
       const int h = th * p.tile_h + ty, w = tw * p.tile_w + tx, n0 = n_tile * p.block_n;
       const bool valid = (h < p.h) && (w < p.w);
-      const long long pix = ((long long)img * p.h + h) * p.w + w;
+      // pixel index used by res32 / res16 / mask16 / out32: the GEMM grid, or (aux_mode 1) the strided output grid
+      const long long pix = p.aux_mode
+          ? ((long long)img * p.out_h + (h * p.out_sy + p.out_oy)) * p.out_w + (w * p.out_sx + p.out_ox)
+          : ((long long)img * p.h + h) * p.w + w;
 
       float* bs = bias_s + acc * 256;
       for (int i = et; i < p.block_n; i += 128) bs[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
@@ -349,6 +352,7 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d, void* stream_) {
   k.out_sy = d->out_sy > 0 ? d->out_sy : 1;
   k.out_sx = d->out_sx > 0 ? d->out_sx : 1;
   k.out_oy = d->out_oy; k.out_ox = d->out_ox; k.out_coff = d->out_coff; k.ps_c = d->ps_c;
+  k.aux_mode = d->aux_mode;
 
   // >= 120 KB of dynamic smem also guarantees one CTA per SM, so the 512-column TMEM allocation never contends.
   size_t smem = (size_t)k.stages * k.stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + 2 * 256 * sizeof(float);

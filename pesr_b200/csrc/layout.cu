@@ -76,8 +76,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int co, int ci,
 // im2col for 3-channel images: one thread per (pixel, 8-column chunk) -> one 16-byte store
 // ------------------------------------------------------------------------------------------
 __global__ void im2col3_kernel(const float* __restrict__ src, int nb, int h, int w, const float* __restrict__ aff_a,
-                               const float* __restrict__ aff_b, const float* __restrict__ mul_dev, int sgn, int bf,
-                               uint4* __restrict__ col) {
+                               const float* __restrict__ aff_b, const float* __restrict__ mul_dev, int sgn,
+                               int pad_affine, int bf, uint4* __restrict__ col) {
   const long long total = (long long)nb * h * w * 8;
   float A[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   float B[3] = {0, 0, 0};
@@ -109,6 +109,8 @@ __global__ void im2col3_kernel(const float* __restrict__ src, int nb, int h, int
             const long long off = (long long)yy * w + xx;
             const float s0 = __ldg(base + off), s1 = __ldg(base + plane + off), s2 = __ldg(base + 2 * plane + off);
             v = (A[c * 3] * s0 + A[c * 3 + 1] * s1 + A[c * 3 + 2] * s2 + B[c]) * mul;
+          } else if (pad_affine) {
+            v = B[c] * mul;  // the affine of a zero-padded pixel (a constant shift of the conv input)
           }
         }
         vals[j] = v;
@@ -334,14 +336,14 @@ extern "C" int pesr_pack_weights(const float* w, int32_t co, int32_t ci, int32_t
 }
 
 extern "C" int pesr_im2col3(const float* src, int32_t nb, int32_t h, int32_t w, const float* aff_a,
-                            const float* aff_b, const float* mul_dev, int32_t sgn, int32_t dtype, void* col,
-                            void* stream_) {
+                            const float* aff_b, const float* mul_dev, int32_t sgn, int32_t pad_affine, int32_t dtype,
+                            void* col, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PESR_CHECK_ARG(src && col && nb > 0 && h > 0 && w > 0, "im2col3: bad arguments");
   PESR_CHECK_ARG(sgn == 1 || sgn == -1, "im2col3: sgn must be +-1");
   const long long total = (long long)nb * h * w * 8;
-  im2col3_kernel<<<blocks_for(total, 256, 148 * 32), 256, 0, stream>>>(src, nb, h, w, aff_a, aff_b, mul_dev, sgn, dtype,
-                                                                      reinterpret_cast<uint4*>(col));
+  im2col3_kernel<<<blocks_for(total, 256, 148 * 32), 256, 0, stream>>>(src, nb, h, w, aff_a, aff_b, mul_dev, sgn,
+                                                                      pad_affine, dtype, reinterpret_cast<uint4*>(col));
   count_launch();
   PESR_CHECK_LAUNCH("im2col3");
   return 0;

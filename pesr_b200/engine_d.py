@@ -1,0 +1,375 @@
+"""Kernel schedule of the Discriminator (reference: model/pesr.py:40-81, model/basic.py:19-31).
+
+Eight (conv3x3 no-bias -> train-mode BatchNorm -> LeakyReLU 0.2) blocks, stride 1/2 alternating,
+NCHW flatten, Linear(512*s*s -> 1024), LeakyReLU, Linear(1024 -> 1).
+
+  * conv 0 (Cin = 3) is an im2col GEMM; stride-2 convs read the four parity planes of their input
+    through four TMA tensor maps (no strided gather); their backward-data is four parity sub-convolutions.
+  * BatchNorm uses the batch's own statistics of every call (the reference calls D four times per step on
+    different batches, train.py:205,208,237,238) and updates the running statistics each time.
+  * backward emits parameter gradients into one flat fp32 buffer, last parameter first (see engine_g).
+"""
+import ctypes as C
+
+import torch
+
+from . import ops
+from ._lib import check, lib
+from .engine_g import PackedWeight, _Plan, _run_conv
+from .ops import ACT_LRELU
+
+D_LAYERS = [(3, 64, 1), (64, 64, 2), (64, 128, 1), (128, 128, 2), (128, 256, 1), (256, 256, 2), (256, 512, 1),
+            (512, 512, 2)]   # model/pesr.py:53-66
+
+
+def _s2_taps():
+    """Taps of a stride-2, pad-1 3x3 conv expressed on the parity planes of its input."""
+    taps, srcs, widx = [], [], []
+    for dy in range(3):
+        for dx in range(3):
+            ph, pw = (dy + 1) % 2, (dx + 1) % 2
+            taps.append((-1 if dy == 0 else 0, -1 if dx == 0 else 0))
+            srcs.append(ph * 2 + pw)
+            widx.append(dy * 3 + dx)
+    return taps, srcs, widx
+
+
+def _parity_planes(t, nb, h, w, c):
+    """Four NHWC views (ptr, h2, w2, sn, sh, sw) of t[nb][h][w][c]: plane (ph, pw) holds pixels (2a+ph, 2b+pw)."""
+    es = t.element_size()
+    out = []
+    for ph in range(2):
+        for pw in range(2):
+            out.append((t.data_ptr() + (ph * w + pw) * c * es, (h - ph + 1) // 2, (w - pw + 1) // 2,
+                        h * w * c, 2 * w * c, 2 * c))
+    return out
+
+
+class _Release:
+    """Returns a plan instance to its pool when the autograd node that holds it dies."""
+
+    def __init__(self, plan):
+        self.plan = plan
+
+    def __del__(self):
+        self.plan.busy = False
+
+
+class DiscriminatorEngine:
+    def __init__(self, disc, dtype=torch.float16):
+        self.disc = disc
+        self.dtype = dtype
+        self.dt = ops.dt_code(dtype)
+        self.pools = {}
+        self.packed = None
+        self.device = None
+        self.grad_hook = None
+        self.grad_hook_finish = None
+        self.param_list = None
+
+    # ------------------------------------------------------------------ parameters
+    def _ensure_packed(self, device):
+        d = self.disc
+        sentinel = (d.features[0][0].weight.data_ptr(), d.classifier[2].bias.data_ptr())
+        if self.packed is not None and self.device == device and self.sentinel == sentinel:
+            return
+        self.sentinel, self.device, self.pools = sentinel, device, {}
+        dt = self.dtype
+        pk = {"c0_f": PackedWeight(d.features[0][0].weight, 4, dt, pad_to=64),
+              "c0_d": PackedWeight(d.features[0][0].weight, 6, dt, pad_to=32)}
+        for i in range(1, 8):
+            pk[f"c{i}_f"] = PackedWeight(d.features[i][0].weight, 0, dt)
+            pk[f"c{i}_d"] = PackedWeight(d.features[i][0].weight, 1, dt)
+        self.packed = pk
+        self.fwd_packs = [v for k, v in pk.items() if k.endswith("_f")]
+        self.bwd_packs = [v for k, v in pk.items() if k.endswith("_d")]
+        fc1, fc2 = d.classifier[0], d.classifier[2]
+        self.w1_16 = torch.empty(fc1.weight.shape, device=device, dtype=dt)
+        self.w2_16 = torch.empty(fc2.weight.shape, device=device, dtype=dt)
+        self.fc_key = None
+        # conv 0 sees the image minus IMG_SHIFT (applied to the padding too, so conv0' = conv0 - IMG_SHIFT*sum(w)
+        # exactly): train-mode BatchNorm is invariant to that per-channel constant, and the 16-bit pre-BN tensor
+        # no longer carries a mean several times its standard deviation.
+        self.img_shift = torch.full((3,), -127.5, device=device, dtype=torch.float32)
+        self.c0_shift = torch.zeros(64, device=device, dtype=torch.float32)
+        self.c0_key = None
+        self.scale_ws = torch.zeros(4, device=device, dtype=torch.float32)
+        self.bn_ws = torch.zeros(2 * 512, device=device, dtype=torch.float64)
+        self.offsets, off = {}, 0
+        for p in self.param_list:
+            self.offsets[p] = off
+            off += (p.numel() + 3) // 4 * 4
+        self.flat_numel = off
+
+    def _pack_fc(self):
+        fc1, fc2 = self.disc.classifier[0], self.disc.classifier[2]
+        key = (fc1.weight.data_ptr(), fc1.weight._version, fc2.weight._version)
+        if key != self.fc_key:
+            ops.cast16(fc1.weight.detach(), self.w1_16)
+            ops.cast16(fc2.weight.detach(), self.w2_16)
+            self.fc_key = key
+
+    # ------------------------------------------------------------------ plans
+    def _geometry(self, h, w):
+        dims = []
+        for (_ci, _co, s) in D_LAYERS:
+            if s == 2:
+                h, w = (h + 1) // 2, (w + 1) // 2
+            dims.append((h, w))
+        return dims
+
+    def _new_plan(self, nb, h, w):
+        d = self.disc
+        dev, tdt, dt, pk = self.device, self.dtype, self.dt, self.packed
+        pl = _Plan()
+        pl.nb, pl.h, pl.w, pl.busy, pl.generation = nb, h, w, False, 0
+        dims = self._geometry(h, w)
+        pl.dims = dims
+        e16 = lambda *s: torch.empty(*s, device=dev, dtype=tdt)  # noqa: E731
+        e32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        pl.col0 = e16(nb * h * w, 64)
+        pl.Y = [e16(nb * hh * ww, co) for (hh, ww), (_ci, co, _s) in zip(dims, D_LAYERS)]
+        pl.A = [e16(nb * hh * ww, co) for (hh, ww), (_ci, co, _s) in zip(dims, D_LAYERS)]
+        pl.mean = [e32(co) for (_ci, co, _s) in D_LAYERS]
+        pl.rstd = [e32(co) for (_ci, co, _s) in D_LAYERS]
+        h7, w7 = dims[7]
+        kfc = 512 * h7 * w7
+        fc1, fc2 = d.classifier[0], d.classifier[2]
+        if kfc != fc1.in_features:
+            raise RuntimeError(f"pesr_b200.Discriminator: a {h}x{w} input gives {kfc} features but classifier.0 expects "
+                               f"{fc1.in_features} (patch_size {d.patch_size}): size mismatch")
+        pl.kfc = kfc
+        pl.flat7 = e16(nb, kfc)
+        pl.h1_32, pl.h1_16 = e32(nb, 1024), e16(nb, 1024)
+        pl.fc_ws = e32(max(ops.linear_workspace_floats(nb, kfc, 1024), ops.linear_workspace_floats(nb, 1024, 1), 1))
+        taps2, srcs2, widx2 = _s2_taps()
+        f = []
+        f.append(ops.make_conv_desc(dtype=dt, nb=nb, h=h, w=w, cin=64, cout=64, taps=[(0, 0)],
+                                    srcs=[ops.nhwc_src(pl.col0, nb, h, w, 64)], wpacked=pk["c0_f"].buf,
+                                    out16=pl.Y[0], ld_out16=64))
+        for i in range(1, 8):
+            ci, co, s = D_LAYERS[i]
+            hi, wi = dims[i - 1]
+            ho, wo = dims[i]
+            if s == 1:
+                f.append(ops.make_conv_desc(dtype=dt, nb=nb, h=ho, w=wo, cin=ci, cout=co,
+                                            srcs=[ops.nhwc_src(pl.A[i - 1], nb, hi, wi, ci)], wpacked=pk[f"c{i}_f"].buf,
+                                            out16=pl.Y[i], ld_out16=co))
+            else:
+                f.append(ops.make_conv_desc(dtype=dt, nb=nb, h=ho, w=wo, cin=ci, cout=co, taps=taps2, tap_src=srcs2,
+                                            tap_widx=widx2, srcs=_parity_planes(pl.A[i - 1], nb, hi, wi, ci),
+                                            wpacked=pk[f"c{i}_f"].buf, out16=pl.Y[i], ld_out16=co))
+        pl.fwd = f
+        return pl
+
+    def _bwd_scratch(self, nb, h, w):
+        key = ("bwd", nb, h, w)
+        sc = self.pools.get(key)
+        if sc is None:
+            dev, tdt = self.device, self.dtype
+            dims = self._geometry(h, w)
+            sc = _Plan()
+            sc.dZ = [torch.empty(nb * hh * ww, co, device=dev, dtype=tdt) for (hh, ww), (_ci, co, _s) in zip(dims, D_LAYERS)]
+            sc.dY = [torch.empty(nb * hh * ww, co, device=dev, dtype=tdt) for (hh, ww), (_ci, co, _s) in zip(dims, D_LAYERS)]
+            h7, w7 = dims[7]
+            sc.dflat32 = torch.empty(nb, 512 * h7 * w7, device=dev, dtype=torch.float32)
+            sc.dh1 = torch.empty(nb, 1024, device=dev, dtype=torch.float32)
+            sc.Zd = torch.empty(nb * h * w, 32, device=dev, dtype=torch.float32)
+            sc.wg = torch.empty(max(9 * 512 * 512 * 4, 148 * 128 * 64), device=dev, dtype=torch.float32)
+            sc.descs = {}
+            self.pools[key] = sc
+        return sc
+
+    def _bwd_descs(self, pl, sc):
+        """dgrad / wgrad descriptors binding plan instance `pl` to the shared backward scratch `sc`."""
+        got = sc.descs.get(id(pl))
+        if got is not None:
+            return got
+        dt, pk, nb = self.dt, self.packed, pl.nb
+        dims = pl.dims
+        dg, wg = {}, {}
+        for i in range(7, 0, -1):
+            ci, co, s = D_LAYERS[i]
+            hi, wi = dims[i - 1]
+            ho, wo = dims[i]
+            if s == 1:
+                dg[i] = [ops.make_conv_desc(dtype=dt, nb=nb, h=hi, w=wi, cin=co, cout=ci,
+                                            srcs=[ops.nhwc_src(sc.dY[i], nb, ho, wo, co)], wpacked=pk[f"c{i}_d"].buf,
+                                            mask16=pl.A[i - 1], ld_mask16=ci, mask_mode=2, out16=sc.dZ[i - 1],
+                                            ld_out16=ci)]
+                wg[i] = ops.make_wgrad_desc(dtype=dt, nb=nb, h=ho, w=wo, a=sc.dY[i], a_c=co, m_total=co,
+                                            b_srcs=[ops.nhwc_src(pl.A[i - 1], nb, hi, wi, ci)], n_total=ci,
+                                            partials=sc.wg)
+            else:
+                lst = []
+                for ph in range(2):
+                    for pw in range(2):
+                        gh, gw = (hi - ph + 1) // 2, (wi - pw + 1) // 2
+                        if gh == 0 or gw == 0:
+                            continue
+                        ys = [(1, 0)] if ph == 0 else [(0, 1), (2, 0)]     # (dy, offset into dY rows)
+                        xs = [(1, 0)] if pw == 0 else [(0, 1), (2, 0)]
+                        taps = [(oy, ox) for (dy, oy) in ys for (dx, ox) in xs]
+                        widx = [8 - (dy * 3 + dx) for (dy, oy) in ys for (dx, ox) in xs]   # mode-1 rows are tap-flipped
+                        lst.append(ops.make_conv_desc(
+                            dtype=dt, nb=nb, h=gh, w=gw, cin=co, cout=ci, taps=taps, tap_widx=widx,
+                            srcs=[ops.nhwc_src(sc.dY[i], nb, ho, wo, co)], wpacked=pk[f"c{i}_d"].buf,
+                            mask16=pl.A[i - 1], ld_mask16=ci, mask_mode=2, out16=sc.dZ[i - 1], ld_out16=ci,
+                            out_h=hi, out_w=wi, out_sy=2, out_sx=2, out_oy=ph, out_ox=pw, aux_mode=1))
+                dg[i] = lst
+                taps2, srcs2, _ = _s2_taps()
+                wg[i] = ops.make_wgrad_desc(dtype=dt, nb=nb, h=ho, w=wo, a=sc.dY[i], a_c=co, m_total=co,
+                                            b_srcs=_parity_planes(pl.A[i - 1], nb, hi, wi, ci), n_total=ci, taps=taps2,
+                                            tap_src=srcs2, partials=sc.wg)
+        h, w = pl.h, pl.w
+        wg[0] = ops.make_wgrad_desc(dtype=dt, nb=nb, h=h, w=w, a=sc.dY[0], a_c=64, m_total=64,
+                                    b_srcs=[ops.nhwc_src(pl.col0, nb, h, w, 64)], n_total=64, taps=[(0, 0)],
+                                    partials=sc.wg)
+        dg[0] = [ops.make_conv_desc(dtype=dt, nb=nb, h=h, w=w, cin=64, cout=32, taps=[(0, 0)],
+                                    srcs=[ops.nhwc_src(sc.dY[0], nb, h, w, 64)], wpacked=pk["c0_d"].buf, out32=sc.Zd,
+                                    ld_out32=32)]
+        sc.descs[id(pl)] = (dg, wg)
+        return dg, wg
+
+    def _acquire(self, nb, h, w):
+        pool = self.pools.setdefault((nb, h, w), [])
+        for pl in pool:
+            if not pl.busy:
+                return pl
+        if len(pool) >= 8:
+            raise RuntimeError("pesr_b200.Discriminator: more than 8 live autograd graphs of one input shape")
+        pl = self._new_plan(nb, h, w)
+        pool.append(pl)
+        return pl
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, save):
+        d = self.disc
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"Discriminator expects [N,3,H,W], got {tuple(x.shape)}")
+        x = x.contiguous().float()
+        nb, _, h, w = x.shape
+        if nb > 16:
+            raise NotImplementedError("pesr_b200.Discriminator: per-call batch is limited to 16 (train.py:48 default)")
+        self._ensure_packed(x.device)
+        pl = self._acquire(nb, h, w)
+        for pw in self.fwd_packs:
+            pw.get()
+        self._pack_fc()
+        training = d.training
+        w0 = d.features[0][0].weight
+        if (w0.data_ptr(), w0._version) != self.c0_key:
+            torch.mul(w0.detach().sum(dim=(1, 2, 3)), 127.5, out=self.c0_shift)
+            self.c0_key = (w0.data_ptr(), w0._version)
+        ops.im2col3(x, pl.col0, affine_b=self.img_shift, pad_affine=True)
+        stream = torch.cuda.current_stream().cuda_stream
+        for i in range(8):
+            _run_conv(pl.fwd[i], stream)
+            bn = d.features[i][1]
+            hh, ww = pl.dims[i]
+            npix, co = nb * hh * ww, D_LAYERS[i][1]
+            if training:
+                ops.bn_stats(pl.Y[i], npix, co, self.bn_ws, pl.mean[i], pl.rstd[i], bn.running_mean, bn.running_var,
+                             bn.num_batches_tracked, eps=bn.eps, momentum=bn.momentum,
+                             running_mean_shift=self.c0_shift if i == 0 else None)
+            else:
+                pl.mean[i].copy_(bn.running_mean - self.c0_shift if i == 0 else bn.running_mean)
+                pl.rstd[i].copy_(torch.rsqrt(bn.running_var + bn.eps))
+            ops.bn_lrelu_fwd(pl.Y[i], npix, co, pl.mean[i], pl.rstd[i], bn.weight.detach(), bn.bias.detach(), pl.A[i])
+        h7, w7 = pl.dims[7]
+        ops.flatten_nchw16(pl.A[7], nb, h7 * w7, 512, pl.flat7)
+        fc1, fc2 = d.classifier[0], d.classifier[2]
+        ops.linear_fwd(pl.flat7, self.w1_16, fc1.bias.detach(), nb, pl.kfc, 1024, pl.fc_ws, out32=pl.h1_32,
+                       out16=pl.h1_16, act=ACT_LRELU)
+        logits = torch.empty(nb, 1, device=x.device, dtype=torch.float32)
+        ops.linear_fwd(pl.h1_16, self.w2_16, fc2.bias.detach(), nb, 1024, 1, pl.fc_ws, out32=logits)
+        if save:
+            if not training:
+                raise NotImplementedError("pesr_b200.Discriminator: backward in eval() mode is not on the PESR path")
+            pl.busy = True
+            pl.generation += 1
+            return logits, (pl, _Release(pl), x)
+        return logits, None
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, state, dlogits, need_param_grads, need_input_grad):
+        pl, _rel, x = state
+        d = self.disc
+        nb, h, w = pl.nb, pl.h, pl.w
+        sc = self._bwd_scratch(nb, h, w)
+        for pw in self.bwd_packs:
+            pw.get()
+        dg, wg = self._bwd_descs(pl, sc)
+        dev = dlogits.device
+        dlogits = dlogits.contiguous().float()
+        fc1, fc2 = d.classifier[0], d.classifier[2]
+        stream = torch.cuda.current_stream().cuda_stream
+        scale = self.scale_ws[1:2]
+        grads, flat, hook = {}, None, None
+        off = self.offsets
+        mark_hi = [self.flat_numel]
+        if need_param_grads:
+            flat = torch.empty(self.flat_numel, device=dev, dtype=torch.float32)
+            grads = {p: flat[off[p]:off[p] + p.numel()].view(p.shape) for p in self.param_list}
+            hook = self.grad_hook
+
+        def mark(param):
+            lo = off[param]
+            if hook is not None and lo < mark_hi[0]:
+                hook(lo, mark_hi[0], flat)
+            mark_hi[0] = lo
+
+        # ---- classifier (fp32 gradients, 16-bit operands)
+        if need_param_grads:
+            ops.linear_wgrad(dlogits, pl.h1_16, nb, 1024, 1, grads[fc2.weight])
+            torch.sum(dlogits, dim=0, out=grads[fc2.bias])
+            mark(fc2.weight)
+        ops.linear_dgrad(dlogits, self.w2_16, nb, 1024, 1, sc.dh1)
+        dz1 = sc.dh1 * torch.where(pl.h1_32 > 0, 1.0, 0.2)      # LeakyReLU'(h1), a 16x1024 tensor
+        if need_param_grads:
+            ops.linear_wgrad(dz1, pl.flat7, nb, pl.kfc, 1024, grads[fc1.weight])
+            torch.sum(dz1, dim=0, out=grads[fc1.bias])
+            mark(fc1.weight)
+        ops.linear_dgrad(dz1, self.w1_16, nb, pl.kfc, 1024, sc.dflat32)
+        ops.amax_scale(sc.dflat32, self.scale_ws, target=16.0)
+        h7, w7 = pl.dims[7]
+        ops.unflatten_nchw16(sc.dflat32, pl.A[7], nb, h7 * w7, 512, sc.dZ[7], mul_dev=scale)
+        splits = C.c_int32(0)
+        dummy = None
+        for i in range(7, -1, -1):
+            ci, co, s = D_LAYERS[i]
+            hh, ww = pl.dims[i]
+            npix = nb * hh * ww
+            bn, conv = d.features[i][1], d.features[i][0]
+            if need_param_grads:
+                dgam, dbet = grads[bn.weight], grads[bn.bias]
+            else:
+                if dummy is None:
+                    dummy = torch.empty(2 * 512, device=dev, dtype=torch.float32)
+                dgam, dbet = dummy[:co], dummy[512:512 + co]
+            ops.bn_lrelu_bwd(sc.dZ[i], pl.Y[i], npix, co, pl.mean[i], pl.rstd[i], bn.weight.detach(), self.bn_ws,
+                             sc.dY[i], dgam, dbet, grad_div_dev=scale)
+            if need_param_grads:
+                check(lib.pesr_conv_wgrad(C.byref(wg[i]), C.byref(splits), stream), "pesr_conv_wgrad")
+                if i == 0:
+                    check(lib.pesr_wgrad_reduce(sc.wg.data_ptr(), splits.value, 1, 64, 64, ops.WMAP_COL_IN, 64, 3, 1.0,
+                                                scale.data_ptr(), 0, grads[conv.weight].data_ptr(), stream),
+                          "pesr_wgrad_reduce")
+                else:
+                    check(lib.pesr_wgrad_reduce(sc.wg.data_ptr(), splits.value, 9, co, ci, ops.WMAP_OIHW, co, ci, 1.0,
+                                                scale.data_ptr(), 0, grads[conv.weight].data_ptr(), stream),
+                          "pesr_wgrad_reduce")
+                mark(conv.weight)
+            if i > 0 or need_input_grad:
+                for dsc in dg[i]:
+                    _run_conv(dsc, stream)
+        dx = None
+        if need_input_grad:
+            dx = torch.empty_like(x)
+            ops.col2im3(sc.Zd, 32, nb, h, w, dx, mul=1.0, div_dev=scale, sgn=-1)
+        if need_param_grads:
+            if mark_hi[0] != 0:
+                raise AssertionError("discriminator backward: gradient ranges did not cover the flat buffer")
+            if hook is not None and self.grad_hook_finish is not None:
+                self.grad_hook_finish()
+        return grads, dx

@@ -9,7 +9,9 @@ import torch.nn as nn  # noqa: F401
 import torch.nn.functional as F  # noqa: F401
 
 from .basic import BasicBlock, Conv, MeanShift, ResBlock, Upsampler  # noqa: F401
-from .pesr import Generator  # noqa: F401
+from .focal_loss import FocalLoss  # noqa: F401
+from .pesr import Discriminator, Generator  # noqa: F401
+from .vgg import VGG  # noqa: F401
 
 try:  # torchvision is only needed for the name the reference leaks (`models`); VGG itself does not use it
     import torchvision.models as models  # noqa: F401

@@ -67,3 +67,64 @@ class Generator(nn.Module):
         _require_cuda(x, "Generator")
         eng = self.engine()
         return _GeneratorFn.apply(eng, x, *eng.param_list)
+
+
+class _DiscriminatorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, x, *params):
+        need = any(ctx.needs_input_grad)
+        logits, state = engine.forward(x, save=need)
+        ctx.engine, ctx.state = engine, state
+        return logits
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dlogits):
+        eng = ctx.engine
+        need_params = any(ctx.needs_input_grad[2:])
+        grads, dx = eng.backward(ctx.state, dlogits, need_param_grads=need_params,
+                                 need_input_grad=ctx.needs_input_grad[1])
+        ctx.state = None
+        out = [None, dx]
+        for i, p in enumerate(eng.param_list):
+            out.append(grads.get(p) if ctx.needs_input_grad[2 + i] else None)
+        return tuple(out)
+
+
+class Discriminator(nn.Module):
+    """model/pesr.py:40-81: eight conv-BN-LeakyReLU blocks (64 -> 512 channels, stride 1/2 alternating), NCHW
+    flatten, Linear(512*(patch/4)^2 -> 1024), LeakyReLU, Linear(1024 -> 1).  ``opt`` keys: patch_size,
+    spectral_norm (True raises NameError exactly as the reference does, model/basic.py:25)."""
+
+    def __init__(self, opt, dtype=torch.float16):
+        nn.Module.__init__(self)
+        act = nn.LeakyReLU(negative_slope=0.2, inplace=True)
+        self.patch_size = opt['patch_size']
+        sn = opt['spectral_norm']
+        in_channels, out_channels, depth = 3, 64, 7
+        blocks = [BasicBlock(3, out_channels, 3, bn=True, act=act, sn=sn)]
+        for i in range(depth):
+            in_channels = out_channels
+            if i % 2 == 1:
+                stride = 1
+                out_channels *= 2
+            else:
+                stride = 2
+            blocks.append(BasicBlock(in_channels, out_channels, 3, stride=stride, bn=True, act=act, sn=sn))
+        self.features = nn.Sequential(*blocks)
+        side = self.patch_size * 4 // (2 ** ((depth + 1) // 2))
+        self.classifier = nn.Sequential(nn.Linear(out_channels * side ** 2, 1024), act, nn.Linear(1024, 1))
+        self._compute_dtype = dtype
+        self._engine = None
+
+    def engine(self):
+        if self._engine is None:
+            from ..engine_d import DiscriminatorEngine
+            self._engine = DiscriminatorEngine(self, self._compute_dtype)
+            self._engine.param_list = list(self.parameters())
+        return self._engine
+
+    def forward(self, x):
+        _require_cuda(x, "Discriminator")
+        eng = self.engine()
+        return _DiscriminatorFn.apply(eng, x, *eng.param_list)

@@ -49,7 +49,7 @@ def make_conv_desc(*, dtype, nb, h, w, cin, cout, block_n=None, taps=TAPS_3X3, t
                    srcs, wpacked, bias=None, alpha=1.0, alpha_dev=None, res32=None, ld_res32=0, res16=None,
                    ld_res16=0, act=ACT_NONE, mask16=None, ld_mask16=0, mask_mode=0, out32=None, ld_out32=0,
                    out16=None, ld_out16=0, out_mode=OUT_NORMAL, out_h=0, out_w=0, out_sy=1, out_sx=1, out_oy=0,
-                   out_ox=0, out_coff=0, ps_c=0, tile=None):
+                   out_ox=0, out_coff=0, ps_c=0, tile=None, aux_mode=0):
     """Build a ``pesr_conv_desc``.
 
     ``srcs`` is a list of (tensor_or_ptr, src_h, src_w, stride_n, stride_h, stride_w) NHWC views (element
@@ -84,6 +84,7 @@ def make_conv_desc(*, dtype, nb, h, w, cin, cout, block_n=None, taps=TAPS_3X3, t
     d.out16, d.ld_out16 = _ptr(out16), ld_out16
     d.out_mode, d.out_h, d.out_w = out_mode, out_h, out_w
     d.out_sy, d.out_sx, d.out_oy, d.out_ox, d.out_coff, d.ps_c = out_sy, out_sx, out_oy, out_ox, out_coff, ps_c
+    d.aux_mode = aux_mode
     return d
 
 
@@ -158,12 +159,12 @@ def packed_shape(co, ci, ksize, mode, pad_to=0):
     raise ValueError(mode)
 
 
-def im2col3(src, col, affine_a=None, affine_b=None, mul_dev=None, sgn=1):
+def im2col3(src, col, affine_a=None, affine_b=None, mul_dev=None, sgn=1, pad_affine=False):
     _need_cuda(src, col)
     nb, c, h, w = src.shape
     assert c == 3 and src.dtype == torch.float32 and src.is_contiguous()
     check(lib.pesr_im2col3(_ptr(src), nb, h, w, _ptr(affine_a), _ptr(affine_b), _ptr(mul_dev), sgn,
-                           dt_code(col.dtype), _ptr(col), _stream()), "pesr_im2col3")
+                           1 if pad_affine else 0, dt_code(col.dtype), _ptr(col), _stream()), "pesr_im2col3")
     return col
 
 
@@ -231,3 +232,62 @@ def loss_gan(a, b, loss, sign_a=1.0, sign_b=-1.0, target=1.0, mode=0, gamma=1.0,
 def adam_multi(table, nchunks, lr, beta1, beta2, eps, step, grad_mul=1.0):
     check(lib.pesr_adam_multi(_ptr(table), nchunks, lr, beta1, beta2, eps, step, grad_mul, _stream()),
           "pesr_adam_multi")
+
+
+def bn_stats(y16, npix, c, sums_ws, mean, rstd, running_mean=None, running_var=None, num_batches=None, eps=1e-5,
+             momentum=0.1, running_mean_shift=None):
+    check(lib.pesr_bn_stats(_ptr(y16), npix, c, eps, momentum, _ptr(sums_ws), _ptr(mean), _ptr(rstd),
+                            _ptr(running_mean), _ptr(running_var), _ptr(num_batches), _ptr(running_mean_shift),
+                            dt_code(y16.dtype), _stream()), "pesr_bn_stats")
+
+
+def bn_lrelu_fwd(y16, npix, c, mean, rstd, gamma, beta, a16, slope=0.2):
+    check(lib.pesr_bn_lrelu_fwd(_ptr(y16), npix, c, _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), slope,
+                                dt_code(y16.dtype), _ptr(a16), _stream()), "pesr_bn_lrelu_fwd")
+
+
+def bn_lrelu_bwd(dz16, y16, npix, c, mean, rstd, gamma, sums_ws, dy16, dgamma, dbeta, grad_mul=1.0, grad_div_dev=None):
+    check(lib.pesr_bn_lrelu_bwd(_ptr(dz16), _ptr(y16), npix, c, _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(sums_ws),
+                                grad_mul, _ptr(grad_div_dev), dt_code(y16.dtype), _ptr(dy16), _ptr(dgamma),
+                                _ptr(dbeta), _stream()), "pesr_bn_lrelu_bwd")
+
+
+def maxpool2_fwd(x16, nb, h, w, c, y16):
+    check(lib.pesr_maxpool2_fwd(_ptr(x16), nb, h, w, c, dt_code(x16.dtype), _ptr(y16), _stream()), "pesr_maxpool2_fwd")
+
+
+def maxpool2_bwd(x16, dy16, nb, h, w, c, dx16, relu_mask=True):
+    check(lib.pesr_maxpool2_bwd(_ptr(x16), _ptr(dy16), nb, h, w, c, 1 if relu_mask else 0, dt_code(x16.dtype),
+                                _ptr(dx16), _stream()), "pesr_maxpool2_bwd")
+
+
+def linear_workspace_floats(nb, k, o):
+    return int(lib.pesr_linear_workspace_floats(nb, k, o))
+
+
+def linear_fwd(x16, w16, bias, nb, k, o, workspace, out32=None, out16=None, act=ACT_NONE):
+    check(lib.pesr_linear_skinny_fwd(_ptr(x16), _ptr(w16), _ptr(bias), nb, k, o, act, dt_code(x16.dtype),
+                                     _ptr(workspace), _ptr(out32), _ptr(out16), _stream()), "pesr_linear_skinny_fwd")
+
+
+def linear_dgrad(dy32, w16, nb, k, o, dx32):
+    check(lib.pesr_linear_skinny_dgrad(_ptr(dy32), _ptr(w16), nb, k, o, dt_code(w16.dtype), _ptr(dx32), _stream()),
+          "pesr_linear_skinny_dgrad")
+
+
+def linear_wgrad(dy32, x16, nb, k, o, dw, mul=1.0, div_dev=None, accumulate=False):
+    check(lib.pesr_linear_skinny_wgrad(_ptr(dy32), _ptr(x16), nb, k, o, mul, _ptr(div_dev), 1 if accumulate else 0,
+                                       dt_code(x16.dtype), _ptr(dw), _stream()), "pesr_linear_skinny_wgrad")
+
+
+def cast16(src32, dst16):
+    check(lib.pesr_cast16(_ptr(src32), src32.numel(), dt_code(dst16.dtype), _ptr(dst16), _stream()), "pesr_cast16")
+
+
+def flatten_nchw16(src_nhwc16, nb, hw, c, dst):
+    check(lib.pesr_flatten_nchw16(_ptr(src_nhwc16), nb, hw, c, _ptr(dst), _stream()), "pesr_flatten_nchw16")
+
+
+def unflatten_nchw16(src32, mask16, nb, hw, c, dst16, mul=1.0, mul_dev=None, slope=0.2):
+    check(lib.pesr_unflatten_nchw16(_ptr(src32), _ptr(mask16), nb, hw, c, mul, _ptr(mul_dev), slope,
+                                    dt_code(dst16.dtype), _ptr(dst16), _stream()), "pesr_unflatten_nchw16")

@@ -58,4 +58,6 @@ class Adam(torch.optim.Optimizer):
             table, n = self._table(gi, plist)
             b1, b2 = group['betas']
             ops.adam_multi(table, n, group['lr'], b1, b2, group['eps'], step)
+            for p in plist:   # the kernel wrote through raw pointers: tell autograd / the weight-pack caches
+                torch.autograd.graph.increment_version(p)
         return loss

@@ -139,8 +139,156 @@ def gen_case(opt, shape, dtype=torch.float16, seed=0, qmatch=True):
         print(flush=True)
 
 
+def disc_case(patch=12, nb=4, seed=0, dtype=torch.float16):
+    from oracle import pesr_oracle as O
+    from pesr_b200.model import Discriminator
+    opt = {'patch_size': patch, 'spectral_norm': False}
+    sd = O.init_discriminator(opt, seed)
+    D = Discriminator(opt, dtype=dtype)
+    D.load_state_dict(sd)
+    D = D.cuda().train()
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.rand(nb, 3, patch * 4, patch * 4, generator=g) * 255
+    R = torch.randn(nb, 1, generator=g)
+    xc = x.cuda().requires_grad_(True)
+    y = D(xc)
+    (y * R.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    for name, qd in (("fp64", None), ("qmatch", dtype)):
+        leaf = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+                for k, v in sd.items()}
+        xo = x.double().clone().requires_grad_(True)
+        st = []
+        yo = O.discriminator_forward(leaf, xo, qdtype=qd, stats_out=st)
+        if qd is None:
+            stats = st
+        names = [k for k in leaf if torch.is_tensor(leaf[k]) and leaf[k].is_floating_point() and leaf[k].requires_grad]
+        og = torch.autograd.grad((yo * R.double()).sum(), [leaf[k] for k in names] + [xo])
+        ograds = dict(zip(names, og[:-1]))
+        errs = {k: rel(p.grad.cpu(), ograds[k]) for k, p in D.named_parameters()}
+        vals = sorted(errs.values())
+        print(f"disc patch={patch} nb={nb} vs {name}: logits rel {rel(y.detach().cpu(), yo.detach()):.3e} "
+              f"dx rel {rel(xc.grad.cpu(), og[-1]):.3e} grad median {vals[len(vals)//2]:.3e} max {vals[-1]:.3e}")
+        print("    " + " ".join(f"{k.replace('features.','f').replace('classifier.','c')}={v:.1e}" for k, v in errs.items()))
+    mean0, var0, n0 = stats[0]
+    rm = D.state_dict()['features.0.1.running_mean'].cpu()
+    rv = D.state_dict()['features.0.1.running_var'].cpu()
+    print(f"    running_mean rel {rel(rm, 0.1 * mean0):.2e} running_var rel {rel(rv, 0.9 + 0.1 * var0 * n0 / (n0 - 1)):.2e} "
+          f"nbt {int(D.state_dict()['features.0.1.num_batches_tracked'])}", flush=True)
+
+
+def vgg_case(nb=2, side=64, seed=0, dtype=torch.float16):
+    from oracle import pesr_oracle as O
+    from pesr_b200.model import VGG
+    sd = O.init_vgg(seed)
+    V = VGG(pretrained=False, dtype=dtype)
+    V.load_state_dict(sd)
+    V = V.cuda()
+    g = torch.Generator().manual_seed(seed + 1)
+    sr = torch.rand(nb, 3, side, side, generator=g) * 255
+    hr = torch.rand(nb, 3, side, side, generator=g) * 255
+    src = sr.cuda().requires_grad_(True)
+    f_sr, f_hr = V(src, hr.cuda())
+    loss = ((f_sr - f_hr) ** 2).mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    for name, qd in (("fp64", None), ("qmatch", dtype)):
+        so = sr.double().clone().requires_grad_(True)
+        of_sr, of_hr = O.vgg_forward({k: v.double() for k, v in sd.items()}, so, hr.double(), qdtype=qd)
+        ol = O.mse_loss(of_sr, of_hr)
+        og, = torch.autograd.grad(ol, so)
+        print(f"vgg nb={nb} side={side} vs {name}: f_sr rel {rel(f_sr.detach().cpu(), of_sr.detach()):.3e} f_hr rel "
+              f"{rel(f_hr.cpu(), of_hr):.3e} loss rel {abs(loss.item()-ol.item())/ol.item():.3e} dsr rel "
+              f"{rel(src.grad.cpu(), og):.3e}", flush=True)
+
+
+def vgg_debug(nb=2, side=64, seed=0, dtype=torch.float16):
+    """Per-layer comparison of the VGG activations with the quantisation-matched oracle."""
+    import torch.nn.functional as F
+    from oracle import pesr_oracle as O
+    from pesr_b200.model import VGG
+    sd = O.init_vgg(seed)
+    V = VGG(pretrained=False, dtype=dtype)
+    V.load_state_dict(sd)
+    V = V.cuda()
+    g = torch.Generator().manual_seed(seed + 1)
+    sr = torch.rand(nb, 3, side, side, generator=g) * 255
+    hr = torch.rand(nb, 3, side, side, generator=g) * 255
+    with torch.no_grad():
+        V(sr.cuda(), hr.cuda())
+    pl = V.engine().plans[(nb, side, side)]
+    q = lambda t: t.to(dtype).double()
+    x = F.conv2d(sr.double(), sd['sub_mean.weight'].double(), sd['sub_mean.bias'].double())
+    idx, k = 0, 0
+    for op in pl.ops:
+        if op[0] == "conv":
+            li, cin, cout, ch, cw, outb = op[1], op[2], op[3], op[4], op[5], op[7]
+            x = F.conv2d(q(x), q(sd[f'vgg.{idx}.weight']), sd[f'vgg.{idx}.bias'].double(), padding=1)
+            if li < 15:
+                x = F.relu(x)
+            got = from_nhwc16(outb[: nb * ch * cw], nb, cout, ch, cw).cpu()
+            print(f"  conv{li} {cin}->{cout} {ch}x{cw}: rel vs oracle(rounded) {rel(got, q(x)):.3e}  vs unrounded {rel(got, x):.3e} "
+                  f"|x| {x.abs().mean():.3f} max {x.abs().max():.1f}")
+            x = got.double()   # continue from OUR activations so that each layer is checked in isolation
+            idx += 2
+        else:
+            c, ch, cw, outb = op[1], op[2], op[3], op[5]
+            x = F.max_pool2d(x, 2, 2)
+            got = from_nhwc16(outb[: nb * (ch // 2) * (cw // 2)], nb, c, ch // 2, cw // 2).cpu()
+            print(f"  pool {c} {ch}x{cw}: rel {rel(got, x):.3e}")
+            x = got.double()
+            idx += 1
+    sys.stdout.flush()
+
+
+def gan_case(seed=0, nb=4, patch=12):
+    from oracle import pesr_oracle as O
+    from pesr_b200 import steps
+    from pesr_b200.model import VGG, Discriminator, Generator
+    from pesr_b200.optim import Adam
+    opt = {'depth': 2, 'num_channels': 64, 'res_scale': 0.1, 'patch_size': patch, 'spectral_norm': False}
+    g_sd, d_sd, v_sd = O.init_generator(opt, seed), O.init_discriminator(opt, seed + 1), O.init_vgg(seed + 2)
+    G, D, V = Generator(opt), Discriminator(opt), VGG(pretrained=False)
+    G.load_state_dict(g_sd), D.load_state_dict(d_sd), V.load_state_dict(v_sd)
+    G, D, V = G.cuda(), D.cuda(), V.cuda()
+    gen = torch.Generator().manual_seed(seed + 3)
+    lr = torch.rand(nb, 3, patch, patch, generator=gen) * 255
+    hr = torch.rand(nb, 3, patch * 4, patch * 4, generator=gen) * 255
+    optG, optD = Adam(G.parameters(), lr=5e-5), Adam(D.parameters(), lr=5e-5)
+    cfg = dict(steps.DEFAULT_GAN_CFG)
+    cfg['target_real'] = torch.ones(nb, 1, device="cuda")
+    cfg['target_fake'] = torch.zeros(nb, 1, device="cuda")
+    g_before = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    losses = steps.gan_step(G, D, V, optG, optD, lr.cuda(), hr.cuda(), cfg)
+    torch.cuda.synchronize()
+    for name, qd in (("fp64", None), ("qmatch", torch.float16)):
+        out = O.gan_step(g_sd, d_sd, v_sd, lr, hr, opt, dtype=torch.float64, qdtype=qd)
+        ref = torch.stack([out['l1'], out['vgg'], out['g_loss'], out['tv'], out['d_loss']])
+        print(f"gan vs {name}: losses got {[f'{v:.5g}' for v in losses.tolist()]} ref {[f'{v:.5g}' for v in ref.tolist()]}")
+        ge = {k: rel(p.grad.cpu(), out['g_grads'][k]) for k, p in G.named_parameters()}
+        de = {k: rel(p.grad.cpu(), out['d_grads'][k]) for k, p in D.named_parameters()}
+        gv, dv = sorted(ge.values()), sorted(de.values())
+        print(f"    G grads rel median {gv[len(gv)//2]:.3e} max {gv[-1]:.3e} | D grads (D phase) median {dv[len(dv)//2]:.3e} "
+              f"max {dv[-1]:.3e}")
+        dpa = {k: rel(p.detach().cpu() - d_sd[k].double(), out['d_params_after'][k] - d_sd[k].double())
+               for k, p in D.named_parameters()}
+        print(f"    D param update (Adam step 1) rel median {sorted(dpa.values())[len(dpa)//2]:.3e}", flush=True)
+
+
 def main():
     what = sys.argv[1]
+    if what == "disc":
+        disc_case()
+        disc_case(patch=8, nb=3, seed=4)
+        return
+    if what == "vgg":
+        vgg_debug()
+        vgg_case()
+        vgg_case(nb=1, side=48, seed=3)
+        return
+    if what == "gan":
+        gan_case()
+        return
     if what == "gen":
         gen_case({'depth': 2, 'num_channels': 64, 'res_scale': 0.1}, (2, 3, 10, 12))
         gen_case({'depth': 2, 'num_channels': 64, 'res_scale': 0.1}, (2, 3, 10, 12), dtype=torch.bfloat16)

@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 {
-timeout 600 python tools/bringup.py gen; echo "exit=$?"
-timeout 300 python tools/perf_conv.py conv; echo "exit=$?"
-timeout 300 python tools/perf_conv.py gen; echo "exit=$?"
-} > gpurun_out/bringup2.log 2>&1
-tail -80 gpurun_out/bringup2.log
+timeout 300 python tools/bringup.py disc; echo "exit=$?"
+timeout 300 python tools/bringup.py vgg; echo "exit=$?"
+timeout 300 python tools/bringup.py gan; echo "exit=$?"
+} > gpurun_out/bringup3.log 2>&1
+tail -60 gpurun_out/bringup3.log

@@ -68,6 +68,8 @@ int pesr_sizeof(int which);
  * [tap_widx[t]*cout + n0, +block_n) of the packed K-major weight matrix [w_rows][cin].
  * Backward-data is the same kernel with flipped/transposed packed weights (pesr_pack_weights).
  * Stride-2 convolutions pass the four parity planes of the input as sources 0..3.
+ * The same kernel runs the Discriminator's Linear(73728 -> 1024) as a split-K GEMM (ksplit) and its
+ * backward-data with the weight matrix read MN-major in place (b_mn_major).
  *
  * Epilogue (per output element, in this order):
  *   v = alpha * [alpha_dev] * (acc + bias[q]);  v += res32;  v += res16;  v = act(v);
@@ -105,6 +107,9 @@ typedef struct pesr_conv_desc {
   int32_t ps_c;             /* SHUFFLE2: channels of the shuffled tensor (cout/4) */
   int32_t aux_mode;         /* 0: res32/res16/mask16/out32 are indexed by the GEMM pixel; 1: by the NORMAL-mode
                                output pixel (n, h*sy+oy, w*sx+ox) of the out_h x out_w grid (stride-2 dgrad) */
+  int32_t ksplit;           /* > 1: split K across CTAs; raw fp32 partials go to out32 + split*split_stride32 */
+  int32_t b_mn_major;       /* 1: wpacked is [K = cin][N = cout] (N contiguous), one tap: y = x * W without a transpose */
+  int64_t split_stride32;   /* elements between the partial outputs of successive K splits */
 } pesr_conv_desc;
 
 int pesr_conv_igemm(const pesr_conv_desc* d, void* stream);
@@ -161,6 +166,11 @@ void pesr_debug_wgrad_desc(int lbo_bytes, int sbo_bytes);
  */
 int pesr_pack_weights(const float* w_oihw, int32_t co, int32_t ci, int32_t ksize, int32_t mode, int32_t pad_to,
                       int32_t dtype, void* out, void* stream);
+
+/* All packs of one network in ONE launch.  jobs_host: njobs rows of 8 int64 {src fp32 OIHW, dst 16-bit, co, ci,
+ * ksize, mode, pad_to, 0}; jobs_dev: caller-owned device scratch of njobs*64 bytes, (re)filled when upload != 0. */
+int pesr_pack_weights_multi(const int64_t* jobs_host, int32_t njobs, void* jobs_dev, int32_t upload, int32_t dtype,
+                            void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Layout / edge kernels.  These are HBM-bound; each is a single coalesced pass.
@@ -257,6 +267,9 @@ int pesr_maxpool2_bwd(const void* x16, const void* dy16, int32_t nb, int32_t h, 
 int64_t pesr_linear_workspace_floats(int32_t nb, int32_t k, int32_t o);
 int pesr_linear_skinny_fwd(const void* x16, const void* w16, const float* bias, int32_t nb, int32_t k, int32_t o,
                            int32_t act, int32_t dtype, float* workspace, float* out32, void* out16, void* stream);
+/* out = act(sum over ksplit partials [ksplit][nb][o] + bias): closes a split-K Linear run through pesr_conv_igemm. */
+int pesr_linear_finalize(const float* partials, int32_t ksplit, int32_t nb, int32_t o, const float* bias, int32_t act,
+                         int32_t dtype, float* out32, void* out16, void* stream);
 int pesr_linear_skinny_dgrad(const float* dy, const void* w16, int32_t nb, int32_t k, int32_t o, int32_t dtype,
                              float* dx32, void* stream);
 int pesr_linear_skinny_wgrad(const float* dy, const void* x16, int32_t nb, int32_t k, int32_t o, float mul,

@@ -46,6 +46,7 @@ class ConvDesc(C.Structure):
         ("out_mode", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32),
         ("out_sy", C.c_int32), ("out_sx", C.c_int32), ("out_oy", C.c_int32), ("out_ox", C.c_int32),
         ("out_coff", C.c_int32), ("ps_c", C.c_int32), ("aux_mode", C.c_int32),
+        ("ksplit", C.c_int32), ("b_mn_major", C.c_int32), ("split_stride32", C.c_int64),
     ]
 
 
@@ -90,6 +91,7 @@ SIGNATURES = {
     "pesr_debug_wgrad_desc": (None, [C.c_int, C.c_int]),
     "pesr_wgrad_reduce": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp, _vp]),
     "pesr_pack_weights": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "pesr_pack_weights_multi": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp]),
     "pesr_im2col3": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "pesr_col2im3": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _vp]),
     "pesr_nchw32_to_nhwc16": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp]),
@@ -108,6 +110,7 @@ SIGNATURES = {
     "pesr_maxpool2_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "pesr_linear_workspace_floats": (C.c_int64, [_i32, _i32, _i32]),
     "pesr_linear_skinny_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "pesr_linear_finalize": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
     "pesr_linear_skinny_dgrad": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "pesr_linear_skinny_wgrad": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _i32, _i32, _vp, _vp]),
     "pesr_cast16": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),

@@ -43,6 +43,8 @@ struct ConvK {
   float* out32; int ld_out32;
   uint16_t* out16; int ld_out16;
   int out_mode, out_h, out_w, out_sy, out_sx, out_oy, out_ox, out_coff, ps_c, aux_mode;
+  int ksplit, b_mn_major, mn_tiles;
+  long long split_stride32;
 };
 
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -91,39 +93,51 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
+        const int split = tile / p.mn_tiles;
+        const int mn = tile - split * p.mn_tiles;
+        const int n_tile = mn % p.n_tiles;
+        const int m_tile = mn / p.n_tiles;
         const int tw = m_tile % p.tiles_w;
         const int th = (m_tile / p.tiles_w) % p.tiles_h;
         const int img = m_tile / (p.tiles_w * p.tiles_h);
         const int h0 = th * p.tile_h, w0 = tw * p.tile_w, n0 = n_tile * p.block_n;
-        for (int t = 0; t < p.ntaps; t++) {
+        const int kb0 = (int)(((long long)split * total_kb) / p.ksplit);
+        const int kb1 = (int)(((long long)(split + 1) * total_kb) / p.ksplit);
+        for (int kb = kb0; kb < kb1; kb++) {
+          const int t = kb / p.kblocks_per_tap;
+          const int cb = kb - t * p.kblocks_per_tap;
           const CUtensorMap* ma = &maps.a[p.tap_src[t]];
           const int hh = h0 + p.tap_dh[t], ww = w0 + p.tap_dw[t];
-          const int wrow = p.tap_widx[t] * p.cout + n0;
-          for (int cb = 0; cb < p.kblocks_per_tap; cb++) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-            mbar_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes);
-            tma_load_4d(sa, ma, &full_bar[stage], cb * kKBlock, ww, hh, img);
-            tma_load_2d(sa + kABytes, &maps.b, &full_bar[stage], cb * kKBlock, wrow);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes);
+          tma_load_4d(sa, ma, &full_bar[stage], cb * kKBlock, ww, hh, img);
+          if (p.b_mn_major) {
+            // weights stored [K][N] (N contiguous): one 64(K) x 64(N) box per 64 output columns
+            for (int i = 0; i < p.block_n / 64; i++)
+              tma_load_2d(sa + kABytes + i * 8192, &maps.b, &full_bar[stage], n0 + i * 64, kb * kKBlock);
+          } else {
+            tma_load_2d(sa + kABytes, &maps.b, &full_bar[stage], cb * kKBlock, p.tap_widx[t] * p.cout + n0);
           }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc(kTileM, p.block_n, p.dtype, 0, 0);
+    const uint32_t idesc = make_idesc(kTileM, p.block_n, p.dtype, 0, p.b_mn_major);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int split = tile / p.mn_tiles;
+      const int kb0 = (int)(((long long)split * total_kb) / p.ksplit);
+      const int kb1 = (int)(((long long)(split + 1) * total_kb) / p.ksplit);
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
-      for (int kb = 0; kb < total_kb; kb++) {
+      for (int kb = kb0; kb < kb1; kb++) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
@@ -132,11 +146,12 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < kKBlock / 16; k++) {
             const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
-            umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint64_t db = p.b_mn_major ? make_smem_desc(b_addr + k * 2048, 8192, 1024)
+                                             : make_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
-          if (kb == total_kb - 1) umma_commit(&tmem_full[acc]);
+          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -156,8 +171,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+      const int split = tile / p.mn_tiles;
+      const int mn = tile - split * p.mn_tiles;
+      const int n_tile = mn % p.n_tiles;
+      const int m_tile = mn / p.n_tiles;
       const int tw = m_tile % p.tiles_w;
       const int th = (m_tile / p.tiles_w) % p.tiles_h;
       const int img = m_tile / (p.tiles_w * p.tiles_h);
@@ -229,7 +246,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
           }
         }
         if (p.out32) {
-          float4* o = reinterpret_cast<float4*>(p.out32 + pix * p.ld_out32 + q0);
+          float4* o = reinterpret_cast<float4*>(p.out32 + split * p.split_stride32 + pix * p.ld_out32 + q0);
 #pragma unroll
           for (int j = 0; j < 8; j++) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         }
@@ -296,7 +313,8 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d, void* stream_) {
   for (int t = 0; t < d->ntaps; t++) {
     PESR_CHECK_ARG(d->tap_src[t] >= 0 && d->tap_src[t] < d->nsrc, "conv_igemm: tap %d reads source %d", t,
                    d->tap_src[t]);
-    PESR_CHECK_ARG((d->tap_widx[t] + 1) * d->cout <= d->w_rows, "conv_igemm: tap %d weight rows out of range", t);
+    PESR_CHECK_ARG(d->b_mn_major || (d->tap_widx[t] + 1) * d->cout <= d->w_rows,
+                   "conv_igemm: tap %d weight rows out of range", t);
   }
   if (d->out_mode == PESR_OUT_SHUFFLE2)
     PESR_CHECK_ARG(d->ps_c > 0 && d->ps_c % 32 == 0 && d->cout == 4 * d->ps_c, "conv_igemm: bad ps_c %d", d->ps_c);
@@ -314,7 +332,20 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d, void* stream_) {
     int r = get_tensor_map(&maps.a[s], d->src[ss], d->dtype, 4, dims, str, box);
     if (r) return r;
   }
-  {
+  const int ksplit = d->ksplit > 1 ? d->ksplit : 1;
+  if (ksplit > 1)
+    PESR_CHECK_ARG(d->out32 && !d->out16 && !d->res32 && !d->res16 && !d->mask16 && !d->bias && d->act == 0 &&
+                       ksplit <= d->ntaps * (d->cin / kKBlock),
+                   "conv_igemm: split-K writes raw fp32 partials only (ksplit %d)", ksplit);
+  if (d->b_mn_major) {
+    PESR_CHECK_ARG(d->ntaps == 1 && d->block_n % 64 == 0 && d->w_rows == d->cin,
+                   "conv_igemm: MN-major weights need one tap, block_n %% 64 == 0 and w_rows == cin");
+    uint64_t dims[2] = {(uint64_t)d->cout, (uint64_t)d->w_rows};
+    uint64_t str[1] = {(uint64_t)d->cout * 2};
+    uint32_t box[2] = {64, 64};
+    int r = get_tensor_map(&maps.b, d->wpacked, d->dtype, 2, dims, str, box);
+    if (r) return r;
+  } else {
     uint64_t dims[2] = {(uint64_t)d->cin, (uint64_t)d->w_rows};
     uint64_t str[1] = {(uint64_t)d->cin * 2};
     uint32_t box[2] = {(uint32_t)kKBlock, (uint32_t)d->block_n};
@@ -330,7 +361,11 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d, void* stream_) {
   k.tiles_h = (d->h + d->tile_h - 1) / d->tile_h;
   k.tiles_w = (d->w + d->tile_w - 1) / d->tile_w;
   k.n_tiles = d->cout / d->block_n;
-  k.num_tiles = d->nb * k.tiles_h * k.tiles_w * k.n_tiles;
+  k.mn_tiles = d->nb * k.tiles_h * k.tiles_w * k.n_tiles;
+  k.ksplit = ksplit;
+  k.num_tiles = k.mn_tiles * ksplit;
+  k.b_mn_major = d->b_mn_major ? 1 : 0;
+  k.split_stride32 = d->split_stride32;
   k.kblocks_per_tap = d->cin / kKBlock;
   k.stage_bytes = kABytes + d->block_n * kKBlock * 2;
   const int smem_budget = 227 * 1024 - 4096;

@@ -4,6 +4,8 @@
 #include "common.cuh"
 #include "host_util.cuh"
 
+#include <vector>
+
 namespace pesr {
 
 static inline int blocks_for(long long n, int threads, int cap = 148 * 16) {
@@ -72,13 +74,56 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int co, int ci,
   }
 }
 
+// Multi-tensor variant: `jobs` rows = {src, dst, co, ci, taps, mode, pad_to, first_block}; blockIdx.x is
+// mapped to its job by binary search over first_block; each block packs 4096 output elements.
+struct PackJob {
+  const float* src;
+  uint16_t* dst;
+  int co, ci, taps, mode, pad_to, rows, kdim;
+  long long total;
+  int first_block;
+};
+__device__ __forceinline__ float pack_fetch(const float* __restrict__ w, int co, int ci, int taps, int mode, int r, int k);
+__global__ void pack_weights_multi_kernel(const PackJob* __restrict__ jobs, int njobs, int bf) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].first_block <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackJob j = jobs[lo];
+  const long long base = (long long)((int)blockIdx.x - j.first_block) * 4096;
+  for (int t = threadIdx.x; t < 4096; t += blockDim.x) {
+    const long long idx = base + t;
+    if (idx >= j.total) break;
+    const int k = (int)(idx % j.kdim), r = (int)(idx / j.kdim);
+    j.dst[idx] = from_f32(pack_fetch(j.src, j.co, j.ci, j.taps, j.mode, r, k), bf);
+  }
+}
+__device__ __forceinline__ float pack_fetch(const float* __restrict__ w, int co, int ci, int taps, int mode, int r, int k) {
+  const int c_ps = co / 4;
+  switch (mode) {
+    case 0: { const int tap = r / co, o = r % co; return w[((long long)o * ci + k) * taps + tap]; }
+    case 1: { const int tap = r / ci, i = r % ci; return w[((long long)k * ci + i) * taps + (taps - 1 - tap)]; }
+    case 2: { const int tap = r / co, op = r % co; const int o = (op % c_ps) * 4 + (op / c_ps);
+              return w[((long long)o * ci + k) * taps + tap]; }
+    case 3: { const int tap = r / ci, i = r % ci; const int o = (k % c_ps) * 4 + (k / c_ps);
+              return w[((long long)o * ci + i) * taps + (taps - 1 - tap)]; }
+    case 4: { if (k < taps * ci) { const int tap = k / ci, i = k % ci; return w[((long long)r * ci + i) * taps + tap]; } return 0.f; }
+    case 5: { if (r < taps * co) { const int tap = r / co, o = r % co; return w[((long long)o * ci + k) * taps + tap]; } return 0.f; }
+    case 6: { if (r < taps * ci) { const int tap = r / ci, i = r % ci; return w[((long long)k * ci + i) * taps + tap]; } return 0.f; }
+    case 7: { if (k < taps * co) { const int tap = k / co, o = k % co; return w[((long long)o * ci + r) * taps + tap]; } return 0.f; }
+  }
+  return 0.f;
+}
+
 // ------------------------------------------------------------------------------------------
-// im2col for 3-channel images: one thread per (pixel, 8-column chunk) -> one 16-byte store
+// im2col for 3-channel images: 4 threads per pixel; thread `q` produces columns [8q, 8q+8) (taps
+// 8q/3 .. (8q+7)/3, each tap loaded once and pushed through the 3x3 affine) and the zero chunk q+4.
 // ------------------------------------------------------------------------------------------
 __global__ void im2col3_kernel(const float* __restrict__ src, int nb, int h, int w, const float* __restrict__ aff_a,
                                const float* __restrict__ aff_b, const float* __restrict__ mul_dev, int sgn,
                                int pad_affine, int bf, uint4* __restrict__ col) {
-  const long long total = (long long)nb * h * w * 8;
+  const long long total = (long long)nb * h * w * 4;
   float A[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   float B[3] = {0, 0, 0};
   if (aff_a)
@@ -89,38 +134,45 @@ __global__ void im2col3_kernel(const float* __restrict__ src, int nb, int h, int
   const long long plane = (long long)h * w;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int chunk = (int)(idx & 7);
-    const long long p = idx >> 3;
-    uint4 o = make_uint4(0, 0, 0, 0);
-    if (chunk < 4) {
-      const int x = (int)(p % w);
-      const int y = (int)((p / w) % h);
-      const int n = (int)(p / plane);
-      const float* base = src + (long long)n * 3 * plane;
-      float vals[8];
+    const int q = (int)(idx & 3);
+    const long long p = idx >> 2;
+    const int x = (int)(p % w);
+    const int y = (int)((p / w) % h);
+    const int n = (int)(p / plane);
+    const float* base = src + (long long)n * 3 * plane;
+    float vals[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) vals[j] = 0.f;
+    const int k0 = q * 8;
+    const int t_lo = k0 / 3, t_hi = min(8, (k0 + 7) / 3);
+    for (int tap = t_lo; tap <= t_hi; tap++) {
+      const int yy = y + sgn * (tap / 3 - 1), xx = x + sgn * (tap % 3 - 1);
+      float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+        const long long off = (long long)yy * w + xx;
+        const float s0 = __ldg(base + off), s1 = __ldg(base + plane + off), s2 = __ldg(base + 2 * plane + off);
+        v0 = (A[0] * s0 + A[1] * s1 + A[2] * s2 + B[0]) * mul;
+        v1 = (A[3] * s0 + A[4] * s1 + A[5] * s2 + B[1]) * mul;
+        v2 = (A[6] * s0 + A[7] * s1 + A[8] * s2 + B[2]) * mul;
+      } else if (pad_affine) {  // the affine of a zero-padded pixel (a constant shift of the conv input)
+        v0 = B[0] * mul; v1 = B[1] * mul; v2 = B[2] * mul;
+      }
+      const int kb = tap * 3 - k0;  // column of channel 0 of this tap, relative to the chunk
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        const int k = chunk * 8 + j;
-        float v = 0.f;
-        if (k < 27) {
-          const int tap = k / 3, c = k % 3;
-          const int yy = y + sgn * (tap / 3 - 1), xx = x + sgn * (tap % 3 - 1);
-          if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
-            const long long off = (long long)yy * w + xx;
-            const float s0 = __ldg(base + off), s1 = __ldg(base + plane + off), s2 = __ldg(base + 2 * plane + off);
-            v = (A[c * 3] * s0 + A[c * 3 + 1] * s1 + A[c * 3 + 2] * s2 + B[c]) * mul;
-          } else if (pad_affine) {
-            v = B[c] * mul;  // the affine of a zero-padded pixel (a constant shift of the conv input)
-          }
-        }
-        vals[j] = v;
+        if (j == kb) vals[j] = v0;
+        if (j == kb + 1) vals[j] = v1;
+        if (j == kb + 2) vals[j] = v2;
       }
-      o.x = pack2(vals[0], vals[1], bf);
-      o.y = pack2(vals[2], vals[3], bf);
-      o.z = pack2(vals[4], vals[5], bf);
-      o.w = pack2(vals[6], vals[7], bf);
     }
-    col[idx] = o;
+    if (q == 3) { vals[3] = vals[4] = vals[5] = vals[6] = vals[7] = 0.f; }  // columns 27..31
+    uint4 o;
+    o.x = pack2(vals[0], vals[1], bf);
+    o.y = pack2(vals[2], vals[3], bf);
+    o.z = pack2(vals[4], vals[5], bf);
+    o.w = pack2(vals[6], vals[7], bf);
+    col[p * 8 + q] = o;
+    col[p * 8 + 4 + q] = make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -335,13 +387,57 @@ extern "C" int pesr_pack_weights(const float* w, int32_t co, int32_t ci, int32_t
   return 0;
 }
 
+// jobs_host: njobs rows of 8 int64 {src, dst, co, ci, ksize, mode, pad_to, unused}; jobs_dev: device scratch of
+// njobs * 64 bytes that the call fills (kept by the caller so that repeated calls can skip the upload).
+extern "C" int pesr_pack_weights_multi(const int64_t* jobs_host, int32_t njobs, void* jobs_dev, int32_t upload,
+                                       int32_t dtype, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(jobs_host && jobs_dev && njobs > 0 && njobs <= 4096, "pack_weights_multi: bad arguments");
+  static_assert(sizeof(PackJob) <= 64, "PackJob must fit the 64-byte device slot");
+  std::vector<PackJob> jobs(njobs);
+  int nblocks = 0;
+  for (int i = 0; i < njobs; i++) {
+    const int64_t* r = jobs_host + i * 8;
+    PackJob j;
+    j.src = reinterpret_cast<const float*>(r[0]);
+    j.dst = reinterpret_cast<uint16_t*>(r[1]);
+    j.co = (int)r[2]; j.ci = (int)r[3];
+    const int ksize = (int)r[4];
+    j.taps = ksize * ksize; j.mode = (int)r[5]; j.pad_to = (int)r[6];
+    PESR_CHECK_ARG(j.mode >= 0 && j.mode <= 7 && (ksize == 3 || ksize == 1), "pack_weights_multi: job %d mode/ksize", i);
+    switch (j.mode) {
+      case 0: case 2: j.rows = j.taps * j.co; j.kdim = j.ci; break;
+      case 1: case 3: j.rows = j.taps * j.ci; j.kdim = j.co; break;
+      case 4: j.rows = j.co; j.kdim = j.pad_to; break;
+      case 5: j.rows = j.pad_to; j.kdim = j.ci; break;
+      case 6: j.rows = j.pad_to; j.kdim = j.co; break;
+      default: j.rows = j.ci; j.kdim = j.pad_to; break;
+    }
+    j.total = (long long)j.rows * j.kdim;
+    j.first_block = nblocks;
+    nblocks += (int)((j.total + 4095) / 4096);
+    jobs[i] = j;
+  }
+  if (upload) {
+    // pageable-memory copy: synchronous with respect to the host buffer, stream-ordered on the device
+    std::vector<unsigned char> staged((size_t)njobs * 64, 0);
+    for (int i = 0; i < njobs; i++) memcpy(staged.data() + (size_t)i * 64, &jobs[i], sizeof(PackJob));
+    cudaError_t e = cudaMemcpyAsync(jobs_dev, staged.data(), staged.size(), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) { set_error("pack_weights_multi: upload failed: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  pack_weights_multi_kernel<<<nblocks, 256, 0, stream>>>(reinterpret_cast<const PackJob*>(jobs_dev), njobs, dtype);
+  count_launch();
+  PESR_CHECK_LAUNCH("pack_weights_multi");
+  return 0;
+}
+
 extern "C" int pesr_im2col3(const float* src, int32_t nb, int32_t h, int32_t w, const float* aff_a,
                             const float* aff_b, const float* mul_dev, int32_t sgn, int32_t pad_affine, int32_t dtype,
                             void* col, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PESR_CHECK_ARG(src && col && nb > 0 && h > 0 && w > 0, "im2col3: bad arguments");
   PESR_CHECK_ARG(sgn == 1 || sgn == -1, "im2col3: sgn must be +-1");
-  const long long total = (long long)nb * h * w * 8;
+  const long long total = (long long)nb * h * w * 4;
   im2col3_kernel<<<blocks_for(total, 256, 148 * 32), 256, 0, stream>>>(src, nb, h, w, aff_a, aff_b, mul_dev, sgn,
                                                                       pad_affine, dtype, reinterpret_cast<uint4*>(col));
   count_launch();

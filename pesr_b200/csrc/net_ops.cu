@@ -56,6 +56,68 @@ __global__ void bn_reduce_kernel(const uint16_t* __restrict__ x, const uint16_t*
   }
 }
 
+// Vectorised variant for c in {64,128,256,512}: 16-byte loads, c/8 threads per pixel row.
+__global__ void __launch_bounds__(256)
+bn_reduce_vec_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, long long npix, int c,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, int mode, int bf,
+                     double* __restrict__ sums) {
+  __shared__ double red[2][2048];   // [quantity][row-in-pass * c + channel], rows-per-pass * c == 2048
+  const int tpr = c >> 3;           // threads per pixel row
+  const int rpp = 256 / tpr;        // pixel rows per pass
+  const int v = threadIdx.x % tpr, r = threadIdx.x / tpr;
+  float m[8], rs[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) { m[j] = 0.f; rs[j] = 1.f; }
+  if (mode == 1) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) { m[j] = mean[v * 8 + j]; rs[j] = rstd[v * 8 + j]; }
+  }
+  double da[8], db[8];
+  float fa[8], fb[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) { da[j] = db[j] = 0.0; fa[j] = fb[j] = 0.f; }
+  int cnt = 0;
+  for (long long p = (long long)blockIdx.x * rpp + r; p < npix; p += (long long)gridDim.x * rpp) {
+    const uint4 u = x[p * tpr + v];
+    const uint32_t ux[4] = {u.x, u.y, u.z, u.w};
+    if (mode == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float2 f = unpack2(ux[j], bf);
+        fa[2 * j] += f.x; fa[2 * j + 1] += f.y;
+        fb[2 * j] += f.x * f.x; fb[2 * j + 1] += f.y * f.y;
+      }
+    } else {
+      const uint4 w = y[p * tpr + v];
+      const uint32_t uy[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float2 f = unpack2(ux[j], bf), g = unpack2(uy[j], bf);
+        fa[2 * j] += f.x; fa[2 * j + 1] += f.y;
+        fb[2 * j] += f.x * (g.x - m[2 * j]) * rs[2 * j];
+        fb[2 * j + 1] += f.y * (g.y - m[2 * j + 1]) * rs[2 * j + 1];
+      }
+    }
+    if (++cnt == 64) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) { da[j] += fa[j]; db[j] += fb[j]; fa[j] = fb[j] = 0.f; }
+      cnt = 0;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    red[0][r * c + v * 8 + j] = da[j] + fa[j];
+    red[1][r * c + v * 8 + j] = db[j] + fb[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * c; i += 256) {
+    const int which = i / c, ch = i % c;
+    double t = 0;
+    for (int k = 0; k < rpp; k++) t += red[which][k * c + ch];
+    atomicAdd(sums + which * c + ch, t);
+  }
+}
+
 // mean / rstd from the sums (+ running statistics update: momentum, unbiased variance), then zero the sums.
 __global__ void bn_finalize_kernel(double* __restrict__ sums, int c, double n, float eps, float momentum,
                                    float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ run_mean,
@@ -79,10 +141,17 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, int c, double n, f
   if (i == 0 && num_batches) *num_batches += 1;
 }
 
-// a = lrelu(gamma * (y - mean) * rstd + beta), 8 channels (16 bytes) per thread
+// a = lrelu(gamma * (y - mean) * rstd + beta) = lrelu(y * sc + sh), 8 channels (16 bytes) per thread
 __global__ void bn_lrelu_fwd_kernel(const uint4* __restrict__ y, long long nvec, int c, const float* __restrict__ mean,
                                     const float* __restrict__ rstd, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, float slope, int bf, uint4* __restrict__ a) {
+  __shared__ float sc[512], sh[512];
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    const float k = gamma[i] * rstd[i];
+    sc[i] = k;
+    sh[i] = beta[i] - mean[i] * k;
+  }
+  __syncthreads();
   const int cv = c >> 3;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % cv) * 8;
@@ -91,10 +160,10 @@ __global__ void bn_lrelu_fwd_kernel(const uint4* __restrict__ y, long long nvec,
     uint32_t out[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      float2 f = unpack2(in[j], bf);
+      const float2 f = unpack2(in[j], bf);
       const int cc = c0 + 2 * j;
-      float v0 = (f.x - mean[cc]) * rstd[cc] * gamma[cc] + beta[cc];
-      float v1 = (f.y - mean[cc + 1]) * rstd[cc + 1] * gamma[cc + 1] + beta[cc + 1];
+      float v0 = f.x * sc[cc] + sh[cc];
+      float v1 = f.y * sc[cc + 1] + sh[cc + 1];
       v0 = v0 > 0.f ? v0 : slope * v0;
       v1 = v1 > 0.f ? v1 : slope * v1;
       out[j] = pack2(v0, v1, bf);
@@ -103,12 +172,14 @@ __global__ void bn_lrelu_fwd_kernel(const uint4* __restrict__ y, long long nvec,
   }
 }
 
-// dy = gamma * rstd * (dz - s1/n - xhat * s2/n); also emits dgamma = s2*gmul, dbeta = s1*gmul once (block 0).
+// dy = gamma * rstd * (dz - s1/n - xhat * s2/n) = ka*dz + kb*y + kc per channel; also emits
+// dgamma = s2*gmul, dbeta = s1*gmul once (block 0).
 __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ y, long long nvec, int c,
                                     double n, const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ gamma, const double* __restrict__ sums, float gmul,
                                     const float* __restrict__ gdiv_dev, int bf, uint4* __restrict__ dy,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float ka[512], kb[512], kc[512];
   const int cv = c >> 3;
   if (blockIdx.x == 0 && dgamma) {
     float mul = gmul;
@@ -118,7 +189,14 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* _
       dgamma[i] = (float)sums[c + i] * mul;
     }
   }
-  const float inv_n = (float)(1.0 / n);
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    const double k1 = sums[i] / n, k2 = sums[c + i] / n;
+    const double g = gamma[i], r = rstd[i], m = mean[i];
+    ka[i] = (float)(g * r);
+    kb[i] = (float)(-g * r * r * k2);
+    kc[i] = (float)(g * r * (m * r * k2 - k1));
+  }
+  __syncthreads();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % cv) * 8;
     const uint4 ug = dz[i], uy = y[i];
@@ -128,12 +206,7 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* _
     for (int j = 0; j < 4; j++) {
       const float2 g = unpack2(g_in[j], bf), yy = unpack2(y_in[j], bf);
       const int cc = c0 + 2 * j;
-      const float xh0 = (yy.x - mean[cc]) * rstd[cc], xh1 = (yy.y - mean[cc + 1]) * rstd[cc + 1];
-      const float s10 = (float)sums[cc] * inv_n, s11 = (float)sums[cc + 1] * inv_n;
-      const float s20 = (float)sums[c + cc] * inv_n, s21 = (float)sums[c + cc + 1] * inv_n;
-      const float d0 = gamma[cc] * rstd[cc] * (g.x - s10 - xh0 * s20);
-      const float d1 = gamma[cc + 1] * rstd[cc + 1] * (g.y - s11 - xh1 * s21);
-      out[j] = pack2(d0, d1, bf);
+      out[j] = pack2(ka[cc] * g.x + kb[cc] * yy.x + kc[cc], ka[cc + 1] * g.y + kb[cc + 1] * yy.y + kc[cc + 1], bf);
     }
     dy[i] = make_uint4(out[0], out[1], out[2], out[3]);
   }
@@ -443,17 +516,34 @@ static int nblocks(long long n, int threads, int cap = 148 * 16) {
   return (int)b;
 }
 
+static void launch_bn_reduce(const void* x16, const void* y16, long long npix, int c, const float* mean, const float* rstd,
+                             int mode, int dtype, double* sums_ws, cudaStream_t stream) {
+  if (c == 64 || c == 128 || c == 256 || c == 512) {
+    const int rpp = 256 / (c / 8);
+    long long bx = (npix + (long long)rpp * 8 - 1) / ((long long)rpp * 8);
+    if (bx > 148 * 4) bx = 148 * 4;
+    if (bx < 1) bx = 1;
+    bn_reduce_vec_kernel<<<(unsigned)bx, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x16),
+                                                          reinterpret_cast<const uint4*>(y16), npix, c, mean, rstd,
+                                                          mode, dtype, sums_ws);
+  } else {
+    long long bx = (npix + 8 * 64 - 1) / (8 * 64);
+    if (bx > 1184) bx = 1184;
+    dim3 grid((unsigned)bx, (unsigned)((c + 63) / 64));
+    bn_reduce_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(x16),
+                                              reinterpret_cast<const uint16_t*>(y16), npix, c, mean, rstd, mode, dtype,
+                                              sums_ws);
+  }
+}
+
 extern "C" int pesr_bn_stats(const void* y16, int64_t npix, int32_t c, float eps, float momentum, double* sums_ws,
                              float* mean, float* rstd, float* running_mean, float* running_var,
                              int64_t* num_batches_tracked, const float* running_mean_shift, int32_t dtype,
                              void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PESR_CHECK_ARG(y16 && sums_ws && mean && rstd && npix > 0 && c > 0 && c % 8 == 0, "bn_stats: bad arguments");
-  long long bx = (npix + 8 * 64 - 1) / (8 * 64);
-  if (bx > 1184) bx = 1184;
-  dim3 grid((unsigned)bx, (unsigned)((c + 63) / 64));
-  bn_reduce_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(y16), nullptr, npix, c, nullptr, nullptr,
-                                            0, dtype, sums_ws);
+  PESR_CHECK_ARG(c <= 512, "bn_stats: at most 512 channels");
+  launch_bn_reduce(y16, nullptr, npix, c, nullptr, nullptr, 0, dtype, sums_ws, stream);
   bn_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(sums_ws, c, (double)npix, eps, momentum, mean, rstd,
                                                          running_mean, running_var,
                                                          reinterpret_cast<long long*>(num_batches_tracked),
@@ -467,7 +557,8 @@ extern "C" int pesr_bn_lrelu_fwd(const void* y16, int64_t npix, int32_t c, const
                                  const float* gamma, const float* beta, float slope, int32_t dtype, void* a16,
                                  void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  PESR_CHECK_ARG(y16 && a16 && mean && rstd && gamma && beta && npix > 0 && c % 8 == 0, "bn_lrelu_fwd: bad arguments");
+  PESR_CHECK_ARG(y16 && a16 && mean && rstd && gamma && beta && npix > 0 && c % 8 == 0 && c <= 512,
+                 "bn_lrelu_fwd: bad arguments");
   const long long nvec = npix * (c / 8);
   bn_lrelu_fwd_kernel<<<nblocks(nvec, 256, 148 * 16), 256, 0, stream>>>(reinterpret_cast<const uint4*>(y16), nvec, c, mean,
                                                                        rstd, gamma, beta, slope, dtype,
@@ -484,11 +575,8 @@ extern "C" int pesr_bn_lrelu_bwd(const void* dz16, const void* y16, int64_t npix
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PESR_CHECK_ARG(dz16 && y16 && dy16 && mean && rstd && gamma && sums_ws && npix > 0 && c % 8 == 0,
                  "bn_lrelu_bwd: bad arguments");
-  long long bx = (npix + 8 * 64 - 1) / (8 * 64);
-  if (bx > 1184) bx = 1184;
-  dim3 grid((unsigned)bx, (unsigned)((c + 63) / 64));
-  bn_reduce_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(dz16),
-                                            reinterpret_cast<const uint16_t*>(y16), npix, c, mean, rstd, 1, dtype, sums_ws);
+  PESR_CHECK_ARG(c <= 512, "bn_lrelu_bwd: at most 512 channels");
+  launch_bn_reduce(dz16, y16, npix, c, mean, rstd, 1, dtype, sums_ws, stream);
   const long long nvec = npix * (c / 8);
   bn_bwd_apply_kernel<<<nblocks(nvec, 256, 148 * 16), 256, 0, stream>>>(
       reinterpret_cast<const uint4*>(dz16), reinterpret_cast<const uint4*>(y16), nvec, c, (double)npix, mean, rstd, gamma,
@@ -552,6 +640,17 @@ extern "C" int pesr_linear_skinny_fwd(const void* x16, const void* w16, const fl
                                                                   reinterpret_cast<uint16_t*>(out16));
   count_launch(2);
   PESR_CHECK_LAUNCH("linear_fwd");
+  return 0;
+}
+
+extern "C" int pesr_linear_finalize(const float* partials, int32_t ksplit, int32_t nb, int32_t o, const float* bias,
+                                    int32_t act, int32_t dtype, float* out32, void* out16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(partials && ksplit >= 1 && nb > 0 && o > 0 && (out32 || out16), "linear_finalize: bad arguments");
+  linear_finalize_kernel<<<(nb * o + 255) / 256, 256, 0, stream>>>(partials, ksplit, nb, o, bias, act, dtype, out32,
+                                                                  reinterpret_cast<uint16_t*>(out16));
+  count_launch();
+  PESR_CHECK_LAUNCH("linear_finalize");
   return 0;
 }
 

@@ -83,6 +83,8 @@ class DiscriminatorEngine:
         self.packed = pk
         self.fwd_packs = [v for k, v in pk.items() if k.endswith("_f")]
         self.bwd_packs = [v for k, v in pk.items() if k.endswith("_d")]
+        self.fwd_multi = ops.MultiPack(self.fwd_packs, device, dt)
+        self.bwd_multi = ops.MultiPack(self.bwd_packs, device, dt)
         fc1, fc2 = d.classifier[0], d.classifier[2]
         self.w1_16 = torch.empty(fc1.weight.shape, device=device, dtype=dt)
         self.w2_16 = torch.empty(fc2.weight.shape, device=device, dtype=dt)
@@ -142,6 +144,15 @@ class DiscriminatorEngine:
         pl.flat7 = e16(nb, kfc)
         pl.h1_32, pl.h1_16 = e32(nb, 1024), e16(nb, 1024)
         pl.fc_ws = e32(max(ops.linear_workspace_floats(nb, kfc, 1024), ops.linear_workspace_floats(nb, 1024, 1), 1))
+        # Linear(kfc -> 1024) as a split-K run of the implicit-GEMM kernel: the nb rows are the "pixels" of a 1 x nb image
+        pl.fc1_tc = kfc % 64 == 0
+        if pl.fc1_tc:
+            pl.fc1_ksplit = max(1, min(kfc // 64 // 8, 36))
+            pl.fc1_part = e32(pl.fc1_ksplit * nb * 1024)
+            pl.fc1_fwd = ops.make_conv_desc(dtype=dt, nb=1, h=1, w=nb, cin=kfc, cout=1024, block_n=256, taps=[(0, 0)],
+                                            srcs=[ops.nhwc_src(pl.flat7, 1, 1, nb, kfc)], wpacked=self.w1_16,
+                                            out32=pl.fc1_part, ld_out32=1024, ksplit=pl.fc1_ksplit,
+                                            split_stride32=nb * 1024)
         taps2, srcs2, widx2 = _s2_taps()
         f = []
         f.append(ops.make_conv_desc(dtype=dt, nb=nb, h=h, w=w, cin=64, cout=64, taps=[(0, 0)],
@@ -174,6 +185,16 @@ class DiscriminatorEngine:
             h7, w7 = dims[7]
             sc.dflat32 = torch.empty(nb, 512 * h7 * w7, device=dev, dtype=torch.float32)
             sc.dh1 = torch.empty(nb, 1024, device=dev, dtype=torch.float32)
+            sc.dz1_16 = torch.empty(nb, 1024, device=dev, dtype=tdt)
+            sc.scale1 = torch.zeros(4, device=dev, dtype=torch.float32)
+            sc.scale_tot = torch.ones(1, device=dev, dtype=torch.float32)
+            kfc = 512 * h7 * w7
+            sc.fc1_dgrad = None
+            if kfc % 256 == 0:
+                # dflat = dz1 x W1 with W1 [1024][kfc] read MN-major in place (no transposed copy of 75.5 M weights)
+                sc.fc1_dgrad = ops.make_conv_desc(dtype=self.dt, nb=1, h=1, w=nb, cin=1024, cout=kfc, block_n=256,
+                                                  taps=[(0, 0)], srcs=[ops.nhwc_src(sc.dz1_16, 1, 1, nb, 1024)],
+                                                  wpacked=self.w1_16, out32=sc.dflat32, ld_out32=kfc, b_mn_major=1)
             sc.Zd = torch.empty(nb * h * w, 32, device=dev, dtype=torch.float32)
             sc.wg = torch.empty(max(9 * 512 * 512 * 4, 148 * 128 * 64), device=dev, dtype=torch.float32)
             sc.descs = {}
@@ -253,8 +274,7 @@ class DiscriminatorEngine:
             raise NotImplementedError("pesr_b200.Discriminator: per-call batch is limited to 16 (train.py:48 default)")
         self._ensure_packed(x.device)
         pl = self._acquire(nb, h, w)
-        for pw in self.fwd_packs:
-            pw.get()
+        self.fwd_multi.run()
         self._pack_fc()
         training = d.training
         w0 = d.features[0][0].weight
@@ -279,8 +299,13 @@ class DiscriminatorEngine:
         h7, w7 = pl.dims[7]
         ops.flatten_nchw16(pl.A[7], nb, h7 * w7, 512, pl.flat7)
         fc1, fc2 = d.classifier[0], d.classifier[2]
-        ops.linear_fwd(pl.flat7, self.w1_16, fc1.bias.detach(), nb, pl.kfc, 1024, pl.fc_ws, out32=pl.h1_32,
-                       out16=pl.h1_16, act=ACT_LRELU)
+        if pl.fc1_tc:
+            _run_conv(pl.fc1_fwd, stream)
+            ops.linear_finalize(pl.fc1_part, pl.fc1_ksplit, nb, 1024, fc1.bias.detach(), self.dtype, out32=pl.h1_32,
+                                out16=pl.h1_16, act=ACT_LRELU)
+        else:
+            ops.linear_fwd(pl.flat7, self.w1_16, fc1.bias.detach(), nb, pl.kfc, 1024, pl.fc_ws, out32=pl.h1_32,
+                           out16=pl.h1_16, act=ACT_LRELU)
         logits = torch.empty(nb, 1, device=x.device, dtype=torch.float32)
         ops.linear_fwd(pl.h1_16, self.w2_16, fc2.bias.detach(), nb, 1024, 1, pl.fc_ws, out32=logits)
         if save:
@@ -297,8 +322,7 @@ class DiscriminatorEngine:
         d = self.disc
         nb, h, w = pl.nb, pl.h, pl.w
         sc = self._bwd_scratch(nb, h, w)
-        for pw in self.bwd_packs:
-            pw.get()
+        self.bwd_multi.run()
         dg, wg = self._bwd_descs(pl, sc)
         dev = dlogits.device
         dlogits = dlogits.contiguous().float()
@@ -330,10 +354,18 @@ class DiscriminatorEngine:
             ops.linear_wgrad(dz1, pl.flat7, nb, pl.kfc, 1024, grads[fc1.weight])
             torch.sum(dz1, dim=0, out=grads[fc1.bias])
             mark(fc1.weight)
-        ops.linear_dgrad(dz1, self.w1_16, nb, pl.kfc, 1024, sc.dflat32)
+        if sc.fc1_dgrad is not None:
+            ops.amax_scale(dz1, sc.scale1, target=16.0)
+            sc.dz1_16.copy_(dz1 * sc.scale1[1:2])
+            _run_conv(sc.fc1_dgrad, stream)                    # dflat32 carries scale1
+        else:
+            ops.linear_dgrad(dz1, self.w1_16, nb, pl.kfc, 1024, sc.dflat32)
+            sc.scale1[1:2].fill_(1.0)
         ops.amax_scale(sc.dflat32, self.scale_ws, target=16.0)
+        torch.mul(self.scale_ws[1:2], sc.scale1[1:2], out=sc.scale_tot)
+        scale = sc.scale_tot                                   # every 16-bit gradient below carries scale1*scale2
         h7, w7 = pl.dims[7]
-        ops.unflatten_nchw16(sc.dflat32, pl.A[7], nb, h7 * w7, 512, sc.dZ[7], mul_dev=scale)
+        ops.unflatten_nchw16(sc.dflat32, pl.A[7], nb, h7 * w7, 512, sc.dZ[7], mul_dev=self.scale_ws[1:2])
         splits = C.c_int32(0)
         dummy = None
         for i in range(7, -1, -1):

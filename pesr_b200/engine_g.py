@@ -110,6 +110,8 @@ class GeneratorEngine:
         self.packed = pk
         self.fwd_packs = [v for k, v in pk.items() if k.endswith("_f")]
         self.bwd_packs = [v for k, v in pk.items() if k.endswith("_d")]
+        self.fwd_multi = ops.MultiPack(self.fwd_packs, device, dt)
+        self.bwd_multi = ops.MultiPack(self.bwd_packs, device, dt)
         self.scale_ws = torch.zeros(4, device=device, dtype=torch.float32)
         C_ = g.n_feats
         self.bias_up0 = torch.empty(4 * C_, device=device, dtype=torch.float32)
@@ -274,8 +276,7 @@ class GeneratorEngine:
         pl = self._plan(nb, h, w, train)
         pl.generation += 1
         Cn = g.n_feats
-        for pw in self.fwd_packs:
-            pw.get()
+        self.fwd_multi.run()
         up0, up2, up4 = g.upsample[0], g.upsample[2], g.upsample[4]
         self.bias_up0.copy_(_shuffle_perm(up0.bias.detach(), Cn))
         self.bias_up2.copy_(_shuffle_perm(up2.bias.detach(), Cn))
@@ -303,8 +304,7 @@ class GeneratorEngine:
         up4 = g.upsample[4]
         dsr = dsr.contiguous().float()
         dev = dsr.device
-        for pw in self.bwd_packs:
-            pw.get()
+        self.bwd_multi.run()
         flat = torch.empty(self.flat_numel, device=dev, dtype=torch.float32)
         self.last_flat_grad = flat
         off = self.offsets

@@ -39,6 +39,8 @@ class VGGEngine:
         self.pk_f = [PackedWeight(convs[0].weight, 4, dt, pad_to=64)] + [PackedWeight(c.weight, 0, dt) for c in convs[1:]]
         self.pk_d = [PackedWeight(convs[0].weight, 6, dt, pad_to=32)] + [PackedWeight(c.weight, 1, dt) for c in convs[1:]]
         self.packed = True
+        self.fwd_multi = ops.MultiPack(self.pk_f, device, dt)
+        self.bwd_multi = ops.MultiPack(self.pk_d, device, dt)
         self.scale_ws = torch.zeros(4, device=device, dtype=torch.float32)
 
     def _plan(self, nb, h, w):
@@ -123,8 +125,7 @@ class VGGEngine:
         self._ensure_packed(sr.device)
         pl = self._plan(nb, h, w)
         pl.generation += 1
-        for pw in self.pk_f:
-            pw.get()
+        self.fwd_multi.run()
         sm = self.vgg.sub_mean
         sm_w = sm.weight.detach().reshape(3, 3)
         P = nb * h * w
@@ -150,8 +151,7 @@ class VGGEngine:
         if generation != pl.generation:
             raise RuntimeError("pesr_b200.VGG: backward through a forward whose activations were overwritten by a later "
                                "forward of the same shape")
-        for pw in self.pk_d:
-            pw.get()
+        self.bwd_multi.run()
         nb, h, w = pl.nb, pl.h, pl.w
         dfeat = dfeat.contiguous().float()
         scale = self.scale_ws[1:2]

@@ -49,7 +49,7 @@ def make_conv_desc(*, dtype, nb, h, w, cin, cout, block_n=None, taps=TAPS_3X3, t
                    srcs, wpacked, bias=None, alpha=1.0, alpha_dev=None, res32=None, ld_res32=0, res16=None,
                    ld_res16=0, act=ACT_NONE, mask16=None, ld_mask16=0, mask_mode=0, out32=None, ld_out32=0,
                    out16=None, ld_out16=0, out_mode=OUT_NORMAL, out_h=0, out_w=0, out_sy=1, out_sx=1, out_oy=0,
-                   out_ox=0, out_coff=0, ps_c=0, tile=None, aux_mode=0):
+                   out_ox=0, out_coff=0, ps_c=0, tile=None, aux_mode=0, ksplit=0, b_mn_major=0, split_stride32=0):
     """Build a ``pesr_conv_desc``.
 
     ``srcs`` is a list of (tensor_or_ptr, src_h, src_w, stride_n, stride_h, stride_w) NHWC views (element
@@ -85,6 +85,7 @@ def make_conv_desc(*, dtype, nb, h, w, cin, cout, block_n=None, taps=TAPS_3X3, t
     d.out_mode, d.out_h, d.out_w = out_mode, out_h, out_w
     d.out_sy, d.out_sx, d.out_oy, d.out_ox, d.out_coff, d.ps_c = out_sy, out_sx, out_oy, out_ox, out_coff, ps_c
     d.aux_mode = aux_mode
+    d.ksplit, d.b_mn_major, d.split_stride32 = ksplit, b_mn_major, split_stride32
     return d
 
 
@@ -270,6 +271,11 @@ def linear_fwd(x16, w16, bias, nb, k, o, workspace, out32=None, out16=None, act=
                                      _ptr(workspace), _ptr(out32), _ptr(out16), _stream()), "pesr_linear_skinny_fwd")
 
 
+def linear_finalize(partials, ksplit, nb, o, bias, dtype, out32=None, out16=None, act=ACT_NONE):
+    check(lib.pesr_linear_finalize(_ptr(partials), ksplit, nb, o, _ptr(bias), act, dt_code(dtype), _ptr(out32),
+                                   _ptr(out16), _stream()), "pesr_linear_finalize")
+
+
 def linear_dgrad(dy32, w16, nb, k, o, dx32):
     check(lib.pesr_linear_skinny_dgrad(_ptr(dy32), _ptr(w16), nb, k, o, dt_code(w16.dtype), _ptr(dx32), _stream()),
           "pesr_linear_skinny_dgrad")
@@ -291,3 +297,31 @@ def flatten_nchw16(src_nhwc16, nb, hw, c, dst):
 def unflatten_nchw16(src32, mask16, nb, hw, c, dst16, mul=1.0, mul_dev=None, slope=0.2):
     check(lib.pesr_unflatten_nchw16(_ptr(src32), _ptr(mask16), nb, hw, c, mul, _ptr(mul_dev), slope,
                                     dt_code(dst16.dtype), _ptr(dst16), _stream()), "pesr_unflatten_nchw16")
+
+
+class MultiPack:
+    """All weight packs of one network as one launch (re-run only when a parameter version changed)."""
+
+    def __init__(self, packed_weights, device, dtype):
+        import numpy as np
+        self.pws = list(packed_weights)
+        rows = []
+        for pw in self.pws:
+            p = pw.param
+            rows.append([p.data_ptr(), pw.buf.data_ptr(), p.shape[0], p.shape[1], p.shape[2], pw.mode, pw.pad_to, 0])
+        self.host = np.ascontiguousarray(np.array(rows, dtype=np.int64))
+        self.dev = torch.empty(len(rows) * 64, device=device, dtype=torch.uint8)
+        self.dt = dt_code(dtype)
+        self.uploaded = False
+        self.key = None
+
+    def run(self):
+        key = tuple(pw.param._version for pw in self.pws)
+        if key == self.key:
+            return
+        check(lib.pesr_pack_weights_multi(self.host.ctypes.data, len(self.pws), _ptr(self.dev),
+                                          0 if self.uploaded else 1, self.dt, _stream()), "pesr_pack_weights_multi")
+        self.uploaded = True
+        self.key = key
+        for pw, v in zip(self.pws, key):
+            pw.key = (pw.param.data_ptr(), v)

@@ -123,7 +123,7 @@ def test_gan_step_losses_match_oracle():
     assert ge[len(ge) // 2] < 0.35      # dominated by the VGG mask-flip noise in d(loss)/d(sr), see module docstring
     # both optimisers stepped: every G weight moved by exactly lr on the first Adam step
     moved = [float((p.detach() - g_before[k]).abs().max()) for k, p in G.named_parameters()]
-    assert max(moved) < 5.1e-5 and min(moved) > 0
+    assert max(moved) < 6.2e-5 and min(moved) > 0   # lr = 5e-5 plus fp32 rounding of |p| ~ 114 (MeanShift bias)
     # second step runs on re-packed weights and reuses every plan
     got2 = steps.gan_step(G, D, V, optG, optD, lr.cuda(), hr.cuda(), cfg)
     assert torch.isfinite(got2).all()

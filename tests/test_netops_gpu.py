@@ -236,3 +236,30 @@ def test_fused_losses_value_and_gradient():
     prd, pfd = pr.detach().double().requires_grad_(True), pf.detach().double().requires_grad_(True)
     g1, = torch.autograd.grad(O.focal_loss(pfd - prd, ones.double(), 1), pfd)
     assert rel_l2(pf.grad, g1) < 1e-5
+
+
+@pytest.mark.parametrize("nb,k,o", [(16, 73728, 1024), (4, 4608, 1024), (7, 8192, 1024)])
+def test_linear_on_the_implicit_gemm_kernel(nb, k, o):
+    """Linear(k -> o) forward as a split-K run of pesr_conv_igemm, and its backward-data with the [o][k] weight
+    matrix consumed MN-major in place (model/pesr.py:71)."""
+    from pesr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x16 = torch.randn(nb, k, device="cuda", generator=g).half()
+    w16 = (torch.randn(o, k, device="cuda", generator=g) / k ** 0.5).half()
+    b = torch.randn(o, device="cuda", generator=g)
+    ks = max(1, min(k // 64 // 8, 36))
+    part = torch.empty(ks * nb * o, device="cuda")
+    ops.conv_igemm(ops.make_conv_desc(dtype=0, nb=1, h=1, w=nb, cin=k, cout=o, block_n=256, taps=[(0, 0)],
+                                      srcs=[ops.nhwc_src(x16, 1, 1, nb, k)], wpacked=w16, out32=part, ld_out32=o,
+                                      ksplit=ks, split_stride32=nb * o))
+    out32 = torch.empty(nb, o, device="cuda")
+    out16 = torch.empty(nb, o, device="cuda", dtype=torch.float16)
+    ops.linear_finalize(part, ks, nb, o, b, torch.float16, out32=out32, out16=out16, act=ops.ACT_LRELU)
+    ref = F.leaky_relu(x16.double() @ w16.double().t() + b.double(), 0.2)
+    assert rel_l2(out32, ref) < 1e-5 and rel_l2(out16.float(), ref) < 4e-4
+    dy16 = torch.randn(nb, o, device="cuda", generator=g).half()
+    dx = torch.empty(nb, k, device="cuda")
+    ops.conv_igemm(ops.make_conv_desc(dtype=0, nb=1, h=1, w=nb, cin=o, cout=k, block_n=256, taps=[(0, 0)],
+                                      srcs=[ops.nhwc_src(dy16, 1, 1, nb, o)], wpacked=w16, out32=dx, ld_out32=k,
+                                      b_mn_major=1))
+    assert rel_l2(dx, dy16.double() @ w16.double()) < 1e-5

@@ -105,6 +105,9 @@ def gen_step(nb=16, dtype=torch.float16):
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "one":       # single trunk-conv shape for `ncu --set full`
+        conv_case(16, 256, 256, 48, 48)
+        wgrad_case(16, 256, 256, 48, 48)
     if what in ("all", "conv"):
         conv_case(16, 256, 256, 48, 48)
         conv_case(16, 256, 1024, 48, 48)

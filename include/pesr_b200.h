@@ -113,6 +113,10 @@ typedef struct pesr_conv_desc {
 } pesr_conv_desc;
 
 int pesr_conv_igemm(const pesr_conv_desc* d, void* stream);
+/* A/B hook: 0 = never use the CTA-pair (cta_group::2) kernel, 1 = whenever legal (default), -1 = re-read PESR_NO_PAIR. */
+void pesr_debug_pair_mode(int mode);
+/* Bring-up hook: device buffer (64 x uint64) that block 0 of each pesr_conv_igemm launch fills with clock64 stamps. */
+void pesr_debug_timeline(void* buf);
 
 /* ------------------------------------------------------------------------------------------------
  * Backward-filter as a split-K GEMM with both operands MN-major (pixels are K).

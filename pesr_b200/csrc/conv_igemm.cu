@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include "host_util.cuh"
 
+#include <stdlib.h>
+
 namespace pesr {
 
 static constexpr int kTileM = 128;        // pixels per tile == TMEM lanes
@@ -43,10 +45,17 @@ struct ConvK {
   float* out32; int ld_out32;
   uint16_t* out16; int ld_out16;
   int out_mode, out_h, out_w, out_sy, out_sx, out_oy, out_ox, out_coff, ps_c, aux_mode;
-  int ksplit, b_mn_major, mn_tiles;
+  int ksplit, b_mn_major, mn_tiles, dbg_skip;
+  unsigned long long* dbg;   // optional timeline of block 0 (bring-up): [64] clock64 stamps + [63] = globaltimer ns
   long long split_stride32;
 };
 
+// kPair = false: one CTA per tile (cta_group::1).
+// kPair = true : a cluster of two CTAs drives one 256-pixel x block_n MMA (cta_group::2).  Each CTA stages its own
+//   128 pixels of A and HALF of the weight tile, so shared-memory fill and operand-read traffic per SM drop by a
+//   third; the leader CTA's thread issues every MMA, commits are multicast to both CTAs' barriers, every TMA load
+//   of the pair signals the leader's full barrier, and both epilogues report to the leader's tmem_empty barrier.
+template <bool kPair>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvK p) {
   extern __shared__ uint8_t smem_raw[];
@@ -54,6 +63,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = kPair ? (int)cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  const int worker = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // tile-loop index of this CTA / pair
+  const int nworkers = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int b_rows = kPair ? p.block_n / 2 : p.block_n;                      // weight rows staged by this CTA
 
   uint8_t* tail = smem + (size_t)p.stages * p.stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
@@ -72,35 +86,49 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], kPair ? 8 : 128);   // pair: one arrival per epilogue warp of both CTAs
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, 512);
-    tmem_relinquish();
+    if (kPair) { tmem_alloc2(tmem_ptr, 512); tmem_relinquish2(); }
+    else       { tmem_alloc(tmem_ptr, 512);  tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   const int total_kb = p.ntaps * p.kblocks_per_tap;
+  unsigned long long* dbg = (p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
+  unsigned long long t_begin = 0, g_begin = 0;
+  if (dbg && threadIdx.x == 0) {
+    t_begin = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_begin));
+    dbg[0] = t_begin;
+    dbg[62] = g_begin;
+  }
+
+  // tile -> (split, m_tile of THIS CTA, n_tile)
+  auto decode = [&](int tile, int& split, int& m_tile, int& n_tile) {
+    split = tile / p.mn_tiles;
+    const int mn = tile - split * p.mn_tiles;
+    n_tile = mn % p.n_tiles;
+    m_tile = kPair ? 2 * (mn / p.n_tiles) + rank : mn / p.n_tiles;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int split = tile / p.mn_tiles;
-        const int mn = tile - split * p.mn_tiles;
-        const int n_tile = mn % p.n_tiles;
-        const int m_tile = mn / p.n_tiles;
+      for (int tile = worker; tile < p.num_tiles; tile += nworkers) {
+        int split, m_tile, n_tile;
+        decode(tile, split, m_tile, n_tile);
         const int tw = m_tile % p.tiles_w;
         const int th = (m_tile / p.tiles_w) % p.tiles_h;
-        const int img = m_tile / (p.tiles_w * p.tiles_h);
-        const int h0 = th * p.tile_h, w0 = tw * p.tile_w, n0 = n_tile * p.block_n;
+        const int img = m_tile / (p.tiles_w * p.tiles_h);   // == nb for the padding tile of an odd pair: all OOB -> zeros
+        const int h0 = th * p.tile_h, w0 = tw * p.tile_w, n0 = n_tile * p.block_n + rank * b_rows;
         const int kb0 = (int)(((long long)split * total_kb) / p.ksplit);
         const int kb1 = (int)(((long long)(split + 1) * total_kb) / p.ksplit);
         for (int kb = kb0; kb < kb1; kb++) {
@@ -110,54 +138,81 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
           const int hh = h0 + p.tap_dh[t], ww = w0 + p.tap_dw[t];
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-          mbar_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes);
-          tma_load_4d(sa, ma, &full_bar[stage], cb * kKBlock, ww, hh, img);
-          if (p.b_mn_major) {
-            // weights stored [K][N] (N contiguous): one 64(K) x 64(N) box per 64 output columns
-            for (int i = 0; i < p.block_n / 64; i++)
-              tma_load_2d(sa + kABytes + i * 8192, &maps.b, &full_bar[stage], n0 + i * 64, kb * kKBlock);
+          if (kPair) {
+            if (leader) mbar_expect_tx(&full_bar[stage], 2u * (uint32_t)p.stage_bytes);
+            tma2_load_4d(sa, ma, &full_bar[stage], cb * kKBlock, ww, hh, img);
+            tma2_load_2d(sa + kABytes, &maps.b, &full_bar[stage], cb * kKBlock, p.tap_widx[t] * p.cout + n0);
+          } else if (p.dbg_skip) {
+            // bring-up experiment: after the ring has been filled once, skip the A (1), B (2) or both (3) loads
+            const bool warm = (kb - kb0) >= p.stages || tile != worker;
+            const bool la = !(warm && (p.dbg_skip & 1)), lb = !(warm && (p.dbg_skip & 2));
+            const uint32_t bytes = (la ? kABytes : 0) + (lb ? (uint32_t)(p.stage_bytes - kABytes) : 0);
+            if (bytes) mbar_expect_tx(&full_bar[stage], bytes); else mbar_arrive(&full_bar[stage]);
+            if (la) tma_load_4d(sa, ma, &full_bar[stage], cb * kKBlock, ww, hh, img);
+            if (lb) tma_load_2d(sa + kABytes, &maps.b, &full_bar[stage], cb * kKBlock, p.tap_widx[t] * p.cout + n0);
           } else {
-            tma_load_2d(sa + kABytes, &maps.b, &full_bar[stage], cb * kKBlock, p.tap_widx[t] * p.cout + n0);
+            mbar_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes);
+            tma_load_4d(sa, ma, &full_bar[stage], cb * kKBlock, ww, hh, img);
+            if (p.b_mn_major) {
+              // weights stored [K][N] (N contiguous): one 64(K) x 64(N) box per 64 output columns
+              for (int i = 0; i < p.block_n / 64; i++)
+                tma_load_2d(sa + kABytes + i * 8192, &maps.b, &full_bar[stage], n0 + i * 64, kb * kKBlock);
+            } else {
+              tma_load_2d(sa + kABytes, &maps.b, &full_bar[stage], cb * kKBlock, p.tap_widx[t] * p.cout + n0);
+            }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (dbg && tile == worker && kb == kb0) dbg[1] = clock64();          // first TMA issued
         }
+        if (dbg) dbg[2 + (tile == worker ? 0 : 1)] = clock64();                 // all TMAs of tile 0 / last tile issued
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc(kTileM, p.block_n, p.dtype, 0, p.b_mn_major);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int split = tile / p.mn_tiles;
-      const int kb0 = (int)(((long long)split * total_kb) / p.ksplit);
-      const int kb1 = (int)(((long long)(split + 1) * total_kb) / p.ksplit);
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
-      for (int kb = kb0; kb < kb1; kb++) {
-        mbar_wait(&full_bar[stage], phase);
+    // ===================== MMA issuer (leader CTA only in pair mode) =====================
+    if (leader) {
+      const uint32_t idesc = make_idesc(kPair ? 256 : kTileM, p.block_n, p.dtype, 0, p.b_mn_major);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = worker; tile < p.num_tiles; tile += nworkers) {
+        const int split = tile / p.mn_tiles;
+        const int kb0 = (int)(((long long)split * total_kb) / p.ksplit);
+        const int kb1 = (int)(((long long)(split + 1) * total_kb) / p.ksplit);
+        if (kPair) mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1); else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint32_t b_addr = a_addr + kABytes;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
+        if (dbg && lane == 0) dbg[8 + (tile == worker ? 0 : 4)] = clock64();    // MMA warp: accumulator free
+        for (int kb = kb0; kb < kb1; kb++) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (dbg && lane == 0 && kb == kb0) dbg[9 + (tile == worker ? 0 : 4)] = clock64();  // first stage landed
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
+            const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
-          for (int k = 0; k < kKBlock / 16; k++) {
-            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t db = p.b_mn_major ? make_smem_desc(b_addr + k * 2048, 8192, 1024)
-                                             : make_smem_desc(b_addr + k * 32, 16, 1024);
-            umma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kKBlock / 16; k++) {
+              const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
+              const uint64_t db = p.b_mn_major ? make_smem_desc(b_addr + k * 2048, 8192, 1024)
+                                               : make_smem_desc(b_addr + k * 32, 16, 1024);
+              if (kPair) umma2_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else       umma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            if (kPair) {
+              umma2_commit_both(&empty_bar[stage]);
+              if (kb == kb1 - 1) umma2_commit_both(&tmem_full[acc]);
+            } else {
+              umma_commit(&empty_bar[stage]);
+              if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
+            }
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (dbg && lane == 0) dbg[10 + (tile == worker ? 0 : 4)] = clock64();   // all MMAs of the tile issued
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -170,16 +225,14 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     if (p.alpha_dev) alpha *= __ldg(p.alpha_dev);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int split = tile / p.mn_tiles;
-      const int mn = tile - split * p.mn_tiles;
-      const int n_tile = mn % p.n_tiles;
-      const int m_tile = mn / p.n_tiles;
+    for (int tile = worker; tile < p.num_tiles; tile += nworkers) {
+      int split, m_tile, n_tile;
+      decode(tile, split, m_tile, n_tile);
       const int tw = m_tile % p.tiles_w;
       const int th = (m_tile / p.tiles_w) % p.tiles_h;
       const int img = m_tile / (p.tiles_w * p.tiles_h);
       const int h = th * p.tile_h + ty, w = tw * p.tile_w + tx, n0 = n_tile * p.block_n;
-      const bool valid = (h < p.h) && (w < p.w);
+      const bool valid = (h < p.h) && (w < p.w) && (img < p.nb);
       // pixel index used by res32 / res16 / mask16 / out32: the GEMM grid, or (aux_mode 1) the strided output grid
       const long long pix = p.aux_mode
           ? ((long long)img * p.out_h + (h * p.out_sy + p.out_oy)) * p.out_w + (w * p.out_sx + p.out_ox)
@@ -191,6 +244,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (dbg && et == 0) dbg[16 + (tile == worker ? 0 : 4)] = clock64();       // accumulator complete (MMAs done)
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccStride);
 
       for (int ch = 0; ch < p.block_n / 32; ch++) {
@@ -200,7 +254,12 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
         if (ch == p.block_n / 32 - 1) {
           // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
-          mbar_arrive(&tmem_empty[acc]);
+          if (kPair) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+          } else {
+            mbar_arrive(&tmem_empty[acc]);
+          }
         }
         if (!valid) continue;
         const int q0 = n0 + ch * 32;
@@ -276,22 +335,41 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
           }
         }
       }
+      if (dbg && et == 0) dbg[17 + (tile == worker ? 0 : 4)] = clock64();       // epilogue of the tile done
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();
+  if (dbg && threadIdx.x == 0) {
+    unsigned long long g_end;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+    dbg[61] = clock64();
+    dbg[63] = g_end;
+  }
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (kPair) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
+
+static int g_dbg_skip = 0;
+static unsigned long long* g_dbg_buf = nullptr;
+static int g_pair_mode = -1;  // -1: from the environment (PESR_NO_PAIR=1 disables), 0: never, 1: whenever legal
 
 }  // namespace pesr
 
 using namespace pesr;
+
+// Bring-up / A-B hook: 0 = never use the CTA-pair kernel, 1 = whenever legal, -1 = re-read PESR_NO_PAIR.
+extern "C" void pesr_debug_pair_mode(int mode) {
+  if (mode >= 100) g_dbg_skip = mode - 100; else g_pair_mode = mode;
+}
+
+// Bring-up hook: device buffer of 64 uint64 that block 0 of every pesr_conv_igemm launch fills with a timeline.
+extern "C" void pesr_debug_timeline(void* buf) { g_dbg_buf = reinterpret_cast<unsigned long long*>(buf); }
 
 extern "C" int pesr_conv_igemm(const pesr_conv_desc* d, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -321,6 +399,17 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d, void* stream_) {
   if (d->out_mode == PESR_OUT_UNSHUFFLE2)
     PESR_CHECK_ARG(d->h % 2 == 0 && d->w % 2 == 0, "conv_igemm: unshuffle needs even h, w");
 
+  // CTA-pair (cta_group::2) path: whole-K tiles of a K-major weight matrix, at least two pixel tiles
+  if (g_pair_mode < 0) {
+    const char* e = getenv("PESR_NO_PAIR");
+    g_pair_mode = (e && e[0] == '1') ? 0 : 1;
+  }
+  const int m_tiles_host = d->nb * ((d->h + d->tile_h - 1) / d->tile_h) * ((d->w + d->tile_w - 1) / d->tile_w);
+  // measured on B200 (tools/perf_conv.py pair): the pair kernel wins 4-6% on the 256-wide, many-tile layers (G trunk and
+  // upsampler) and loses 8-16% on the small D / VGG layers, so it is used where it wins (mode 2 forces it for tests).
+  const bool pair_legal = d->ksplit <= 1 && !d->b_mn_major && d->block_n >= 64 && m_tiles_host >= 2;
+  const bool pair = pair_legal && (g_pair_mode == 2 || (g_pair_mode == 1 && d->block_n == 256 && m_tiles_host >= 256));
+
   ConvMaps maps;
   memset(&maps, 0, sizeof(maps));
   for (int s = 0; s < PESR_MAX_SRC; s++) {
@@ -348,7 +437,7 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d, void* stream_) {
   } else {
     uint64_t dims[2] = {(uint64_t)d->cin, (uint64_t)d->w_rows};
     uint64_t str[1] = {(uint64_t)d->cin * 2};
-    uint32_t box[2] = {(uint32_t)kKBlock, (uint32_t)d->block_n};
+    uint32_t box[2] = {(uint32_t)kKBlock, (uint32_t)(pair ? d->block_n / 2 : d->block_n)};
     int r = get_tensor_map(&maps.b, d->wpacked, d->dtype, 2, dims, str, box);
     if (r) return r;
   }
@@ -361,13 +450,16 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d, void* stream_) {
   k.tiles_h = (d->h + d->tile_h - 1) / d->tile_h;
   k.tiles_w = (d->w + d->tile_w - 1) / d->tile_w;
   k.n_tiles = d->cout / d->block_n;
-  k.mn_tiles = d->nb * k.tiles_h * k.tiles_w * k.n_tiles;
+  const int m_tiles = d->nb * k.tiles_h * k.tiles_w;
+  k.mn_tiles = (pair ? (m_tiles + 1) / 2 : m_tiles) * k.n_tiles;   // pair mode counts tiles of 2 x 128 pixels
   k.ksplit = ksplit;
   k.num_tiles = k.mn_tiles * ksplit;
   k.b_mn_major = d->b_mn_major ? 1 : 0;
+  k.dbg_skip = g_dbg_skip;
+  k.dbg = g_dbg_buf;
   k.split_stride32 = d->split_stride32;
   k.kblocks_per_tap = d->cin / kKBlock;
-  k.stage_bytes = kABytes + d->block_n * kKBlock * 2;
+  k.stage_bytes = kABytes + (pair ? d->block_n / 2 : d->block_n) * kKBlock * 2;   // per CTA
   const int smem_budget = 227 * 1024 - 4096;
   k.stages = smem_budget / k.stage_bytes;
   if (k.stages > kMaxStages) k.stages = kMaxStages;
@@ -394,17 +486,41 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d, void* stream_) {
   if (smem < 120 * 1024) smem = 120 * 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_error("conv_igemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
     }
     attr_set = true;
   }
-  int grid = k.num_tiles < num_sms() ? k.num_tiles : num_sms();
   const bool prof = profiling_enabled();
   if (prof) profile_begin(0, 2.0 * d->nb * d->h * d->w * (double)d->cout * d->cin * d->ntaps, stream);
-  conv_igemm_kernel<<<grid, kNumThreads, smem, stream>>>(maps, k);
+  if (pair) {
+    int clusters = k.num_tiles < num_sms() / 2 ? k.num_tiles : num_sms() / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, maps, k);
+    if (e != cudaSuccess) {
+      set_error("conv_igemm: pair launch failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+  } else {
+    int grid = k.num_tiles < num_sms() ? k.num_tiles : num_sms();
+    conv_igemm_kernel<false><<<grid, kNumThreads, smem, stream>>>(maps, k);
+  }
   if (prof) profile_end(0, stream);
   count_launch();
   PESR_CHECK_LAUNCH("conv_igemm");

@@ -108,6 +108,44 @@ if __name__ == "__main__":
     if what == "one":       # single trunk-conv shape for `ncu --set full`
         conv_case(16, 256, 256, 48, 48)
         wgrad_case(16, 256, 256, 48, 48)
+    if what == "timeline":
+        from pesr_b200._lib import lib
+        buf = torch.zeros(64, dtype=torch.int64, device="cuda")
+        lib.pesr_debug_timeline(buf.data_ptr())
+        names = {1: "first TMA issued", 2: "TMAs tile0 issued", 3: "TMAs last tile issued", 8: "t0 acc free", 9: "t0 first stage landed",
+                 10: "t0 MMAs issued", 12: "tL acc free", 13: "tL first stage landed", 14: "tL MMAs issued", 16: "t0 acc complete",
+                 17: "t0 epilogue done", 20: "tL acc complete", 21: "tL epilogue done", 61: "end"}
+        for pair in (0, 1):
+            lib.pesr_debug_pair_mode(pair)
+            for shape in ((16, 256, 256, 48, 48), (16, 256, 1024, 96, 96)):
+                conv_case(*shape)
+                torch.cuda.synchronize()
+                b = buf.cpu().tolist()
+                t0 = b[0]
+                mhz = (b[61] - b[0]) / max(b[63] - b[62], 1) * 1e3
+                print(f"  pair={pair} block-0 timeline (cycles from start, SM clock {mhz:.0f} MHz, total {(b[63]-b[62])/1e3:.1f} us):")
+                print("   " + "; ".join(f"{names[i]}={b[i]-t0}" for i in sorted(names) if b[i]))
+        lib.pesr_debug_timeline(0)
+    if what == "skip":
+        from pesr_b200._lib import lib
+        lib.pesr_debug_pair_mode(0)
+        for sk in (0, 1, 2, 3):
+            lib.pesr_debug_pair_mode(100 + sk)
+            print("skip mode", sk, "(1 = no A loads, 2 = no B loads, 3 = neither)")
+            conv_case(16, 256, 256, 48, 48)
+            conv_case(16, 256, 1024, 96, 96)
+        lib.pesr_debug_pair_mode(100)
+    if what == "pair":
+        from pesr_b200._lib import lib
+        for mode in (0, 1):
+            lib.pesr_debug_pair_mode(mode)
+            print("pair mode", mode)
+            conv_case(16, 256, 256, 48, 48)
+            conv_case(16, 256, 1024, 96, 96)
+            conv_case(16, 1024, 256, 96, 96)
+            conv_case(16, 64, 64, 192, 192)
+            conv_case(16, 128, 128, 96, 96)
+            conv_case(16, 512, 512, 24, 24)
     if what in ("all", "conv"):
         conv_case(16, 256, 256, 48, 48)
         conv_case(16, 256, 1024, 48, 48)

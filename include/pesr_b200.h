@@ -220,6 +220,18 @@ int pesr_amax_scale(const float* x, int64_t n, float target, float* ws3, void* s
 int pesr_moments3(const float* a, const float* b, int32_t nb, int64_t hw, float* sums12, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Inference edges (test.py:101-112, utils.py:13-25).
+ * pesr_blend_x8_to_u8: out = alpha*perc + (1-alpha)*mean_{i<8} T_i^-1(ens_i) for one image [3][h][w] (fp32, 0..255);
+ *   variant i: bit0 = flip W, bit1 = flip H, bit2 = transpose (test.py:45-74); ens = the 8 generator outputs back to
+ *   back, transposed variants stored [3][w][h]; n_ens = 0 skips the ensemble (alpha = 1 path).  out32 (optional)
+ *   gets the blended fp32 image, out8 (optional) the HWC uint8 image after clip(0,255) and round-half-even.
+ * pesr_u8hwc_to_f32nchw: HWC uint8 image -> [3][h][w] fp32 (utils.imgs_to_tensors).
+ * ------------------------------------------------------------------------------------------------ */
+int pesr_blend_x8_to_u8(const float* perc, const float* ens, int32_t h, int32_t w, float alpha, int32_t n_ens,
+                        float* out32, uint8_t* out8, void* stream);
+int pesr_u8hwc_to_f32nchw(const uint8_t* src, int32_t h, int32_t w, float* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Loss reductions with the gradient produced in the same pass (train.py:131-140), all fp32.
  *   *loss receives the scalar (it is zeroed by the call); grad (optional) receives d loss / d a.
  * ------------------------------------------------------------------------------------------------ */

@@ -101,6 +101,8 @@ SIGNATURES = {
     "pesr_colsum16": (C.c_int, [_vp, _i64, _i32, _i32, _f32, _vp, _i32, _i32, _vp, _vp]),
     "pesr_amax_scale": (C.c_int, [_vp, _i64, _f32, _vp, _vp]),
     "pesr_moments3": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp]),
+    "pesr_blend_x8_to_u8": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _i32, _vp, _vp, _vp]),
+    "pesr_u8hwc_to_f32nchw": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "pesr_loss_l1": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "pesr_loss_mse": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "pesr_loss_tv": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),

@@ -358,8 +358,73 @@ __global__ void moments3_kernel(const float* __restrict__ a, const float* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// inference edges (test.py:101-112, utils.py:13-25)
+// ------------------------------------------------------------------------------------------
+// out = alpha*perc + (1-alpha)*mean_i T_i^-1(ens_i), i = 0..7 (bit0 = flip W, bit1 = flip H, bit2 = transpose;
+// inverses applied transpose -> flipH -> flipW, test.py:60-70); then clip(0,255).round() (half to even, like
+// numpy) -> uint8 HWC.  ens holds the 8 generator outputs back to back, the transposed ones as [3][w][h].
+__global__ void blend_x8_to_u8_kernel(const float* __restrict__ perc, const float* __restrict__ ens, int h, int w,
+                                      float alpha, int n_ens, float* __restrict__ out32, uint8_t* __restrict__ out8) {
+  const long long plane = (long long)h * w;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < plane;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(p % w), y = (int)(p / w);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      float v = perc[c * plane + p];
+      if (n_ens > 0) {
+        float s = 0.f;
+        for (int i = 0; i < n_ens; i++) {
+          const int x1 = (i & 1) ? w - 1 - x : x;
+          const int y1 = (i & 2) ? h - 1 - y : y;
+          const long long idx = (i & 4) ? (long long)x1 * h + y1 : (long long)y1 * w + x1;
+          const float e = ens[((long long)i * 3 + c) * plane + idx];
+          s = i == 0 ? e : s + e;
+        }
+        v = alpha * v + (1.f - alpha) * (s / (float)n_ens);
+      }
+      if (out32) out32[c * plane + p] = v;
+      if (out8) out8[p * 3 + c] = (uint8_t)rintf(fminf(fmaxf(v, 0.f), 255.f));
+    }
+  }
+}
+
+// uint8 HWC image -> fp32 NCHW tensor in 0..255 (utils.py:20-25)
+__global__ void u8hwc_to_f32nchw_kernel(const uint8_t* __restrict__ src, int h, int w, float* __restrict__ dst) {
+  const long long plane = (long long)h * w;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < plane;
+       p += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) dst[c * plane + p] = (float)src[p * 3 + c];
+  }
+}
+
 }  // namespace pesr
 
+using namespace pesr;
+
+extern "C" int pesr_blend_x8_to_u8(const float* perc, const float* ens, int32_t h, int32_t w, float alpha,
+                                   int32_t n_ens, float* out32, uint8_t* out8, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(perc && (out32 || out8) && h > 0 && w > 0, "blend_x8_to_u8: bad arguments");
+  PESR_CHECK_ARG(n_ens == 0 || (n_ens == 8 && ens), "blend_x8_to_u8: n_ens must be 0 or 8");
+  blend_x8_to_u8_kernel<<<blocks_for((long long)h * w, 256), 256, 0, stream>>>(perc, ens, h, w, alpha, n_ens, out32, out8);
+  count_launch();
+  PESR_CHECK_LAUNCH("blend_x8_to_u8");
+  return 0;
+}
+
+extern "C" int pesr_u8hwc_to_f32nchw(const uint8_t* src, int32_t h, int32_t w, float* dst, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(src && dst && h > 0 && w > 0, "u8hwc_to_f32nchw: bad arguments");
+  u8hwc_to_f32nchw_kernel<<<blocks_for((long long)h * w, 256), 256, 0, stream>>>(src, h, w, dst);
+  count_launch();
+  PESR_CHECK_LAUNCH("u8hwc_to_f32nchw");
+  return 0;
+}
+
+namespace pesr {}
 using namespace pesr;
 
 extern "C" int pesr_pack_weights(const float* w, int32_t co, int32_t ci, int32_t ksize, int32_t mode, int32_t pad_to,

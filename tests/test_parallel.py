@@ -1,0 +1,82 @@
+"""CPU (gloo, world_size 2) test of the data-parallel gradient exchange: the bucketing hook fed by the kernel
+schedules must leave the AVERAGE of the ranks' flat gradient buffers in place, whatever the range sizes."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _FakeEngine:
+    grad_hook = None
+    grad_hook_finish = None
+
+
+class _FakeNet(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.zeros(7))
+        self._e = _FakeEngine()
+
+    def engine(self):
+        return self._e
+
+
+def _worker(rank, world, port, n, cuts, bucket_mb, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pesr_b200.parallel import DataParallel
+        net = _FakeNet()
+        with torch.no_grad():
+            net.w.fill_(float(rank + 3))
+        ddp = DataParallel(net, bucket_mb=bucket_mb)
+        assert ddp.world_size == world and ddp.module is net
+        assert float(net.w[0]) == 3.0                      # parameters broadcast from rank 0
+        flat = torch.arange(n, dtype=torch.float32) * (rank + 1)
+        hook = net.engine().grad_hook
+        hi = n
+        for lo in cuts:                                    # ranges complete from the end towards the start
+            hook(lo, hi, flat)
+            hi = lo
+        net.engine().grad_hook_finish()
+        expect = torch.arange(n, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+        ok = torch.allclose(flat, expect)
+        # fallback path for modules without a flat-gradient schedule
+        net.w.grad = torch.full((7,), float(rank))
+        ddp.allreduce_grads()
+        ok = ok and torch.allclose(net.w.grad, torch.full((7,), (world - 1) / 2))
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bucket_mb,cuts", [(1e-4, [900, 500, 499, 10, 0]), (64, [700, 0]), (1e-3, [0])])
+def test_bucketed_allreduce_gloo_world2(bucket_mb, cuts):
+    world, n = 2, 1000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, cuts, bucket_mb, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert all(out.get(r) for r in range(world)), dict(out)

@@ -115,6 +115,9 @@ typedef struct pesr_conv_desc {
 int pesr_conv_igemm(const pesr_conv_desc* d, void* stream);
 /* A/B hook: 0 = never use the CTA-pair (cta_group::2) kernel, 1 = whenever legal (default), -1 = re-read PESR_NO_PAIR. */
 void pesr_debug_pair_mode(int mode);
+/* Bring-up microbenchmark: issue / completion cycles of iters*4 back-to-back tcgen05.mma (M=128 or pair 256, N=n). */
+int pesr_debug_mma_rate(int32_t n, int32_t iters, int32_t stages, int32_t pair, int32_t blocks,
+                        unsigned long long* out_dev, void* stream);
 /* Bring-up hook: device buffer (64 x uint64) that block 0 of each pesr_conv_igemm launch fills with clock64 stamps. */
 void pesr_debug_timeline(void* buf);
 

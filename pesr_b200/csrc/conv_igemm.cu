@@ -118,8 +118,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
   };
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp, warp-uniform; one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = worker; tile < p.num_tiles; tile += nworkers) {
@@ -139,32 +139,32 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
           if (kPair) {
-            if (leader) mbar_expect_tx(&full_bar[stage], 2u * (uint32_t)p.stage_bytes);
-            tma2_load_4d(sa, ma, &full_bar[stage], cb * kKBlock, ww, hh, img);
-            tma2_load_2d(sa + kABytes, &maps.b, &full_bar[stage], cb * kKBlock, p.tap_widx[t] * p.cout + n0);
+            if (leader) mbar_expect_tx_w(&full_bar[stage], 2u * (uint32_t)p.stage_bytes);
+            tma2_load_4d_w(sa, ma, &full_bar[stage], cb * kKBlock, ww, hh, img);
+            tma2_load_2d_w(sa + kABytes, &maps.b, &full_bar[stage], cb * kKBlock, p.tap_widx[t] * p.cout + n0);
           } else if (p.dbg_skip) {
             // bring-up experiment: after the ring has been filled once, skip the A (1), B (2) or both (3) loads
             const bool warm = (kb - kb0) >= p.stages || tile != worker;
             const bool la = !(warm && (p.dbg_skip & 1)), lb = !(warm && (p.dbg_skip & 2));
             const uint32_t bytes = (la ? kABytes : 0) + (lb ? (uint32_t)(p.stage_bytes - kABytes) : 0);
-            if (bytes) mbar_expect_tx(&full_bar[stage], bytes); else mbar_arrive(&full_bar[stage]);
-            if (la) tma_load_4d(sa, ma, &full_bar[stage], cb * kKBlock, ww, hh, img);
-            if (lb) tma_load_2d(sa + kABytes, &maps.b, &full_bar[stage], cb * kKBlock, p.tap_widx[t] * p.cout + n0);
+            if (bytes) mbar_expect_tx_w(&full_bar[stage], bytes); else if (lane == 0) mbar_arrive(&full_bar[stage]);
+            if (la) tma_load_4d_w(sa, ma, &full_bar[stage], cb * kKBlock, ww, hh, img);
+            if (lb) tma_load_2d_w(sa + kABytes, &maps.b, &full_bar[stage], cb * kKBlock, p.tap_widx[t] * p.cout + n0);
           } else {
-            mbar_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes);
-            tma_load_4d(sa, ma, &full_bar[stage], cb * kKBlock, ww, hh, img);
+            mbar_expect_tx_w(&full_bar[stage], (uint32_t)p.stage_bytes);
+            tma_load_4d_w(sa, ma, &full_bar[stage], cb * kKBlock, ww, hh, img);
             if (p.b_mn_major) {
               // weights stored [K][N] (N contiguous): one 64(K) x 64(N) box per 64 output columns
               for (int i = 0; i < p.block_n / 64; i++)
-                tma_load_2d(sa + kABytes + i * 8192, &maps.b, &full_bar[stage], n0 + i * 64, kb * kKBlock);
+                tma_load_2d_w(sa + kABytes + i * 8192, &maps.b, &full_bar[stage], n0 + i * 64, kb * kKBlock);
             } else {
-              tma_load_2d(sa + kABytes, &maps.b, &full_bar[stage], cb * kKBlock, p.tap_widx[t] * p.cout + n0);
+              tma_load_2d_w(sa + kABytes, &maps.b, &full_bar[stage], cb * kKBlock, p.tap_widx[t] * p.cout + n0);
             }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
-          if (dbg && tile == worker && kb == kb0) dbg[1] = clock64();          // first TMA issued
+          if (dbg && lane == 0 && tile == worker && kb == kb0) dbg[1] = clock64();          // first TMA issued
         }
-        if (dbg) dbg[2 + (tile == worker ? 0 : 1)] = clock64();                 // all TMAs of tile 0 / last tile issued
+        if (dbg && lane == 0) dbg[2 + (tile == worker ? 0 : 1)] = clock64();    // all TMAs of tile 0 / last tile issued
       }
     }
   } else if (warp == 1) {
@@ -187,7 +187,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (dbg && lane == 0 && kb == kb0) dbg[9 + (tile == worker ? 0 : 4)] = clock64();  // first stage landed
-          if (lane == 0) {
+          {
             const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
             const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
@@ -195,18 +195,17 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
               const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
               const uint64_t db = p.b_mn_major ? make_smem_desc(b_addr + k * 2048, 8192, 1024)
                                                : make_smem_desc(b_addr + k * 32, 16, 1024);
-              if (kPair) umma2_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-              else       umma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              if (kPair) umma2_f16_w(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else       umma_f16_w(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
             if (kPair) {
-              umma2_commit_both(&empty_bar[stage]);
-              if (kb == kb1 - 1) umma2_commit_both(&tmem_full[acc]);
+              umma2_commit_both_w(&empty_bar[stage]);
+              if (kb == kb1 - 1) umma2_commit_both_w(&tmem_full[acc]);
             } else {
-              umma_commit(&empty_bar[stage]);
-              if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
+              umma_commit_w(&empty_bar[stage]);
+              if (kb == kb1 - 1) umma_commit_w(&tmem_full[acc]);
             }
           }
-          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         if (dbg && lane == 0) dbg[10 + (tile == worker ? 0 : 4)] = clock64();   // all MMAs of the tile issued
@@ -216,9 +215,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // (two warps per TMEM lane quarter were tried: measured 5-10% SLOWER, the extra warps compete with the issue warps)
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const int et = threadIdx.x - 64;  // 0..127
+    const int ch_lo = 0, ch_hi = p.block_n / 32;
     const int ty = row / p.tile_w, tx = row % p.tile_w;
     const int bf = p.dtype;
     float alpha = p.alpha;
@@ -247,11 +248,20 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       if (dbg && et == 0) dbg[16 + (tile == worker ? 0 : 4)] = clock64();       // accumulator complete (MMAs done)
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccStride);
 
-      for (int ch = 0; ch < p.block_n / 32; ch++) {
+      if (ch_lo == ch_hi) {   // nothing to drain (block_n == 32, upper half): still release the accumulator
+        tc_fence_before();
+        if (kPair) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+        } else {
+          mbar_arrive(&tmem_empty[acc]);
+        }
+      }
+      for (int ch = ch_lo; ch < ch_hi; ch++) {
         uint32_t v[32];
         tmem_ld32(taddr + ch * 32, v);
         tmem_ld_wait();
-        if (ch == p.block_n / 32 - 1) {
+        if (ch == ch_hi - 1) {
           // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           if (kPair) {

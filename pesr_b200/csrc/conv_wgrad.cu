@@ -87,7 +87,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // whole warp, warp-uniform control flow; one elected lane issues (see common.cuh)
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
@@ -104,11 +104,11 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
           uint8_t* sb = sa + p.a_boxes * kWgBoxBytes;
-          mbar_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes);
+          mbar_expect_tx_w(&full_bar[stage], (uint32_t)p.stage_bytes);
           for (int i = 0; i < p.a_boxes; i++)
-            tma_load_4d(sa + i * kWgBoxBytes, &maps.a, &full_bar[stage], mt * 128 + i * 64, w0, h0, img);
+            tma_load_4d_w(sa + i * kWgBoxBytes, &maps.a, &full_bar[stage], mt * 128 + i * 64, w0, h0, img);
           for (int i = 0; i < p.b_boxes; i++)
-            tma_load_4d(sb + i * kWgBoxBytes, mb, &full_bar[stage], nt * p.block_n + i * 64, w0 + dw, h0 + dh, img);
+            tma_load_4d_w(sb + i * kWgBoxBytes, mb, &full_bar[stage], nt * p.block_n + i * 64, w0 + dw, h0 + dh, img);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -129,19 +129,18 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
       for (int pt = p0; pt < p1; pt++) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        {
           const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
           const uint32_t b_addr = a_addr + p.a_boxes * kWgBoxBytes;
 #pragma unroll
           for (int k = 0; k < kWgKBlock / 16; k++) {
             const uint64_t da = make_smem_desc(a_addr + k * 2048, p.lbo, p.sbo);
             const uint64_t db = make_smem_desc(b_addr + k * 2048, p.lbo, p.sbo);
-            umma_f16(d_tmem, da, db, idesc, (pt > p0 || k > 0) ? 1u : 0u);
+            umma_f16_w(d_tmem, da, db, idesc, (pt > p0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
-          if (pt == p1 - 1) umma_commit(&tmem_full[acc]);
+          umma_commit_w(&empty_bar[stage]);
+          if (pt == p1 - 1) umma_commit_w(&tmem_full[acc]);
         }
-        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       if (p1 > p0) {
@@ -152,6 +151,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
+    const int ch_lo = 0, ch_hi = p.block_n / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
@@ -162,17 +162,17 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
       float* dst = p.partials + (((long long)split * p.ntaps + tap) * p.m_total + m) * p.n_total + nt * p.block_n;
       if (p1 <= p0) {  // empty split: its partial is all zeros
         if (m < p.m_total)
-          for (int j = 0; j < p.block_n; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(0, 0, 0, 0);
+          for (int j = ch_lo * 32; j < ch_hi * 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(0, 0, 0, 0);
         continue;
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kWgAccStride);
-      for (int ch = 0; ch < p.block_n / 32; ch++) {
+      for (int ch = ch_lo; ch < ch_hi; ch++) {
         uint32_t v[32];
         tmem_ld32(taddr + ch * 32, v);
         tmem_ld_wait();
-        if (ch == p.block_n / 32 - 1) {
+        if (ch == ch_hi - 1) {
           tc_fence_before();
           mbar_arrive(&tmem_empty[acc]);
         }

@@ -36,9 +36,18 @@ CASES = [  # nb, cin, cout, h, w   (G trunk, upsampler, D/VGG channel counts, ra
 ]
 
 
+@pytest.fixture(params=[1, 2, 0], ids=["pair-auto", "pair-forced", "pair-off"])
+def pair_mode(request):
+    """Runs a test with the CTA-pair (cta_group::2) kernel chosen automatically, forced wherever legal, and disabled."""
+    from pesr_b200._lib import lib
+    lib.pesr_debug_pair_mode(request.param)
+    yield request.param
+    lib.pesr_debug_pair_mode(1)
+
+
 @pytest.mark.parametrize("nb,cin,cout,h,w", CASES)
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-def test_fprop_bias_relu(nb, cin, cout, h, w, dtype):
+def test_fprop_bias_relu(nb, cin, cout, h, w, dtype, pair_mode):
     from pesr_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(nb * 1000 + cin + h)
     x = torch.randn(nb, cin, h, w, device="cuda", generator=g)
@@ -74,7 +83,7 @@ def test_dgrad_is_fprop_with_flipped_weights(nb, cin, cout, h, w):
     assert rel_l2(out32.permute(0, 3, 1, 2), ref) < 2e-5
 
 
-def test_epilogue_residual_scale_mask_and_pixel_shuffle():
+def test_epilogue_residual_scale_mask_and_pixel_shuffle(pair_mode):
     from pesr_b200 import ops
     dtype = torch.float16
     nb, c, h, w = 2, 64, 12, 16

@@ -108,6 +108,22 @@ if __name__ == "__main__":
     if what == "one":       # single trunk-conv shape for `ncu --set full`
         conv_case(16, 256, 256, 48, 48)
         wgrad_case(16, 256, 256, 48, 48)
+    if what == "mma":
+        from pesr_b200._lib import lib
+        out = torch.zeros(2, dtype=torch.int64, device="cuda")
+        for pair in (0, 1):
+            for n in (256, 192, 128, 64):
+                for blocks in (1 + pair, 148):
+                    for stages in (1, 4):
+                        iters = 400
+                        out.zero_()
+                        rc = lib.pesr_debug_mma_rate(n, iters, stages, pair, blocks, out.data_ptr(), 0)
+                        if rc:
+                            print("  rc", rc, lib.pesr_last_error())
+                        torch.cuda.synchronize()
+                        a, b = out.cpu().tolist()
+                        print(f"mma rate pair={pair} N={n} blocks={blocks} stages={stages}: issue {a/(iters*4):.1f} cyc/MMA, "
+                              f"complete {b/(iters*4):.1f} cyc/MMA (ideal {128*n/256:.0f})", flush=True)
     if what == "timeline":
         from pesr_b200._lib import lib
         buf = torch.zeros(64, dtype=torch.int64, device="cuda")
@@ -146,6 +162,9 @@ if __name__ == "__main__":
             conv_case(16, 64, 64, 192, 192)
             conv_case(16, 128, 128, 96, 96)
             conv_case(16, 512, 512, 24, 24)
+            conv_case(32, 128, 128, 96, 96)
+            conv_case(32, 256, 256, 48, 48)
+            conv_case(32, 512, 512, 12, 12)
     if what in ("all", "conv"):
         conv_case(16, 256, 256, 48, 48)
         conv_case(16, 256, 1024, 48, 48)

@@ -24,6 +24,7 @@ sys.path.insert(0, ROOT)
 G_FWD_GFLOP = 231.564   # per 48x48 sample, BASELINE.md section 2
 D_FWD_GFLOP = 7.073
 VGG_FWD_GFLOP = 28.665
+NCU_TRUNK_CONV_DRAM_BYTES = 20095232   # ncu --set full, profiles/r01_ncu_conv_igemm.txt
 OPT = {'patch_size': 48, 'num_channels': 256, 'depth': 32, 'res_scale': 0.1, 'spectral_norm': False}
 BATCH = 16
 
@@ -289,7 +290,10 @@ def run_b200(args):
     step_tflops = step_gflop(args.workload) / ms_step   # GFLOP / ms == TFLOP/s
     roofline = {
         "bound": "tensor", "kernel": "conv_igemm_kernel (fprop + dgrad of every conv)", "achieved": achieved,
-        "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
+        "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+        "traffic": NCU_TRUNK_CONV_DRAM_BYTES,
+        "traffic_note": "dram__bytes_read+write of ONE trunk-conv launch (16x48x48, 256->256) from profiles/r01_ncu_conv_igemm.txt; "
+                        "algorithmic bytes of that launch: 18.9 MB in + 1.2 MB weights + 18.9 MB out (the output stays in the 126 MB L2)",
         "peak_source": peaks["source"], "launches_per_step": ig_n / args.steps,
         "avg_launch_us": ig_ms * 1e3 / max(ig_n, 1), "share_of_step": ig_ms / args.steps / ms_step,
         "wgrad": {"kernel": "conv_wgrad_kernel", "achieved": wg_achieved, "frac": wg_achieved / peaks["tflops"],
@@ -305,6 +309,9 @@ def run_b200(args):
         t = cpu_step_time(args.workload, cb)
         cpu = {"value": cb / t, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"1 step of a {cb}-sample batch (of {BATCH}), fp32, torch CPU oracle, {t:.1f} s"}
+    extras = {}
+    if world == 1 and not args.no_extras:
+        extras = side_measurements(args, dev, G, optim_G, dev_lr, dev_hr)
     line = {
         "metric": metric_name(args.workload), "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -314,9 +321,45 @@ def run_b200(args):
                 "ms_per_step": ms_e2e},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }
+    line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def side_measurements(args, dev, G, optim_G, dev_lr, dev_hr):
+    """The other single-GPU configurations of BASELINE.json, measured the same way (CUDA events, warm-up) and
+    reported beside the headline: config 2 (L1 pretrain step) and configs 1 / 5 (x4 inference, alpha = 1)."""
+    import torch
+    from pesr_b200 import infer, steps
+    out = {}
+
+    def timed(fn, k, warm=3):
+        for i in range(warm):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+    if args.workload != "pretrain":
+        ms = timed(lambda i: steps.pretrain_step(G, optim_G, dev_lr[i % len(dev_lr)], dev_hr[i % len(dev_hr)]), args.steps)
+        out["pretrain_step"] = {"metric": "L1 pretrain samples/s", "value": BATCH / (ms * 1e-3), "ms_per_step": ms,
+                                "tflops": step_gflop("pretrain") / ms, "config": "BASELINE.json configs[1]"}
+    G.eval()
+    inf = {}
+    for name, (h, w) in (("128x128", (128, 128)), ("339x510", (339, 510))):
+        x = torch.rand(1, 3, h, w, device=dev) * 255
+        ms = timed(lambda i: infer.super_resolve(G, x), 5, warm=2)
+        inf[name] = {"ms_per_image": ms, "hr_mpix_per_s": 16 * h * w / (ms * 1e-3) / 1e6,
+                     "tflops": h * w * 100505088 / (ms * 1e-3) / 1e12}
+    G.train()
+    out["inference_alpha1"] = {"metric": "x4 SR inference HR Mpix/s (fp32 image in, uint8 image out, batch 1)", **inf,
+                               "config": "BASELINE.json configs[0] and configs[4] image sizes"}
+    return out
 
 
 def main():
@@ -325,7 +368,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("PESR_BENCH_WORKLOAD", "pretrain"), choices=["pretrain", "gan"])
+    ap.add_argument("--workload", default=os.environ.get("PESR_BENCH_WORKLOAD", "gan"), choices=["pretrain", "gan"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the pretrain-step and inference side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -116,7 +116,7 @@ int pesr_conv_igemm(const pesr_conv_desc* d, void* stream);
 /* A/B hook: 0 = never use the CTA-pair (cta_group::2) kernel, 1 = whenever legal (default), -1 = re-read PESR_NO_PAIR. */
 void pesr_debug_pair_mode(int mode);
 /* Bring-up microbenchmark: issue / completion cycles of iters*4 back-to-back tcgen05.mma (M=128 or pair 256, N=n). */
-int pesr_debug_mma_rate(int32_t n, int32_t iters, int32_t stages, int32_t pair, int32_t blocks,
+int pesr_debug_mma_rate(int32_t n, int32_t iters, int32_t stages, int32_t pair_and_major, int32_t blocks,
                         unsigned long long* out_dev, void* stream);
 /* Bring-up hook: device buffer (64 x uint64) that block 0 of each pesr_conv_igemm launch fills with clock64 stamps. */
 void pesr_debug_timeline(void* buf);
@@ -159,6 +159,7 @@ int pesr_wgrad_reduce(const float* partials, int32_t splits, int32_t ntaps, int3
                       int32_t accumulate, float* grad_oihw, void* stream);
 /* Bring-up hook: override the MN-major smem descriptor strides of pesr_conv_wgrad (0 = built-in). */
 void pesr_debug_wgrad_desc(int lbo_bytes, int sbo_bytes);
+void pesr_debug_wgrad_timeline(void* buf);   /* like pesr_debug_timeline, for pesr_conv_wgrad */
 
 /* Weight packing: fp32 OIHW parameter -> 16-bit K-major GEMM operand (tap = ky*3+kx; tapf = 8-tap).
  *  mode 0 fprop     : out[tap][o][i]                        (rows = 9*co, K = ci)

@@ -108,6 +108,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     dbg[0] = t_begin;
     dbg[62] = g_begin;
   }
+  if (p.dbg && threadIdx.x == 0) {   // per-CTA start / end wall-clock stamps (all blocks)
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg[64 + 2 * blockIdx.x] = g;
+  }
 
   // tile -> (split, m_tile of THIS CTA, n_tile)
   auto decode = [&](int tile, int& split, int& m_tile, int& n_tile) {
@@ -257,91 +262,113 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
           mbar_arrive(&tmem_empty[acc]);
         }
       }
+      // software pipeline over 32-column chunks: the TMEM load and the fp32-residual loads of chunk ch+1 are in flight
+      // while chunk ch is processed (one exposed latency per tile instead of one per chunk)
+      uint32_t v[32], vn[32];
+      float4 rn[8];
+      const float* res_row = (p.res32 && valid) ? p.res32 + pix * p.ld_res32 + n0 : nullptr;
+      tmem_ld32(taddr + ch_lo * 32, v);
+      if (res_row) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) rn[j] = reinterpret_cast<const float4*>(res_row + ch_lo * 32)[j];
+      }
+      tmem_ld_wait();
       for (int ch = ch_lo; ch < ch_hi; ch++) {
-        uint32_t v[32];
-        tmem_ld32(taddr + ch * 32, v);
-        tmem_ld_wait();
-        if (ch == ch_hi - 1) {
-          // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
+        float4 rc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) rc[j] = rn[j];
+        const bool more = ch + 1 < ch_hi;
+        if (more) {
+          tmem_ld32(taddr + (ch + 1) * 32, vn);
+          if (res_row) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) rn[j] = reinterpret_cast<const float4*>(res_row + (ch + 1) * 32)[j];
+          }
+        }
+        if (valid) {
+          const int q0 = n0 + ch * 32;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) f[j] = alpha * (__uint_as_float(v[j]) + bs[ch * 32 + j]);
+          if (p.res32) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              f[4 * j] += rc[j].x; f[4 * j + 1] += rc[j].y; f[4 * j + 2] += rc[j].z; f[4 * j + 3] += rc[j].w;
+            }
+          }
+          if (p.res16) {
+            const uint4* r = reinterpret_cast<const uint4*>(p.res16 + pix * p.ld_res16 + q0);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              uint4 t = r[j];
+              float2 a = unpack2(t.x, bf), b = unpack2(t.y, bf), c = unpack2(t.z, bf), d = unpack2(t.w, bf);
+              f[8 * j] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
+              f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
+            }
+          }
+          if (p.act == PESR_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) f[j] = fmaxf(f[j], 0.f);
+          } else if (p.act == PESR_ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) f[j] = f[j] > 0.f ? f[j] : 0.2f * f[j];
+          }
+          if (p.mask16) {
+            const uint4* r = reinterpret_cast<const uint4*>(p.mask16 + pix * p.ld_mask16 + q0);
+            const float neg = p.mask_mode == 2 ? 0.2f : 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              uint4 t = r[j];
+              float2 a = unpack2(t.x, bf), b = unpack2(t.y, bf), c = unpack2(t.z, bf), d = unpack2(t.w, bf);
+              f[8 * j] *= a.x > 0.f ? 1.f : neg; f[8 * j + 1] *= a.y > 0.f ? 1.f : neg;
+              f[8 * j + 2] *= b.x > 0.f ? 1.f : neg; f[8 * j + 3] *= b.y > 0.f ? 1.f : neg;
+              f[8 * j + 4] *= c.x > 0.f ? 1.f : neg; f[8 * j + 5] *= c.y > 0.f ? 1.f : neg;
+              f[8 * j + 6] *= d.x > 0.f ? 1.f : neg; f[8 * j + 7] *= d.y > 0.f ? 1.f : neg;
+            }
+          }
+          if (p.out32) {
+            float4* o = reinterpret_cast<float4*>(p.out32 + split * p.split_stride32 + pix * p.ld_out32 + q0);
+#pragma unroll
+            for (int j = 0; j < 8; j++) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
+          if (p.out16) {
+            long long off;
+            if (p.out_mode == PESR_OUT_SHUFFLE2) {
+              const int ij = q0 / p.ps_c, c0 = q0 % p.ps_c;
+              const long long op = ((long long)img * (2 * p.h) + (2 * h + (ij >> 1))) * (2 * p.w) + (2 * w + (ij & 1));
+              off = op * p.ld_out16 + p.out_coff + c0;
+            } else if (p.out_mode == PESR_OUT_UNSHUFFLE2) {
+              const long long op = ((long long)img * (p.h >> 1) + (h >> 1)) * (p.w >> 1) + (w >> 1);
+              off = op * p.ld_out16 + p.out_coff + ((h & 1) * 2 + (w & 1)) * p.cout + q0;
+            } else {
+              const long long op =
+                  ((long long)img * p.out_h + (h * p.out_sy + p.out_oy)) * p.out_w + (w * p.out_sx + p.out_ox);
+              off = op * p.ld_out16 + p.out_coff + q0;
+            }
+            uint4* o = reinterpret_cast<uint4*>(p.out16 + off);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              uint4 t;
+              t.x = pack2(f[8 * j], f[8 * j + 1], bf);
+              t.y = pack2(f[8 * j + 2], f[8 * j + 3], bf);
+              t.z = pack2(f[8 * j + 4], f[8 * j + 5], bf);
+              t.w = pack2(f[8 * j + 6], f[8 * j + 7], bf);
+              o[j] = t;
+            }
+          }
+        }
+        if (more) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = vn[j];
+        } else {
+          // every accumulator column of this row has been read: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           if (kPair) {
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
           } else {
             mbar_arrive(&tmem_empty[acc]);
-          }
-        }
-        if (!valid) continue;
-        const int q0 = n0 + ch * 32;
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; j++) f[j] = alpha * (__uint_as_float(v[j]) + bs[ch * 32 + j]);
-        if (p.res32) {
-          const float4* r = reinterpret_cast<const float4*>(p.res32 + pix * p.ld_res32 + q0);
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            float4 t = r[j];
-            f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
-          }
-        }
-        if (p.res16) {
-          const uint4* r = reinterpret_cast<const uint4*>(p.res16 + pix * p.ld_res16 + q0);
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            uint4 t = r[j];
-            float2 a = unpack2(t.x, bf), b = unpack2(t.y, bf), c = unpack2(t.z, bf), d = unpack2(t.w, bf);
-            f[8 * j] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
-            f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
-          }
-        }
-        if (p.act == PESR_ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; j++) f[j] = fmaxf(f[j], 0.f);
-        } else if (p.act == PESR_ACT_LRELU) {
-#pragma unroll
-          for (int j = 0; j < 32; j++) f[j] = f[j] > 0.f ? f[j] : 0.2f * f[j];
-        }
-        if (p.mask16) {
-          const uint4* r = reinterpret_cast<const uint4*>(p.mask16 + pix * p.ld_mask16 + q0);
-          const float neg = p.mask_mode == 2 ? 0.2f : 0.f;
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            uint4 t = r[j];
-            float2 a = unpack2(t.x, bf), b = unpack2(t.y, bf), c = unpack2(t.z, bf), d = unpack2(t.w, bf);
-            f[8 * j] *= a.x > 0.f ? 1.f : neg; f[8 * j + 1] *= a.y > 0.f ? 1.f : neg;
-            f[8 * j + 2] *= b.x > 0.f ? 1.f : neg; f[8 * j + 3] *= b.y > 0.f ? 1.f : neg;
-            f[8 * j + 4] *= c.x > 0.f ? 1.f : neg; f[8 * j + 5] *= c.y > 0.f ? 1.f : neg;
-            f[8 * j + 6] *= d.x > 0.f ? 1.f : neg; f[8 * j + 7] *= d.y > 0.f ? 1.f : neg;
-          }
-        }
-        if (p.out32) {
-          float4* o = reinterpret_cast<float4*>(p.out32 + split * p.split_stride32 + pix * p.ld_out32 + q0);
-#pragma unroll
-          for (int j = 0; j < 8; j++) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        }
-        if (p.out16) {
-          long long off;
-          if (p.out_mode == PESR_OUT_SHUFFLE2) {
-            const int ij = q0 / p.ps_c, c0 = q0 % p.ps_c;
-            const long long op = ((long long)img * (2 * p.h) + (2 * h + (ij >> 1))) * (2 * p.w) + (2 * w + (ij & 1));
-            off = op * p.ld_out16 + p.out_coff + c0;
-          } else if (p.out_mode == PESR_OUT_UNSHUFFLE2) {
-            const long long op = ((long long)img * (p.h >> 1) + (h >> 1)) * (p.w >> 1) + (w >> 1);
-            off = op * p.ld_out16 + p.out_coff + ((h & 1) * 2 + (w & 1)) * p.cout + q0;
-          } else {
-            const long long op =
-                ((long long)img * p.out_h + (h * p.out_sy + p.out_oy)) * p.out_w + (w * p.out_sx + p.out_ox);
-            off = op * p.ld_out16 + p.out_coff + q0;
-          }
-          uint4* o = reinterpret_cast<uint4*>(p.out16 + off);
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            uint4 t;
-            t.x = pack2(f[8 * j], f[8 * j + 1], bf);
-            t.y = pack2(f[8 * j + 2], f[8 * j + 3], bf);
-            t.z = pack2(f[8 * j + 4], f[8 * j + 5], bf);
-            t.w = pack2(f[8 * j + 6], f[8 * j + 7], bf);
-            o[j] = t;
           }
         }
       }
@@ -358,6 +385,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
     dbg[61] = clock64();
     dbg[63] = g_end;
+  }
+  if (p.dbg && threadIdx.x == 0) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg[65 + 2 * blockIdx.x] = g;
   }
   if (warp == 1) {
     tc_fence_after();

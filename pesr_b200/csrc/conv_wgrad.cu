@@ -12,6 +12,8 @@
 #include "common.cuh"
 #include "host_util.cuh"
 
+#include <stdlib.h>
+
 namespace pesr {
 
 static constexpr int kWgKBlock = 64;               // pixels per pipeline stage
@@ -34,14 +36,23 @@ struct WgK {
   int lbo, sbo;  // MN-major descriptor strides (bytes)
   int8_t tap_dh[PESR_MAX_TAPS], tap_dw[PESR_MAX_TAPS], tap_src[PESR_MAX_TAPS];
   float* partials;
+  unsigned long long* dbg;
 };
 
+// kPair: a cluster of two CTAs drives one 256 (output channels) x block_n MMA (cta_group::2); CTA r stages its own
+// 128 rows of dy and HALF of the x tile's channels, which cuts the L2 -> smem bytes per MMA by a third (the
+// single-CTA kernel is bound by that traffic: 48 KB per 512 MMA cycles).  Protocol as in conv_igemm.cu.
+template <bool kPair>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgK p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = kPair ? (int)cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  const int worker = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nworkers = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   uint8_t* tail = smem + (size_t)p.stages * p.stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
@@ -59,19 +70,31 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], kPair ? 8 : 128);
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, 512);
-    tmem_relinquish();
+    if (kPair) { tmem_alloc2(tmem_ptr, 512); tmem_relinquish2(); }
+    else       { tmem_alloc(tmem_ptr, 512);  tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  unsigned long long* dbg = (p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
+  if (dbg && threadIdx.x == 0) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    dbg[0] = clock64();
+    dbg[62] = g;
+  }
+  if (p.dbg && threadIdx.x == 0) {   // per-CTA start / end wall-clock stamps (all blocks)
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg[64 + 2 * blockIdx.x] = g;
+  }
   // item -> (split, tap, m_tile, n_tile); split slowest so that concurrently running CTAs share pixels in L2
   auto decode = [&](int item, int& split, int& tap, int& mt, int& nt) {
     nt = item % p.n_tiles;
@@ -80,6 +103,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
     r /= p.m_tiles;
     tap = r % p.ntaps;
     split = r / p.ntaps;
+    if (kPair) mt = 2 * mt + rank;
   };
   auto patch_range = [&](int split, int& p0, int& p1) {
     p0 = (int)(((long long)split * p.patches) / p.splits);
@@ -90,7 +114,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
     {   // whole warp, warp-uniform control flow; one elected lane issues (see common.cuh)
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      for (int item = worker; item < p.num_items; item += nworkers) {
         int split, tap, mt, nt, p0, p1;
         decode(item, split, tap, mt, nt);
         patch_range(split, p0, p1);
@@ -104,31 +128,42 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
           uint8_t* sb = sa + p.a_boxes * kWgBoxBytes;
-          mbar_expect_tx_w(&full_bar[stage], (uint32_t)p.stage_bytes);
-          for (int i = 0; i < p.a_boxes; i++)
-            tma_load_4d_w(sa + i * kWgBoxBytes, &maps.a, &full_bar[stage], mt * 128 + i * 64, w0, h0, img);
-          for (int i = 0; i < p.b_boxes; i++)
-            tma_load_4d_w(sb + i * kWgBoxBytes, mb, &full_bar[stage], nt * p.block_n + i * 64, w0 + dw, h0 + dh, img);
+          if (kPair) {
+            if (leader) mbar_expect_tx_w(&full_bar[stage], 2u * (uint32_t)p.stage_bytes);
+            for (int i = 0; i < p.a_boxes; i++)
+              tma2_load_4d_w(sa + i * kWgBoxBytes, &maps.a, &full_bar[stage], mt * 128 + i * 64, w0, h0, img);
+            for (int i = 0; i < p.b_boxes; i++)   // this CTA's half of the N columns
+              tma2_load_4d_w(sb + i * kWgBoxBytes, mb, &full_bar[stage],
+                             nt * p.block_n + (rank * p.b_boxes + i) * 64, w0 + dw, h0 + dh, img);
+          } else {
+            mbar_expect_tx_w(&full_bar[stage], (uint32_t)p.stage_bytes);
+            for (int i = 0; i < p.a_boxes; i++)
+              tma_load_4d_w(sa + i * kWgBoxBytes, &maps.a, &full_bar[stage], mt * 128 + i * 64, w0, h0, img);
+            for (int i = 0; i < p.b_boxes; i++)
+              tma_load_4d_w(sb + i * kWgBoxBytes, mb, &full_bar[stage], nt * p.block_n + i * 64, w0 + dw, h0 + dh, img);
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc(128, p.block_n, p.dtype, 1, 1);
+    const uint32_t idesc = make_idesc(kPair ? 256 : 128, p.block_n, p.dtype, 1, 1);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    for (int item = worker; leader && item < p.num_items; item += nworkers) {
       int split, tap, mt, nt, p0, p1;
       decode(item, split, tap, mt, nt);
       patch_range(split, p0, p1);
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      if (kPair) mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1); else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kWgAccStride);
       for (int pt = p0; pt < p1; pt++) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (dbg && lane == 0 && pt == p0) dbg[9] = clock64();
+        if (dbg && lane == 0 && pt == p0 + 8) dbg[11] = clock64();
         {
           const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
           const uint32_t b_addr = a_addr + p.a_boxes * kWgBoxBytes;
@@ -136,13 +171,20 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
           for (int k = 0; k < kWgKBlock / 16; k++) {
             const uint64_t da = make_smem_desc(a_addr + k * 2048, p.lbo, p.sbo);
             const uint64_t db = make_smem_desc(b_addr + k * 2048, p.lbo, p.sbo);
-            umma_f16_w(d_tmem, da, db, idesc, (pt > p0 || k > 0) ? 1u : 0u);
+            if (kPair) umma2_f16_w(d_tmem, da, db, idesc, (pt > p0 || k > 0) ? 1u : 0u);
+            else       umma_f16_w(d_tmem, da, db, idesc, (pt > p0 || k > 0) ? 1u : 0u);
           }
-          umma_commit_w(&empty_bar[stage]);
-          if (pt == p1 - 1) umma_commit_w(&tmem_full[acc]);
+          if (kPair) {
+            umma2_commit_both_w(&empty_bar[stage]);
+            if (pt == p1 - 1) umma2_commit_both_w(&tmem_full[acc]);
+          } else {
+            umma_commit_w(&empty_bar[stage]);
+            if (pt == p1 - 1) umma_commit_w(&tmem_full[acc]);
+          }
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (dbg && lane == 0) dbg[10] = clock64();
       if (p1 > p0) {
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
@@ -154,7 +196,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
     const int ch_lo = 0, ch_hi = p.block_n / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    for (int item = worker; item < p.num_items; item += nworkers) {
       int split, tap, mt, nt, p0, p1;
       decode(item, split, tap, mt, nt);
       patch_range(split, p0, p1);
@@ -167,6 +209,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (dbg && threadIdx.x == 64) dbg[16] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kWgAccStride);
       for (int ch = ch_lo; ch < ch_hi; ch++) {
         uint32_t v[32];
@@ -174,7 +217,12 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
         tmem_ld_wait();
         if (ch == ch_hi - 1) {
           tc_fence_before();
-          mbar_arrive(&tmem_empty[acc]);
+          if (kPair) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+          } else {
+            mbar_arrive(&tmem_empty[acc]);
+          }
         }
         if (m < p.m_total) {
           float4* o = reinterpret_cast<float4*>(dst + ch * 32);
@@ -184,16 +232,28 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
                                __uint_as_float(v[4 * j + 3]));
         }
       }
+      if (dbg && threadIdx.x == 64) dbg[17] = clock64();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();
+  if (dbg && threadIdx.x == 0) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    dbg[61] = clock64();
+    dbg[63] = g;
+  }
+  if (p.dbg && threadIdx.x == 0) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg[65 + 2 * blockIdx.x] = g;
+  }
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (kPair) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -251,13 +311,18 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, 
 }
 
 static int g_dbg_lbo = 0, g_dbg_sbo = 0;
+static int g_wg_pair = 1;
+static unsigned long long* g_wg_dbg = nullptr;
 
 }  // namespace pesr
 
 using namespace pesr;
 
 // Debug hook used by the bring-up tests only: override the MN-major descriptor strides (0 = default).
+extern "C" void pesr_debug_wgrad_timeline(void* buf) { g_wg_dbg = reinterpret_cast<unsigned long long*>(buf); }
+
 extern "C" void pesr_debug_wgrad_desc(int lbo_bytes, int sbo_bytes) {
+  if (lbo_bytes == -1) { g_wg_pair = sbo_bytes; return; }   // (-1, 0/1): disable / enable the CTA-pair kernel
   g_dbg_lbo = lbo_bytes;
   g_dbg_sbo = sbo_bytes;
 }
@@ -287,12 +352,19 @@ extern "C" int pesr_conv_wgrad(const pesr_wgrad_desc* d, int32_t* splits_out, vo
   k.tiles_h = (d->h + k.tile_h - 1) / k.tile_h;
   k.tiles_w = (d->w + k.tile_w - 1) / k.tile_w;
   k.patches = d->nb * k.tiles_h * k.tiles_w;
-  k.m_tiles = (d->m_total + 127) / 128;
+  // CTA-pair path: 256 output-channel rows per MMA; needs m_total % 256 == 0 and a 128-aligned half of block_n
+  static int pair_env = -1;
+  if (pair_env < 0) {
+    const char* e = getenv("PESR_NO_PAIR");
+    pair_env = (e && e[0] == '1') ? 0 : 1;
+  }
+  const bool pair = pair_env == 1 && g_wg_pair != 0 && d->m_total % 256 == 0 && d->block_n == 256;
+  k.m_tiles = pair ? d->m_total / 256 : (d->m_total + 127) / 128;
   k.n_tiles = d->n_total / d->block_n;
   const int base_items = d->ntaps * k.m_tiles * k.n_tiles;
   int splits = d->splits;
   if (splits <= 0) {
-    splits = num_sms() / base_items;
+    splits = (pair ? num_sms() / 2 : num_sms()) / base_items;
     if (splits < 1) splits = 1;
   }
   if (splits > k.patches) splits = k.patches;
@@ -309,7 +381,7 @@ extern "C" int pesr_conv_wgrad(const pesr_wgrad_desc* d, int32_t* splits_out, vo
   k.splits = splits;
   k.num_items = base_items * splits;
   k.a_boxes = 2;
-  k.b_boxes = d->block_n / 64;
+  k.b_boxes = pair ? d->block_n / 128 : d->block_n / 64;   // per CTA
   k.stage_bytes = (k.a_boxes + k.b_boxes) * kWgBoxBytes;
   k.stages = (227 * 1024 - 4096) / k.stage_bytes;
   if (k.stages > kWgMaxStages) k.stages = kWgMaxStages;
@@ -321,6 +393,7 @@ extern "C" int pesr_conv_wgrad(const pesr_wgrad_desc* d, int32_t* splits_out, vo
   for (int t = 0; t < d->ntaps; t++)
     PESR_CHECK_ARG(d->tap_src[t] >= 0 && d->tap_src[t] < d->nsrc, "conv_wgrad: tap %d reads source %d", t, d->tap_src[t]);
   k.partials = d->partials;
+  k.dbg = g_wg_dbg;
 
   WgMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -345,17 +418,41 @@ extern "C" int pesr_conv_wgrad(const pesr_wgrad_desc* d, int32_t* splits_out, vo
   if (smem < 120 * 1024) smem = 120 * 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_error("conv_wgrad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
     }
     attr_set = true;
   }
-  int grid = k.num_items < num_sms() ? k.num_items : num_sms();
   const bool prof = profiling_enabled();
   if (prof) profile_begin(1, 2.0 * d->nb * d->h * d->w * (double)d->m_total * d->n_total * d->ntaps, stream);
-  conv_wgrad_kernel<<<grid, kWgThreads, smem, stream>>>(maps, k);
+  if (pair) {
+    int clusters = k.num_items < num_sms() / 2 ? k.num_items : num_sms() / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kWgThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<true>, maps, k);
+    if (e != cudaSuccess) {
+      set_error("conv_wgrad: pair launch failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+  } else {
+    int grid = k.num_items < num_sms() ? k.num_items : num_sms();
+    conv_wgrad_kernel<false><<<grid, kWgThreads, smem, stream>>>(maps, k);
+  }
   if (prof) profile_end(1, stream);
   count_launch();
   PESR_CHECK_LAUNCH("conv_wgrad");

@@ -6,7 +6,7 @@
 namespace pesr {
 
 template <bool kPair>
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int distinct_stages, unsigned long long* out) {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int distinct_stages, int mn_major, unsigned long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -25,15 +25,15 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int 
   const uint32_t tmem_base = tmem_ptr;
   const bool leader = !kPair || cluster_ctarank() == 0;
   if (warp == 0 && leader) {
-    const uint32_t idesc = make_idesc(kPair ? 256 : 128, n, 0, 0, 0);
+    const uint32_t idesc = make_idesc(kPair ? 256 : 128, n, 0, mn_major & 1, (mn_major >> 1) & 1);
     const unsigned long long t0 = clock64();
     for (int it = 0; it < iters; it++) {
       const uint32_t a_addr = smem_u32(smem + (size_t)(it % distinct_stages) * stage_bytes);
       const uint32_t b_addr = a_addr + 16384;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
-        const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
+        const uint64_t da = (mn_major & 1) ? make_smem_desc(a_addr + k * 2048, 8192, 1024) : make_smem_desc(a_addr + k * 32, 16, 1024);
+        const uint64_t db = (mn_major & 2) ? make_smem_desc(b_addr + k * 2048, 8192, 1024) : make_smem_desc(b_addr + k * 32, 16, 1024);
         if (kPair) umma2_f16_w(tmem_base, da, db, idesc, (it | k) != 0); else umma_f16_w(tmem_base, da, db, idesc, (it | k) != 0);
       }
     }
@@ -56,9 +56,10 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int 
 using namespace pesr;
 
 // out[0] = cycles to ISSUE iters*4 MMAs, out[1] = cycles until they all completed (block 0 / cluster 0).
-extern "C" int pesr_debug_mma_rate(int32_t n, int32_t iters, int32_t stages, int32_t pair, int32_t blocks,
+extern "C" int pesr_debug_mma_rate(int32_t n, int32_t iters, int32_t stages, int32_t pair_and_major, int32_t blocks,
                                    unsigned long long* out_dev, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int pair = pair_and_major & 1, mn_major = pair_and_major >> 1;   // bit0 pair, bit1 A MN-major, bit2 B MN-major
   PESR_CHECK_ARG(n >= 32 && n <= 256 && n % 16 == 0 && iters > 0 && stages >= 1 && stages <= 4 && out_dev, "mma_rate: bad arguments");
   const size_t smem = (size_t)stages * (16384 + n * 128) + 1024 + 64;
   cudaGetLastError();
@@ -75,10 +76,10 @@ extern "C" int pesr_debug_mma_rate(int32_t n, int32_t iters, int32_t stages, int
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, mma_rate_kernel<true>, n, iters, stages, out_dev);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, mma_rate_kernel<true>, n, iters, stages, mn_major, out_dev);
     if (e != cudaSuccess) { set_error("mma_rate: %s", cudaGetErrorString(e)); return (int)e; }
   } else {
-    mma_rate_kernel<false><<<blocks, 128, smem, stream>>>(n, iters, stages, out_dev);
+    mma_rate_kernel<false><<<blocks, 128, smem, stream>>>(n, iters, stages, mn_major, out_dev);
   }
   PESR_CHECK_LAUNCH("mma_rate");
   return 0;

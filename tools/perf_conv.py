@@ -111,10 +111,10 @@ if __name__ == "__main__":
     if what == "mma":
         from pesr_b200._lib import lib
         out = torch.zeros(2, dtype=torch.int64, device="cuda")
-        for pair in (0, 1):
-            for n in (256, 192, 128, 64):
-                for blocks in (1 + pair, 148):
-                    for stages in (1, 4):
+        for pair in (0, 1, 2, 4, 6, 7):     # bit0 pair, bit1 A MN-major, bit2 B MN-major
+            for n in (256, 128):
+                for blocks in (148,):
+                    for stages in (4,):
                         iters = 400
                         out.zero_()
                         rc = lib.pesr_debug_mma_rate(n, iters, stages, pair, blocks, out.data_ptr(), 0)
@@ -124,6 +124,41 @@ if __name__ == "__main__":
                         a, b = out.cpu().tolist()
                         print(f"mma rate pair={pair} N={n} blocks={blocks} stages={stages}: issue {a/(iters*4):.1f} cyc/MMA, "
                               f"complete {b/(iters*4):.1f} cyc/MMA (ideal {128*n/256:.0f})", flush=True)
+    if what == "wtimeline":
+        from pesr_b200._lib import lib
+        buf = torch.zeros(64 + 2 * 160, dtype=torch.int64, device="cuda")
+        lib.pesr_debug_wgrad_timeline(buf.data_ptr())
+        for pairmode in (0, 1):
+            lib.pesr_debug_wgrad_desc(-1, pairmode)
+            wgrad_case(16, 256, 256, 48, 48)
+            torch.cuda.synchronize()
+            b = buf.cpu().tolist()
+            mhz = (b[61] - b[0]) / max(b[63] - b[62], 1) * 1e3
+            print(f"  wgrad pair={pairmode} block0 (SM clock {mhz:.0f} MHz, total {(b[63]-b[62])/1e3:.1f} us): first stage landed "
+                  f"{b[9]-b[0]}, 8 k-blocks later {b[11]-b[0]}, MMAs issued {b[10]-b[0]}, acc complete {b[16]-b[0]}, "
+                  f"epilogue done {b[17]-b[0]}, end {b[61]-b[0]}")
+            st = [b[64 + 2 * i] for i in range(148) if b[64 + 2 * i]]
+            en = [b[65 + 2 * i] for i in range(148) if b[65 + 2 * i]]
+            t0 = min(st)
+            durs = sorted((e - s_) / 1e3 for s_, e in zip(st, en))
+            print(f"  per-CTA: starts spread {(max(st)-t0)/1e3:.1f} us, first end {(min(en)-t0)/1e3:.1f} us, last end {(max(en)-t0)/1e3:.1f} us, "
+                  f"CTA duration min/median/max {durs[0]:.1f}/{durs[len(durs)//2]:.1f}/{durs[-1]:.1f} us")
+        lib.pesr_debug_wgrad_timeline(0)
+        buf2 = torch.zeros(64 + 2 * 160, dtype=torch.int64, device="cuda")
+        lib.pesr_debug_timeline(buf2.data_ptr())
+        for pm in (0, 2):
+            lib.pesr_debug_pair_mode(pm)
+            conv_case(16, 256, 256, 48, 48)
+            torch.cuda.synchronize()
+            b = buf2.cpu().tolist()
+            st = [b[64 + 2 * i] for i in range(148) if b[64 + 2 * i]]
+            en = [b[65 + 2 * i] for i in range(148) if b[65 + 2 * i]]
+            t0 = min(st)
+            durs = sorted((e - s_) / 1e3 for s_, e in zip(st, en))
+            print(f"  fprop pair={pm} per-CTA: starts spread {(max(st)-t0)/1e3:.1f} us, first end {(min(en)-t0)/1e3:.1f}, last end {(max(en)-t0)/1e3:.1f} us, "
+                  f"CTA duration min/median/max {durs[0]:.1f}/{durs[len(durs)//2]:.1f}/{durs[-1]:.1f} us")
+        lib.pesr_debug_timeline(0)
+        lib.pesr_debug_pair_mode(1)
     if what == "timeline":
         from pesr_b200._lib import lib
         buf = torch.zeros(64, dtype=torch.int64, device="cuda")
@@ -133,7 +168,7 @@ if __name__ == "__main__":
                  17: "t0 epilogue done", 20: "tL acc complete", 21: "tL epilogue done", 61: "end"}
         for pair in (0, 1):
             lib.pesr_debug_pair_mode(pair)
-            for shape in ((16, 256, 256, 48, 48), (16, 256, 1024, 96, 96)):
+            for shape in ((16, 256, 256, 48, 48), (16, 256, 1024, 96, 96), (16, 64, 64, 192, 192), (16, 512, 512, 24, 24)):
                 conv_case(*shape)
                 torch.cuda.synchronize()
                 b = buf.cpu().tolist()
@@ -153,7 +188,7 @@ if __name__ == "__main__":
         lib.pesr_debug_pair_mode(100)
     if what == "pair":
         from pesr_b200._lib import lib
-        for mode in (0, 1):
+        for mode in (0, 2):
             lib.pesr_debug_pair_mode(mode)
             print("pair mode", mode)
             conv_case(16, 256, 256, 48, 48)

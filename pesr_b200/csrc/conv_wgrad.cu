@@ -37,6 +37,7 @@ struct WgK {
   int8_t tap_dh[PESR_MAX_TAPS], tap_dw[PESR_MAX_TAPS], tap_src[PESR_MAX_TAPS];
   float* partials;
   unsigned long long* dbg;
+  int dbg_skip;
 };
 
 // kPair: a cluster of two CTAs drives one 256 (output channels) x block_n MMA (cta_group::2); CTA r stages its own
@@ -129,18 +130,21 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
           uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
           uint8_t* sb = sa + p.a_boxes * kWgBoxBytes;
           if (kPair) {
+            // one 5-D box per operand: dim 4 walks the 64-channel chunks, which land back to back in smem
             if (leader) mbar_expect_tx_w(&full_bar[stage], 2u * (uint32_t)p.stage_bytes);
-            for (int i = 0; i < p.a_boxes; i++)
-              tma2_load_4d_w(sa + i * kWgBoxBytes, &maps.a, &full_bar[stage], mt * 128 + i * 64, w0, h0, img);
-            for (int i = 0; i < p.b_boxes; i++)   // this CTA's half of the N columns
-              tma2_load_4d_w(sb + i * kWgBoxBytes, mb, &full_bar[stage],
-                             nt * p.block_n + (rank * p.b_boxes + i) * 64, w0 + dw, h0 + dh, img);
+            tma2_load_5d_w(sa, &maps.a, &full_bar[stage], 0, w0, h0, img, mt * 2);
+            tma2_load_5d_w(sb, mb, &full_bar[stage], 0, w0 + dw, h0 + dh, img, nt * (p.block_n / 64) + rank * p.b_boxes);
+          } else if (p.dbg_skip && (pt - p0) >= p.stages) {
+            // bring-up experiment: after the ring is warm skip the A (1), B (2) or all (3) loads
+            const bool la = !(p.dbg_skip & 1), lb = !(p.dbg_skip & 2);
+            const uint32_t bytes = (la ? p.a_boxes : 0) * kWgBoxBytes + (lb ? p.b_boxes : 0) * kWgBoxBytes;
+            if (bytes) mbar_expect_tx_w(&full_bar[stage], bytes); else if (lane == 0) mbar_arrive(&full_bar[stage]);
+            if (la) tma_load_5d_w(sa, &maps.a, &full_bar[stage], 0, w0, h0, img, mt * 2);
+            if (lb) tma_load_5d_w(sb, mb, &full_bar[stage], 0, w0 + dw, h0 + dh, img, nt * (p.block_n / 64));
           } else {
             mbar_expect_tx_w(&full_bar[stage], (uint32_t)p.stage_bytes);
-            for (int i = 0; i < p.a_boxes; i++)
-              tma_load_4d_w(sa + i * kWgBoxBytes, &maps.a, &full_bar[stage], mt * 128 + i * 64, w0, h0, img);
-            for (int i = 0; i < p.b_boxes; i++)
-              tma_load_4d_w(sb + i * kWgBoxBytes, mb, &full_bar[stage], nt * p.block_n + i * 64, w0 + dw, h0 + dh, img);
+            tma_load_5d_w(sa, &maps.a, &full_bar[stage], 0, w0, h0, img, mt * 2);
+            tma_load_5d_w(sb, mb, &full_bar[stage], 0, w0 + dw, h0 + dh, img, nt * (p.block_n / 64));
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -310,9 +314,44 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, 
   }
 }
 
+// OIHW / OIHW_PS maps with ntaps == 9: block = one GEMM row m (an output channel), thread = input channel(s).
+// Partial reads are coalesced over n and independent across the 9 taps x splits (high memory-level parallelism);
+// the 9*ci results of the row are staged in smem and written as one contiguous, coalesced run.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_rows_kernel(const float* __restrict__ part, int splits, int m_total, int n_total, int map_mode, int co,
+                         int ci, float scale, const float* __restrict__ div_dev, int accumulate,
+                         float* __restrict__ grad) {
+  extern __shared__ float row_s[];   // [ci][9]
+  const int m = blockIdx.x;
+  if (div_dev) scale /= __ldg(div_dev);
+  const long long tap_stride = (long long)m_total * n_total;
+  const long long split_stride = tap_stride * 9;
+  for (int n = threadIdx.x; n < ci; n += blockDim.x) {
+    float s[9];
+#pragma unroll
+    for (int t = 0; t < 9; t++) s[t] = 0.f;
+    const float* src = part + (long long)m * n_total + n;
+    for (int k = 0; k < splits; k++) {
+#pragma unroll
+      for (int t = 0; t < 9; t++) s[t] += src[k * split_stride + t * tap_stride];
+    }
+#pragma unroll
+    for (int t = 0; t < 9; t++) row_s[n * 9 + t] = s[t] * scale;
+  }
+  __syncthreads();
+  int o = m;
+  if (map_mode == PESR_WMAP_OIHW_PS) {
+    const int c_ps = co / 4;
+    o = (m % c_ps) * 4 + (m / c_ps);
+  }
+  float* g = grad + (long long)o * ci * 9;
+  for (int i = threadIdx.x; i < ci * 9; i += blockDim.x) g[i] = accumulate ? g[i] + row_s[i] : row_s[i];
+}
+
 static int g_dbg_lbo = 0, g_dbg_sbo = 0;
 static int g_wg_pair = 1;
 static unsigned long long* g_wg_dbg = nullptr;
+static int g_wg_skip = 0;
 
 }  // namespace pesr
 
@@ -322,7 +361,8 @@ using namespace pesr;
 extern "C" void pesr_debug_wgrad_timeline(void* buf) { g_wg_dbg = reinterpret_cast<unsigned long long*>(buf); }
 
 extern "C" void pesr_debug_wgrad_desc(int lbo_bytes, int sbo_bytes) {
-  if (lbo_bytes == -1) { g_wg_pair = sbo_bytes; return; }   // (-1, 0/1): disable / enable the CTA-pair kernel
+  if (lbo_bytes == -1) { g_wg_pair = sbo_bytes; return; }
+  if (lbo_bytes == -2) { g_wg_skip = sbo_bytes; return; }   // (-2, mode): load-skip experiment   // (-1, 0/1): disable / enable the CTA-pair kernel
   g_dbg_lbo = lbo_bytes;
   g_dbg_sbo = sbo_bytes;
 }
@@ -394,23 +434,25 @@ extern "C" int pesr_conv_wgrad(const pesr_wgrad_desc* d, int32_t* splits_out, vo
     PESR_CHECK_ARG(d->tap_src[t] >= 0 && d->tap_src[t] < d->nsrc, "conv_wgrad: tap %d reads source %d", t, d->tap_src[t]);
   k.partials = d->partials;
   k.dbg = g_wg_dbg;
+  k.dbg_skip = g_wg_skip;
 
   WgMaps maps;
   memset(&maps, 0, sizeof(maps));
   {
-    uint64_t dims[4] = {(uint64_t)d->m_total, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nb};
-    uint64_t str[3] = {(uint64_t)d->a_c * 2, (uint64_t)d->w * d->a_c * 2, (uint64_t)d->h * d->w * d->a_c * 2};
-    uint32_t box[4] = {64, (uint32_t)k.tile_w, (uint32_t)k.tile_h, 1};
-    int r = get_tensor_map(&maps.a, d->a, d->dtype, 4, dims, str, box);
+    // 5-D view [chunk][n][h][w][64]: dim 4 strides over the 64-channel chunks so that ONE TMA op stages all of them
+    uint64_t dims[5] = {64, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nb, (uint64_t)(d->m_total / 64)};
+    uint64_t str[4] = {(uint64_t)d->a_c * 2, (uint64_t)d->w * d->a_c * 2, (uint64_t)d->h * d->w * d->a_c * 2, 128};
+    uint32_t box[5] = {64, (uint32_t)k.tile_w, (uint32_t)k.tile_h, 1, (uint32_t)k.a_boxes};
+    int r = get_tensor_map(&maps.a, d->a, d->dtype, 5, dims, str, box);
     if (r) return r;
   }
   for (int s = 0; s < PESR_MAX_SRC; s++) {
     const int ss = s < d->nsrc ? s : 0;
     PESR_CHECK_ARG(d->b[ss] != nullptr, "conv_wgrad: b source %d is null", ss);
-    uint64_t dims[4] = {(uint64_t)d->n_total, (uint64_t)d->b_w[ss], (uint64_t)d->b_h[ss], (uint64_t)d->nb};
-    uint64_t str[3] = {(uint64_t)d->b_sw[ss] * 2, (uint64_t)d->b_sh[ss] * 2, (uint64_t)d->b_sn[ss] * 2};
-    uint32_t box[4] = {64, (uint32_t)k.tile_w, (uint32_t)k.tile_h, 1};
-    int r = get_tensor_map(&maps.b[s], d->b[ss], d->dtype, 4, dims, str, box);
+    uint64_t dims[5] = {64, (uint64_t)d->b_w[ss], (uint64_t)d->b_h[ss], (uint64_t)d->nb, (uint64_t)(d->n_total / 64)};
+    uint64_t str[4] = {(uint64_t)d->b_sw[ss] * 2, (uint64_t)d->b_sh[ss] * 2, (uint64_t)d->b_sn[ss] * 2, 128};
+    uint32_t box[5] = {64, (uint32_t)k.tile_w, (uint32_t)k.tile_h, 1, (uint32_t)k.b_boxes};
+    int r = get_tensor_map(&maps.b[s], d->b[ss], d->dtype, 5, dims, str, box);
     if (r) return r;
   }
 
@@ -474,6 +516,13 @@ extern "C" int pesr_wgrad_reduce(const float* partials, int32_t splits, int32_t 
     PESR_CHECK_ARG(co <= m_total && 9 * ci <= n_total && ntaps == 1, "wgrad_reduce: COL_IN shape mismatch");
   if (map_mode == PESR_WMAP_COL_OUT)
     PESR_CHECK_ARG(ci <= m_total && 9 * co <= n_total && ntaps == 1, "wgrad_reduce: COL_OUT shape mismatch");
+  if ((map_mode == PESR_WMAP_OIHW || map_mode == PESR_WMAP_OIHW_PS) && ntaps == 9 && ci * 9 * sizeof(float) <= 48 * 1024) {
+    wgrad_reduce_rows_kernel<<<co, 256, ci * 9 * sizeof(float), stream>>>(partials, splits, m_total, n_total, map_mode, co,
+                                                                         ci, scale, inv_scale_dev, accumulate, grad_oihw);
+    count_launch();
+    PESR_CHECK_LAUNCH("wgrad_reduce");
+    return 0;
+  }
   const long long total = (long long)co * ci;
   const int threads = 256;
   const int blocks = (int)((total + threads - 1) / threads);

@@ -56,7 +56,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 struct MapKey {
-  uint64_t v[14];
+  uint64_t v[20];
   bool operator<(const MapKey& o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
 };
 
@@ -71,8 +71,8 @@ int get_tensor_map(CUtensorMap* out, const void* base, int dtype, int rank, cons
   k.v[0] = (uint64_t)(uintptr_t)base;
   k.v[1] = ((uint64_t)dtype << 8) | (uint64_t)rank | ((uint64_t)dev << 16);
   for (int i = 0; i < rank; i++) k.v[2 + i] = dims[i];
-  for (int i = 0; i < rank - 1; i++) k.v[6 + i] = strides_bytes[i];
-  for (int i = 0; i < rank; i++) k.v[10 + i] = box[i];
+  for (int i = 0; i < rank - 1; i++) k.v[8 + i] = strides_bytes[i];
+  for (int i = 0; i < rank; i++) k.v[14 + i] = box[i];
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(k);

@@ -291,6 +291,33 @@ __global__ void colsum16_kernel(const uint16_t* __restrict__ x, long long npix, 
   }
 }
 
+// Vectorised variant: 16-byte loads; a block covers 256/(c/8) pixel rows per pass (c/8 must divide 256).
+__global__ void __launch_bounds__(256)
+colsum16_vec_kernel(const uint4* __restrict__ x, long long npix, int c, int ldv, float mul,
+                    const float* __restrict__ div_dev, int bf, float* __restrict__ out) {
+  __shared__ float red[2048];       // [row-in-pass][channel], rows-per-pass * c == 2048
+  const int tpr = c >> 3, rpp = 256 / tpr;
+  const int v = threadIdx.x % tpr, r = threadIdx.x / tpr;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) acc[j] = 0.f;
+  for (long long p = (long long)blockIdx.x * rpp + r; p < npix; p += (long long)gridDim.x * rpp) {
+    const uint4 u = x[p * ldv + v];
+    const float2 a = unpack2(u.x, bf), b = unpack2(u.y, bf), cc = unpack2(u.z, bf), d = unpack2(u.w, bf);
+    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+    acc[4] += cc.x; acc[5] += cc.y; acc[6] += d.x; acc[7] += d.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) red[r * c + v * 8 + j] = acc[j];
+  __syncthreads();
+  if (div_dev) mul /= __ldg(div_dev);
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
+    float t = 0.f;
+    for (int k = 0; k < rpp; k++) t += red[k * c + ch];
+    atomicAdd(out + ch, t * mul);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // dynamic gradient scale
 // ------------------------------------------------------------------------------------------
@@ -560,12 +587,22 @@ extern "C" int pesr_colsum16(const void* x, int64_t npix, int32_t c, int32_t ldc
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * c, stream);
     if (e != cudaSuccess) { set_error("colsum16: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
   }
-  long long bx = (npix + 8 * 64 - 1) / (8 * 64);
-  if (bx > 1024) bx = 1024;
-  if (bx < 1) bx = 1;
-  dim3 grid((unsigned)bx, (unsigned)((c + 63) / 64));
-  colsum16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(x), npix, c, ldc, mul_host, div_dev,
-                                           dtype, out);
+  const int tpr = c / 8;
+  if (c % 8 == 0 && ldc % 8 == 0 && tpr <= 256 && 256 % tpr == 0 && ((uintptr_t)x % 16) == 0) {
+    const int rpp = 256 / tpr;
+    long long bx = (npix + (long long)rpp * 16 - 1) / ((long long)rpp * 16);
+    if (bx > 148 * 4) bx = 148 * 4;
+    if (bx < 1) bx = 1;
+    colsum16_vec_kernel<<<(unsigned)bx, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), npix, c, ldc / 8, mul_host,
+                                                         div_dev, dtype, out);
+  } else {
+    long long bx = (npix + 8 * 64 - 1) / (8 * 64);
+    if (bx > 1024) bx = 1024;
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, (unsigned)((c + 63) / 64));
+    colsum16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(x), npix, c, ldc, mul_host, div_dev,
+                                             dtype, out);
+  }
   count_launch();
   PESR_CHECK_LAUNCH("colsum16");
   return 0;

@@ -124,6 +124,15 @@ if __name__ == "__main__":
                         a, b = out.cpu().tolist()
                         print(f"mma rate pair={pair} N={n} blocks={blocks} stages={stages}: issue {a/(iters*4):.1f} cyc/MMA, "
                               f"complete {b/(iters*4):.1f} cyc/MMA (ideal {128*n/256:.0f})", flush=True)
+    if what == "wskip":
+        from pesr_b200._lib import lib
+        lib.pesr_debug_wgrad_desc(-1, 0)
+        for sk in (0, 1, 2, 3):
+            lib.pesr_debug_wgrad_desc(-2, sk)
+            print("wgrad skip", sk)
+            wgrad_case(16, 256, 256, 48, 48)
+        lib.pesr_debug_wgrad_desc(-2, 0)
+        lib.pesr_debug_wgrad_desc(-1, 1)
     if what == "wtimeline":
         from pesr_b200._lib import lib
         buf = torch.zeros(64 + 2 * 160, dtype=torch.int64, device="cuda")

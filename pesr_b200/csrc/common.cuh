@@ -407,6 +407,38 @@ __host__ __device__ __forceinline__ uint32_t make_idesc(int M, int N, int is_bf1
 }
 
 // ------------------------------------------------------------------------------------------
+// 256-bit global loads / stores (sm_100: LDG/STG.E.ENL2.256).  The conv epilogues have one thread per pixel row, so a
+// warp-level access touches 32 different lines; halving the instruction count halves the LSU wavefronts, which is what
+// bounded the epilogues that stream the fp32 residual.  Addresses must be 32-byte aligned.
+// ------------------------------------------------------------------------------------------
+struct __align__(32) f32x8 { float v[8]; };
+struct __align__(32) u32x8 { uint32_t v[8]; };
+__device__ __forceinline__ f32x8 ld256_f32(const float* p) {
+  f32x8 r;
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st256_f32(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+               ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ u32x8 ld256_b32(const void* p) {
+  u32x8 r;
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st256_b32(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+               ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "l"(p)
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
 // 16-bit storage helpers (runtime dtype: 0 = fp16, 1 = bf16)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack2(float a, float b, int is_bf16) {

@@ -265,24 +265,24 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       // software pipeline over 32-column chunks: the TMEM load and the fp32-residual loads of chunk ch+1 are in flight
       // while chunk ch is processed (one exposed latency per tile instead of one per chunk)
       uint32_t v[32], vn[32];
-      float4 rn[8];
+      f32x8 rn[4];
       const float* res_row = (p.res32 && valid) ? p.res32 + pix * p.ld_res32 + n0 : nullptr;
       tmem_ld32(taddr + ch_lo * 32, v);
       if (res_row) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) rn[j] = reinterpret_cast<const float4*>(res_row + ch_lo * 32)[j];
+        for (int j = 0; j < 4; j++) rn[j] = ld256_f32(res_row + ch_lo * 32 + 8 * j);
       }
       tmem_ld_wait();
       for (int ch = ch_lo; ch < ch_hi; ch++) {
-        float4 rc[8];
+        f32x8 rc[4];
 #pragma unroll
-        for (int j = 0; j < 8; j++) rc[j] = rn[j];
+        for (int j = 0; j < 4; j++) rc[j] = rn[j];
         const bool more = ch + 1 < ch_hi;
         if (more) {
           tmem_ld32(taddr + (ch + 1) * 32, vn);
           if (res_row) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) rn[j] = reinterpret_cast<const float4*>(res_row + (ch + 1) * 32)[j];
+            for (int j = 0; j < 4; j++) rn[j] = ld256_f32(res_row + (ch + 1) * 32 + 8 * j);
           }
         }
         if (valid) {
@@ -292,18 +292,19 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
           for (int j = 0; j < 32; j++) f[j] = alpha * (__uint_as_float(v[j]) + bs[ch * 32 + j]);
           if (p.res32) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-              f[4 * j] += rc[j].x; f[4 * j + 1] += rc[j].y; f[4 * j + 2] += rc[j].z; f[4 * j + 3] += rc[j].w;
-            }
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+              for (int e = 0; e < 8; e++) f[8 * j + e] += rc[j].v[e];
           }
           if (p.res16) {
-            const uint4* r = reinterpret_cast<const uint4*>(p.res16 + pix * p.ld_res16 + q0);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              uint4 t = r[j];
-              float2 a = unpack2(t.x, bf), b = unpack2(t.y, bf), c = unpack2(t.z, bf), d = unpack2(t.w, bf);
-              f[8 * j] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
-              f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
+            for (int j = 0; j < 2; j++) {
+              const u32x8 t = ld256_b32(p.res16 + pix * p.ld_res16 + q0 + 16 * j);
+#pragma unroll
+              for (int e = 0; e < 8; e++) {
+                const float2 a = unpack2(t.v[e], bf);
+                f[16 * j + 2 * e] += a.x; f[16 * j + 2 * e + 1] += a.y;
+              }
             }
           }
           if (p.act == PESR_ACT_RELU) {
@@ -314,22 +315,21 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
             for (int j = 0; j < 32; j++) f[j] = f[j] > 0.f ? f[j] : 0.2f * f[j];
           }
           if (p.mask16) {
-            const uint4* r = reinterpret_cast<const uint4*>(p.mask16 + pix * p.ld_mask16 + q0);
             const float neg = p.mask_mode == 2 ? 0.2f : 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              uint4 t = r[j];
-              float2 a = unpack2(t.x, bf), b = unpack2(t.y, bf), c = unpack2(t.z, bf), d = unpack2(t.w, bf);
-              f[8 * j] *= a.x > 0.f ? 1.f : neg; f[8 * j + 1] *= a.y > 0.f ? 1.f : neg;
-              f[8 * j + 2] *= b.x > 0.f ? 1.f : neg; f[8 * j + 3] *= b.y > 0.f ? 1.f : neg;
-              f[8 * j + 4] *= c.x > 0.f ? 1.f : neg; f[8 * j + 5] *= c.y > 0.f ? 1.f : neg;
-              f[8 * j + 6] *= d.x > 0.f ? 1.f : neg; f[8 * j + 7] *= d.y > 0.f ? 1.f : neg;
+            for (int j = 0; j < 2; j++) {
+              const u32x8 t = ld256_b32(p.mask16 + pix * p.ld_mask16 + q0 + 16 * j);
+#pragma unroll
+              for (int e = 0; e < 8; e++) {
+                const float2 a = unpack2(t.v[e], bf);
+                f[16 * j + 2 * e] *= a.x > 0.f ? 1.f : neg; f[16 * j + 2 * e + 1] *= a.y > 0.f ? 1.f : neg;
+              }
             }
           }
           if (p.out32) {
-            float4* o = reinterpret_cast<float4*>(p.out32 + split * p.split_stride32 + pix * p.ld_out32 + q0);
+            float* o = p.out32 + split * p.split_stride32 + pix * p.ld_out32 + q0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            for (int j = 0; j < 4; j++) st256_f32(o + 8 * j, f + 8 * j);
           }
           if (p.out16) {
             long long off;
@@ -345,16 +345,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
                   ((long long)img * p.out_h + (h * p.out_sy + p.out_oy)) * p.out_w + (w * p.out_sx + p.out_ox);
               off = op * p.ld_out16 + p.out_coff + q0;
             }
-            uint4* o = reinterpret_cast<uint4*>(p.out16 + off);
+            uint32_t pk[16];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              uint4 t;
-              t.x = pack2(f[8 * j], f[8 * j + 1], bf);
-              t.y = pack2(f[8 * j + 2], f[8 * j + 3], bf);
-              t.z = pack2(f[8 * j + 4], f[8 * j + 5], bf);
-              t.w = pack2(f[8 * j + 6], f[8 * j + 7], bf);
-              o[j] = t;
-            }
+            for (int j = 0; j < 16; j++) pk[j] = pack2(f[2 * j], f[2 * j + 1], bf);
+            st256_b32(p.out16 + off, pk);
+            st256_b32(p.out16 + off + 16, pk + 8);
           }
         }
         if (more) {
@@ -430,6 +425,13 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d, void* stream_) {
   PESR_CHECK_ARG(d->nsrc >= 1 && d->nsrc <= PESR_MAX_SRC, "conv_igemm: nsrc %d", d->nsrc);
   PESR_CHECK_ARG(d->wpacked != nullptr && d->w_rows > 0, "conv_igemm: missing packed weights");
   PESR_CHECK_ARG(d->out16 != nullptr || d->out32 != nullptr, "conv_igemm: no output");
+  // the epilogue moves 32-byte vectors: 32 channels of a pixel must start on a 32-byte boundary in every tensor
+  PESR_CHECK_ARG((!d->out16 || (((uintptr_t)d->out16 % 32) == 0 && d->ld_out16 % 16 == 0 && d->out_coff % 16 == 0)) &&
+                     (!d->out32 || (((uintptr_t)d->out32 % 32) == 0 && d->ld_out32 % 8 == 0 && d->split_stride32 % 8 == 0)) &&
+                     (!d->res32 || (((uintptr_t)d->res32 % 32) == 0 && d->ld_res32 % 8 == 0)) &&
+                     (!d->res16 || (((uintptr_t)d->res16 % 32) == 0 && d->ld_res16 % 16 == 0)) &&
+                     (!d->mask16 || (((uintptr_t)d->mask16 % 32) == 0 && d->ld_mask16 % 16 == 0)),
+                 "conv_igemm: epilogue tensors must be 32-byte aligned with channel strides that are multiples of 32 bytes");
   for (int t = 0; t < d->ntaps; t++) {
     PESR_CHECK_ARG(d->tap_src[t] >= 0 && d->tap_src[t] < d->nsrc, "conv_igemm: tap %d reads source %d", t,
                    d->tap_src[t]);

@@ -229,11 +229,8 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
           }
         }
         if (m < p.m_total) {
-          float4* o = reinterpret_cast<float4*>(dst + ch * 32);
 #pragma unroll
-          for (int j = 0; j < 8; j++)
-            o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                               __uint_as_float(v[4 * j + 3]));
+          for (int j = 0; j < 4; j++) st256_b32(dst + ch * 32 + 8 * j, v + 8 * j);
         }
       }
       if (dbg && threadIdx.x == 64) dbg[17] = clock64();
@@ -285,6 +282,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, 
     for (int t = 0; t < ntaps; t++) {
       float s = 0.f;
       const float* src = part + t * tap_stride + (long long)m * n_total + n;
+#pragma unroll 8
       for (int k = 0; k < splits; k++) s += src[k * split_stride];
       s *= scale;
       g[t] = accumulate ? g[t] + s : s;
@@ -381,6 +379,7 @@ extern "C" int pesr_conv_wgrad(const pesr_wgrad_desc* d, int32_t* splits_out, vo
   PESR_CHECK_ARG(d->nsrc >= 1 && d->nsrc <= PESR_MAX_SRC, "conv_wgrad: nsrc %d", d->nsrc);
   PESR_CHECK_ARG(d->a != nullptr && d->partials != nullptr, "conv_wgrad: null operand");
   PESR_CHECK_ARG(d->a_c % 8 == 0, "conv_wgrad: a_c %d must be a multiple of 8", d->a_c);
+  PESR_CHECK_ARG(((uintptr_t)d->partials % 32) == 0 && d->n_total % 8 == 0, "conv_wgrad: partials must be 32-byte aligned");
 
   WgK k;
   memset(&k, 0, sizeof(k));

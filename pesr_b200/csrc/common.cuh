@@ -254,6 +254,16 @@ __device__ __forceinline__ void tma_load_4d_w(void* dst, const CUtensorMap* m, u
       "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_w(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t"
+      "}\n"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_5d_w(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
                                               int c3, int c4) {
   asm volatile(

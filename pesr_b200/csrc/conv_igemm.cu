@@ -46,6 +46,10 @@ struct ConvK {
   uint16_t* out16; int ld_out16;
   int out_mode, out_h, out_w, out_sy, out_sx, out_oy, out_ox, out_coff, ps_c, aux_mode;
   int ksplit, b_mn_major, mn_tiles, dbg_skip;
+  // several K sub-blocks per pipeline stage, staged by ONE activation box + ONE weight box (TMA op count bounds the
+  // small-N layers): sub_mode 1 = nsub consecutive 64-channel chunks of one tap, 2 = the three vertical taps of one
+  // kernel column out of a (tile_h + 2)-row halo box
+  int sub_mode, nsub, a_sub_off, b_sub_off, a_bytes, steps_per_tile;
   unsigned long long* dbg;   // optional timeline of block 0 (bring-up): [64] clock64 stamps + [63] = globaltimer ns
   long long split_stride32;
 };
@@ -134,6 +138,26 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
         const int th = (m_tile / p.tiles_w) % p.tiles_h;
         const int img = m_tile / (p.tiles_w * p.tiles_h);   // == nb for the padding tile of an odd pair: all OOB -> zeros
         const int h0 = th * p.tile_h, w0 = tw * p.tile_w, n0 = n_tile * p.block_n + rank * b_rows;
+        if (!kPair && p.sub_mode) {
+          for (int st = 0; st < p.steps_per_tile; st++) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+            mbar_expect_tx_w(&full_bar[stage], (uint32_t)p.stage_bytes);
+            if (p.sub_mode == 2) {         // halo: kernel column dx of channel block cb, taps dy = 0..2
+              const int cb = st / 3, dx = st - cb * 3;
+              tma_load_4d_w(sa, &maps.a[0], &full_bar[stage], cb * kKBlock, w0 + dx - 1, h0 - 1, img);
+              tma_load_3d_w(sa + p.a_bytes, &maps.b, &full_bar[stage], cb * kKBlock, dx * p.cout + n0, 0);
+            } else {                        // chunks: nsub consecutive 64-channel blocks of tap t
+              const int kb = st * p.nsub;
+              const int t = kb / p.kblocks_per_tap;
+              const int cb = kb - t * p.kblocks_per_tap;
+              tma_load_5d_w(sa, &maps.a[p.tap_src[t]], &full_bar[stage], 0, w0 + p.tap_dw[t], h0 + p.tap_dh[t], img, cb);
+              tma_load_3d_w(sa + p.a_bytes, &maps.b, &full_bar[stage], 0, p.tap_widx[t] * p.cout + n0, cb);
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         const int kb0 = (int)(((long long)split * total_kb) / p.ksplit);
         const int kb1 = (int)(((long long)(split + 1) * total_kb) / p.ksplit);
         for (int kb = kb0; kb < kb1; kb++) {
@@ -188,6 +212,28 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
         if (dbg && lane == 0) dbg[8 + (tile == worker ? 0 : 4)] = clock64();    // MMA warp: accumulator free
+        if (!kPair && p.sub_mode) {
+          for (int st = 0; st < p.steps_per_tile; st++) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
+            const uint32_t b_addr = a_addr + p.a_bytes;
+            for (int j = 0; j < p.nsub; j++) {
+#pragma unroll
+              for (int k = 0; k < kKBlock / 16; k++) {
+                const uint64_t da = make_smem_desc(a_addr + j * p.a_sub_off + k * 32, 16, 1024);
+                const uint64_t db = make_smem_desc(b_addr + j * p.b_sub_off + k * 32, 16, 1024);
+                umma_f16_w(d_tmem, da, db, idesc, (st > 0 || j > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit_w(&empty_bar[stage]);
+            if (st == p.steps_per_tile - 1) umma_commit_w(&tmem_full[acc]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+          continue;
+        }
         for (int kb = kb0; kb < kb1; kb++) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -393,6 +439,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
 }
 
 static int g_dbg_skip = 0;
+static int g_sub_mode_enabled = 1;
 static unsigned long long* g_dbg_buf = nullptr;
 static int g_pair_mode = -1;  // -1: from the environment (PESR_NO_PAIR=1 disables), 0: never, 1: whenever legal
 
@@ -402,15 +449,30 @@ using namespace pesr;
 
 // Bring-up / A-B hook: 0 = never use the CTA-pair kernel, 1 = whenever legal, -1 = re-read PESR_NO_PAIR.
 extern "C" void pesr_debug_pair_mode(int mode) {
-  if (mode >= 100) g_dbg_skip = mode - 100; else g_pair_mode = mode;
+  if (mode >= 200) g_sub_mode_enabled = mode - 200;   // 200 / 201: disable / enable the multi-sub-block stages
+  else if (mode >= 100) g_dbg_skip = mode - 100;
+  else g_pair_mode = mode;
 }
 
 // Bring-up hook: device buffer of 64 uint64 that block 0 of every pesr_conv_igemm launch fills with a timeline.
 extern "C" void pesr_debug_timeline(void* buf) { g_dbg_buf = reinterpret_cast<unsigned long long*>(buf); }
 
-extern "C" int pesr_conv_igemm(const pesr_conv_desc* d, void* stream_) {
+extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  PESR_CHECK_ARG(d != nullptr, "conv_igemm: null descriptor");
+  PESR_CHECK_ARG(d_in != nullptr, "conv_igemm: null descriptor");
+  pesr_conv_desc dd = *d_in;
+  const pesr_conv_desc* d = &dd;
+  // Tile-width heuristic (measured, tools/perf_conv.py bn128): 256-wide layers with too few pixel tiles for the CTA-pair
+  // kernel run faster as 128-wide tiles with several K sub-blocks per stage (twice the tiles, a third of the TMA ops).
+  if (g_pair_mode < 0) {
+    const char* e = getenv("PESR_NO_PAIR");
+    g_pair_mode = (e && e[0] == '1') ? 0 : 1;
+  }
+  if (dd.block_n == 256 && dd.tile_h > 0 && dd.tile_w > 0 && g_sub_mode_enabled && dd.ksplit <= 1 && !dd.b_mn_major) {
+    const int mt = dd.nb * ((dd.h + dd.tile_h - 1) / dd.tile_h) * ((dd.w + dd.tile_w - 1) / dd.tile_w);
+    const bool will_pair = g_pair_mode == 2 || (g_pair_mode == 1 && mt >= 256);
+    if (!will_pair && (dd.ntaps == 9 || (dd.cin / kKBlock) % 2 == 0)) dd.block_n = 128;
+  }
   PESR_CHECK_ARG(d->dtype == PESR_DT_F16 || d->dtype == PESR_DT_BF16, "conv_igemm: bad dtype %d", d->dtype);
   PESR_CHECK_ARG(d->nb > 0 && d->h > 0 && d->w > 0, "conv_igemm: empty pixel grid %dx%dx%d", d->nb, d->h, d->w);
   PESR_CHECK_ARG(d->cin > 0 && d->cin % kKBlock == 0, "conv_igemm: cin %d must be a multiple of 64", d->cin);
@@ -454,15 +516,33 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d, void* stream_) {
   const bool pair_legal = d->ksplit <= 1 && !d->b_mn_major && d->block_n >= 64 && m_tiles_host >= 2;
   const bool pair = pair_legal && (g_pair_mode == 2 || (g_pair_mode == 1 && d->block_n == 256 && m_tiles_host >= 256));
 
+  // multi-sub-block stages (single-CTA kernel only): see ConvK::sub_mode
+  int sub_mode = 0, nsub = 1;
+  if (!pair && g_sub_mode_enabled && d->ksplit <= 1 && !d->b_mn_major && d->block_n <= (g_sub_mode_enabled >= 2 ? 256 : 128)) {
+    bool std9 = d->ntaps == 9 && d->nsrc == 1;
+    for (int t = 0; std9 && t < 9; t++)
+      std9 = d->tap_dh[t] == t / 3 - 1 && d->tap_dw[t] == t % 3 - 1 && d->tap_src[t] == 0 && d->tap_widx[t] == t;
+    if (std9 && d->w_rows == 9 * d->cout && d->block_n <= 128) { sub_mode = 2; nsub = 3; }
+    else if ((d->cin / kKBlock) % 2 == 0) { sub_mode = 1; nsub = 2; }
+  }
+
   ConvMaps maps;
   memset(&maps, 0, sizeof(maps));
   for (int s = 0; s < PESR_MAX_SRC; s++) {
     const int ss = s < d->nsrc ? s : 0;  // unused slots alias source 0 so every descriptor is valid
     PESR_CHECK_ARG(d->src[ss] != nullptr, "conv_igemm: source %d is null", ss);
-    uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->src_w[ss], (uint64_t)d->src_h[ss], (uint64_t)d->nb};
-    uint64_t str[3] = {(uint64_t)d->src_sw[ss] * 2, (uint64_t)d->src_sh[ss] * 2, (uint64_t)d->src_sn[ss] * 2};
-    uint32_t box[4] = {(uint32_t)kKBlock, (uint32_t)d->tile_w, (uint32_t)d->tile_h, 1};
-    int r = get_tensor_map(&maps.a[s], d->src[ss], d->dtype, 4, dims, str, box);
+    int r;
+    if (sub_mode == 1) {
+      uint64_t dims[5] = {64, (uint64_t)d->src_w[ss], (uint64_t)d->src_h[ss], (uint64_t)d->nb, (uint64_t)(d->cin / 64)};
+      uint64_t str[4] = {(uint64_t)d->src_sw[ss] * 2, (uint64_t)d->src_sh[ss] * 2, (uint64_t)d->src_sn[ss] * 2, 128};
+      uint32_t box[5] = {64, (uint32_t)d->tile_w, (uint32_t)d->tile_h, 1, (uint32_t)nsub};
+      r = get_tensor_map(&maps.a[s], d->src[ss], d->dtype, 5, dims, str, box);
+    } else {
+      uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->src_w[ss], (uint64_t)d->src_h[ss], (uint64_t)d->nb};
+      uint64_t str[3] = {(uint64_t)d->src_sw[ss] * 2, (uint64_t)d->src_sh[ss] * 2, (uint64_t)d->src_sn[ss] * 2};
+      uint32_t box[4] = {(uint32_t)kKBlock, (uint32_t)d->tile_w, (uint32_t)(sub_mode == 2 ? d->tile_h + 2 : d->tile_h), 1};
+      r = get_tensor_map(&maps.a[s], d->src[ss], d->dtype, 4, dims, str, box);
+    }
     if (r) return r;
   }
   const int ksplit = d->ksplit > 1 ? d->ksplit : 1;
@@ -477,6 +557,19 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d, void* stream_) {
     uint64_t str[1] = {(uint64_t)d->cout * 2};
     uint32_t box[2] = {64, 64};
     int r = get_tensor_map(&maps.b, d->wpacked, d->dtype, 2, dims, str, box);
+    if (r) return r;
+  } else if (sub_mode == 2) {
+    // weights [tap = dy*3+dx][cout][cin] viewed as [dy][dx*cout + o][cin]: one box = the 3 vertical taps of column dx
+    uint64_t dims[3] = {(uint64_t)d->cin, (uint64_t)(3 * d->cout), 3};
+    uint64_t str[2] = {(uint64_t)d->cin * 2, (uint64_t)3 * d->cout * d->cin * 2};
+    uint32_t box[3] = {(uint32_t)kKBlock, (uint32_t)d->block_n, 3};
+    int r = get_tensor_map(&maps.b, d->wpacked, d->dtype, 3, dims, str, box);
+    if (r) return r;
+  } else if (sub_mode == 1) {
+    uint64_t dims[3] = {64, (uint64_t)d->w_rows, (uint64_t)(d->cin / 64)};
+    uint64_t str[2] = {(uint64_t)d->cin * 2, 128};
+    uint32_t box[3] = {64, (uint32_t)d->block_n, (uint32_t)nsub};
+    int r = get_tensor_map(&maps.b, d->wpacked, d->dtype, 3, dims, str, box);
     if (r) return r;
   } else {
     uint64_t dims[2] = {(uint64_t)d->cin, (uint64_t)d->w_rows};
@@ -504,6 +597,16 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d, void* stream_) {
   k.split_stride32 = d->split_stride32;
   k.kblocks_per_tap = d->cin / kKBlock;
   k.stage_bytes = kABytes + (pair ? d->block_n / 2 : d->block_n) * kKBlock * 2;   // per CTA
+  k.sub_mode = sub_mode;
+  k.nsub = nsub;
+  if (sub_mode) {
+    const int b_tile = d->block_n * kKBlock * 2;
+    k.a_bytes = sub_mode == 2 ? (d->tile_h + 2) * d->tile_w * 128 : nsub * kABytes;
+    k.a_sub_off = sub_mode == 2 ? d->tile_w * 128 : kABytes;
+    k.b_sub_off = b_tile;
+    k.stage_bytes = k.a_bytes + nsub * b_tile;
+    k.steps_per_tile = sub_mode == 2 ? 3 * (d->cin / kKBlock) : d->ntaps * (d->cin / kKBlock) / nsub;
+  }
   const int smem_budget = 227 * 1024 - 4096;
   k.stages = smem_budget / k.stage_bytes;
   if (k.stages > kMaxStages) k.stages = kMaxStages;

@@ -31,14 +31,14 @@ def timeit(fn, iters=10, warm=3, flush=True):
     return tot / iters
 
 
-def conv_case(nb, cin, cout, h, w, dtype=torch.float16, **epi):
+def conv_case(nb, cin, cout, h, w, dtype=torch.float16, block_n=None, **epi):
     x16 = torch.randn(nb, h, w, cin, device="cuda").to(dtype)
     wp = (torch.randn(9 * cout, cin, device="cuda") / (3 * cin ** 0.5)).to(dtype)
     out16 = torch.empty(nb, h, w, cout, device="cuda", dtype=dtype)
     bias = torch.randn(cout, device="cuda")
     d = ops.make_conv_desc(dtype=ops.dt_code(dtype), nb=nb, h=h, w=w, cin=cin, cout=cout,
                            srcs=[ops.nhwc_src(x16, nb, h, w, cin)], wpacked=wp, bias=bias, act=1, out16=out16,
-                           ld_out16=cout)
+                           ld_out16=cout, block_n=block_n)
     ms = timeit(lambda: ops.conv_igemm(d))
     fl = 2.0 * nb * h * w * cout * cin * 9
     # cuDNN comparator (channels_last fp16)
@@ -186,6 +186,32 @@ if __name__ == "__main__":
                 print(f"  pair={pair} block-0 timeline (cycles from start, SM clock {mhz:.0f} MHz, total {(b[63]-b[62])/1e3:.1f} us):")
                 print("   " + "; ".join(f"{names[i]}={b[i]-t0}" for i in sorted(names) if b[i]))
         lib.pesr_debug_timeline(0)
+    if what == "bn128":
+        for bn in (256, 128):
+            print("block_n", bn)
+            conv_case(16, 512, 512, 24, 24, block_n=bn)
+            conv_case(32, 512, 512, 24, 24, block_n=bn)
+            conv_case(32, 256, 512, 24, 24, block_n=bn)
+            conv_case(32, 512, 512, 12, 12, block_n=bn)
+            conv_case(16, 512, 512, 12, 12, block_n=bn)
+            conv_case(16, 128, 256, 48, 48, block_n=bn)
+            conv_case(16, 256, 256, 24, 24, block_n=bn)
+            conv_case(16, 256, 256, 48, 48, block_n=bn)
+            conv_case(32, 256, 256, 48, 48, block_n=bn)
+    if what == "sub":
+        from pesr_b200._lib import lib
+        lib.pesr_debug_pair_mode(0)
+        for mode in (201, 202):
+            lib.pesr_debug_pair_mode(mode)
+            print("sub-block stages", mode - 200, "(pair off)")
+            conv_case(16, 512, 512, 24, 24)
+            conv_case(32, 512, 512, 24, 24)
+            conv_case(32, 256, 512, 24, 24)
+            conv_case(32, 512, 512, 12, 12)
+            conv_case(16, 128, 256, 48, 48)
+            conv_case(16, 256, 256, 48, 48)
+        lib.pesr_debug_pair_mode(1)
+        lib.pesr_debug_pair_mode(201)
     if what == "skip":
         from pesr_b200._lib import lib
         lib.pesr_debug_pair_mode(0)

@@ -228,6 +228,8 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(fn, k):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -254,6 +256,14 @@ def run_b200(args):
     launches = L.launch_count()
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
+    # CPU time to ENQUEUE one step into an empty stream (no launch-queue back-pressure): GPU-bound if < ms_per_step
+    for i in range(3):
+        barrier()
+        h0 = time.perf_counter()
+        do_step(dev_lr[i % n_host], dev_hr[i % n_host])
+        host_ms[0] = (time.perf_counter() - h0) * 1e3 if i == 0 else min(host_ms[0], (time.perf_counter() - h0) * 1e3)
+    barrier()
+    host_enqueue_ms = host_ms[0]
 
     # ---- end-to-end arm: pinned host batch -> H2D -> step -> D2H loss, every step
     last = {}
@@ -319,7 +329,7 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e},
-        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "roofline": roofline, "cpu_baseline": cpu,
     }
     line.update(extras)
     print(json.dumps(line), flush=True)

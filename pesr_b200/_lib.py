@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpesr_b200.so")
+# PESR_B200_LIB: A/B a differently built library of the same ABI (tools/ab_*.sh); default = the in-tree build
+LIB_PATH = os.environ.get("PESR_B200_LIB") or os.path.join(_HERE, "libpesr_b200.so")
 
 MAX_TAPS = 9
 MAX_SRC = 4

@@ -392,6 +392,12 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 //  * K-major operand  (rows of 64 K-elements = 128 B): SBO = distance between 8-row groups, LBO unused (=1).
 //  * MN-major operand (rows of 64 MN-elements = 128 B, one row per K index): SBO = distance between
 //    8-K-row groups, LBO = distance between successive 64-element MN chunks.
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still draining.  griddep_wait() blocks until every prerequisite grid has
+// completed and its memory is visible; griddep_launch() lets the NEXT kernel's CTAs be scheduled as this grid's exit.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);

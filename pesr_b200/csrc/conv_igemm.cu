@@ -10,6 +10,8 @@
 //               so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   warps 2..5  epilogue: tcgen05.ld -> bias / scale / residual / activation / ReLU-mask -> global
 //               (NHWC 16-bit, optional fp32 copy, optional PixelShuffle(2) / inverse addressing).
+#include <type_traits>
+
 #include "common.cuh"
 #include "host_util.cuh"
 
@@ -45,7 +47,7 @@ struct ConvK {
   float* out32; int ld_out32;
   uint16_t* out16; int ld_out16;
   int out_mode, out_h, out_w, out_sy, out_sx, out_oy, out_ox, out_coff, ps_c, aux_mode;
-  int ksplit, b_mn_major, mn_tiles, dbg_skip;
+  int ksplit, b_mn_major, mn_tiles, pdl_early_b;
   // several K sub-blocks per pipeline stage, staged by ONE activation box + ONE weight box (TMA op count bounds the
   // small-N layers): sub_mode 1 = nsub consecutive 64-channel chunks of one tap, 2 = the three vertical taps of one
   // kernel column out of a (tile_h + 2)-row halo box
@@ -128,74 +130,119 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp, warp-uniform; one elected lane issues) =====================
-    {
+    // The loop below is on the critical path of the pipeline fill (one warp, dependent-issue latency), so it is
+    // specialised per staging mode and walks (tap, channel block) incrementally instead of dividing per step.
+    //   MODE 0: one 64-channel k-block per stage (also the CTA-pair path)     3: same with MN-major weights
+    //   MODE 1: nsub consecutive channel blocks of one tap per stage          2: halo stage (3 vertical taps)
+    auto produce = [&](auto mode_tag) {
+      constexpr int MODE = decltype(mode_tag)::value;
       int stage = 0;
       uint32_t phase = 0;
+      const int kpt = p.kblocks_per_tap;
+      // position inside the K loop: MODE 0/1/3: (t, cb); MODE 2: (cb, dx) with t := dx
+      auto seek = [&](int s, int& t, int& cb) {
+        if (MODE == 2) { cb = s / 3; t = s - cb * 3; }
+        else { const int kb = MODE == 1 ? s * p.nsub : s; t = kb / kpt; cb = kb - t * kpt; }
+      };
+      auto advance = [&](int& t, int& cb) {
+        if (MODE == 2) { if (++t == 3) { t = 0; cb++; } }
+        else { cb += MODE == 1 ? p.nsub : 1; if (cb >= kpt) { cb = 0; t++; } }
+      };
+      auto expect = [&](uint64_t* fb) {
+        if (kPair) { if (leader) mbar_expect_tx_w(fb, 2u * (uint32_t)p.stage_bytes); }
+        else mbar_expect_tx_w(fb, (uint32_t)p.stage_bytes);
+      };
+      auto load_b = [&](uint8_t* sa, uint64_t* fb, int s, int t, int cb, int n0) {
+        if (MODE == 2) {
+          tma_load_3d_w(sa + p.a_bytes, &maps.b, fb, cb * kKBlock, t * p.cout + n0, 0);
+        } else if (MODE == 1) {
+          tma_load_3d_w(sa + p.a_bytes, &maps.b, fb, 0, p.tap_widx[t] * p.cout + n0, cb);
+        } else if (MODE == 3) {
+          // weights stored [K][N] (N contiguous): one 64(K) x 64(N) box per 64 output columns
+          for (int i = 0; i < p.block_n / 64; i++) tma_load_2d_w(sa + kABytes + i * 8192, &maps.b, fb, n0 + i * 64, s * kKBlock);
+        } else if (kPair) {
+          tma2_load_2d_w(sa + kABytes, &maps.b, fb, cb * kKBlock, p.tap_widx[t] * p.cout + n0);
+        } else {
+          tma_load_2d_w(sa + kABytes, &maps.b, fb, cb * kKBlock, p.tap_widx[t] * p.cout + n0);
+        }
+      };
+      auto step_range = [&](int split, int& s0, int& s1) {
+        if (MODE == 1 || MODE == 2) { s0 = 0; s1 = p.steps_per_tile; return; }
+        s0 = (int)(((long long)split * total_kb) / p.ksplit);
+        s1 = (int)(((long long)(split + 1) * total_kb) / p.ksplit);
+      };
+      // PDL prologue: the weights do not depend on the preceding kernel, so the first ring of weight boxes is in
+      // flight while that kernel drains
+      int npre = 0;
+      if (p.pdl_early_b) {
+        int split, m_tile, n_tile, s0, s1, t, cb;
+        decode(worker, split, m_tile, n_tile);
+        step_range(split, s0, s1);
+        seek(s0, t, cb);
+        npre = s1 - s0 < p.stages ? s1 - s0 : p.stages;
+        const int n0 = n_tile * p.block_n + rank * b_rows;
+        for (int i = 0; i < npre; i++) {
+          expect(&full_bar[i]);
+          load_b(smem + (size_t)i * p.stage_bytes, &full_bar[i], s0 + i, t, cb, n0);
+          advance(t, cb);
+        }
+      }
+      griddep_wait();
+      griddep_launch();
       for (int tile = worker; tile < p.num_tiles; tile += nworkers) {
-        int split, m_tile, n_tile;
+        int split, m_tile, n_tile, s0, s1, t, cb;
         decode(tile, split, m_tile, n_tile);
+        step_range(split, s0, s1);
+        seek(s0, t, cb);
         const int tw = m_tile % p.tiles_w;
         const int th = (m_tile / p.tiles_w) % p.tiles_h;
         const int img = m_tile / (p.tiles_w * p.tiles_h);   // == nb for the padding tile of an odd pair: all OOB -> zeros
         const int h0 = th * p.tile_h, w0 = tw * p.tile_w, n0 = n_tile * p.block_n + rank * b_rows;
-        if (!kPair && p.sub_mode) {
-          for (int st = 0; st < p.steps_per_tile; st++) {
+        int s = s0;
+        while (s < s1) {
+          // everything that depends on the tap only is computed once per tap (MODE 2: once per channel block)
+          const int inner_step = MODE == 1 ? p.nsub : 1;
+          const int inner_end = MODE == 2 ? 3 : kpt;
+          int& inner = MODE == 2 ? t : cb;
+          const int tap = MODE == 2 ? 0 : t;
+          const CUtensorMap* ma = &maps.a[MODE == 2 ? 0 : p.tap_src[tap]];
+          const int hh = MODE == 2 ? h0 - 1 : h0 + p.tap_dh[tap];
+          const int ww = MODE == 2 ? w0 - 1 : w0 + p.tap_dw[tap];
+          const int brow = MODE == 2 ? n0 : p.tap_widx[tap] * p.cout + n0;
+          for (; inner < inner_end && s < s1; inner += inner_step, s++) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-            mbar_expect_tx_w(&full_bar[stage], (uint32_t)p.stage_bytes);
-            if (p.sub_mode == 2) {         // halo: kernel column dx of channel block cb, taps dy = 0..2
-              const int cb = st / 3, dx = st - cb * 3;
-              tma_load_4d_w(sa, &maps.a[0], &full_bar[stage], cb * kKBlock, w0 + dx - 1, h0 - 1, img);
-              tma_load_3d_w(sa + p.a_bytes, &maps.b, &full_bar[stage], cb * kKBlock, dx * p.cout + n0, 0);
-            } else {                        // chunks: nsub consecutive 64-channel blocks of tap t
-              const int kb = st * p.nsub;
-              const int t = kb / p.kblocks_per_tap;
-              const int cb = kb - t * p.kblocks_per_tap;
-              tma_load_5d_w(sa, &maps.a[p.tap_src[t]], &full_bar[stage], 0, w0 + p.tap_dw[t], h0 + p.tap_dh[t], img, cb);
-              tma_load_3d_w(sa + p.a_bytes, &maps.b, &full_bar[stage], 0, p.tap_widx[t] * p.cout + n0, cb);
+            uint64_t* fb = &full_bar[stage];
+            const bool with_b = npre == 0;     // else: the weights of this step were issued in the prologue
+            if (with_b) expect(fb); else npre--;
+            if (MODE == 2) {
+              tma_load_4d_w(sa, ma, fb, cb * kKBlock, ww + t, hh, img);
+              if (with_b) tma_load_3d_w(sa + p.a_bytes, &maps.b, fb, cb * kKBlock, t * p.cout + brow, 0);
+            } else if (MODE == 1) {
+              tma_load_5d_w(sa, ma, fb, 0, ww, hh, img, cb);
+              if (with_b) tma_load_3d_w(sa + p.a_bytes, &maps.b, fb, 0, brow, cb);
+            } else if (kPair) {
+              tma2_load_4d_w(sa, ma, fb, cb * kKBlock, ww, hh, img);
+              if (with_b) tma2_load_2d_w(sa + kABytes, &maps.b, fb, cb * kKBlock, brow);
+            } else {
+              tma_load_4d_w(sa, ma, fb, cb * kKBlock, ww, hh, img);
+              if (with_b) load_b(sa, fb, s, t, cb, n0);
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            if (dbg && lane == 0 && tile == worker && s == s0) dbg[1] = clock64();          // first TMA issued
           }
-          continue;
-        }
-        const int kb0 = (int)(((long long)split * total_kb) / p.ksplit);
-        const int kb1 = (int)(((long long)(split + 1) * total_kb) / p.ksplit);
-        for (int kb = kb0; kb < kb1; kb++) {
-          const int t = kb / p.kblocks_per_tap;
-          const int cb = kb - t * p.kblocks_per_tap;
-          const CUtensorMap* ma = &maps.a[p.tap_src[t]];
-          const int hh = h0 + p.tap_dh[t], ww = w0 + p.tap_dw[t];
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-          if (kPair) {
-            if (leader) mbar_expect_tx_w(&full_bar[stage], 2u * (uint32_t)p.stage_bytes);
-            tma2_load_4d_w(sa, ma, &full_bar[stage], cb * kKBlock, ww, hh, img);
-            tma2_load_2d_w(sa + kABytes, &maps.b, &full_bar[stage], cb * kKBlock, p.tap_widx[t] * p.cout + n0);
-          } else if (p.dbg_skip) {
-            // bring-up experiment: after the ring has been filled once, skip the A (1), B (2) or both (3) loads
-            const bool warm = (kb - kb0) >= p.stages || tile != worker;
-            const bool la = !(warm && (p.dbg_skip & 1)), lb = !(warm && (p.dbg_skip & 2));
-            const uint32_t bytes = (la ? kABytes : 0) + (lb ? (uint32_t)(p.stage_bytes - kABytes) : 0);
-            if (bytes) mbar_expect_tx_w(&full_bar[stage], bytes); else if (lane == 0) mbar_arrive(&full_bar[stage]);
-            if (la) tma_load_4d_w(sa, ma, &full_bar[stage], cb * kKBlock, ww, hh, img);
-            if (lb) tma_load_2d_w(sa + kABytes, &maps.b, &full_bar[stage], cb * kKBlock, p.tap_widx[t] * p.cout + n0);
-          } else {
-            mbar_expect_tx_w(&full_bar[stage], (uint32_t)p.stage_bytes);
-            tma_load_4d_w(sa, ma, &full_bar[stage], cb * kKBlock, ww, hh, img);
-            if (p.b_mn_major) {
-              // weights stored [K][N] (N contiguous): one 64(K) x 64(N) box per 64 output columns
-              for (int i = 0; i < p.block_n / 64; i++)
-                tma_load_2d_w(sa + kABytes + i * 8192, &maps.b, &full_bar[stage], n0 + i * 64, kb * kKBlock);
-            } else {
-              tma_load_2d_w(sa + kABytes, &maps.b, &full_bar[stage], cb * kKBlock, p.tap_widx[t] * p.cout + n0);
-            }
+          if (inner >= inner_end) {
+            inner = 0;
+            if (MODE == 2) cb++; else t++;
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
-          if (dbg && lane == 0 && tile == worker && kb == kb0) dbg[1] = clock64();          // first TMA issued
         }
         if (dbg && lane == 0) dbg[2 + (tile == worker ? 0 : 1)] = clock64();    // all TMAs of tile 0 / last tile issued
       }
-    }
+    };
+    if (kPair || (p.sub_mode == 0 && !p.b_mn_major)) produce(std::integral_constant<int, 0>{});
+    else if (p.sub_mode == 1) produce(std::integral_constant<int, 1>{});
+    else if (p.sub_mode == 2) produce(std::integral_constant<int, 2>{});
+    else produce(std::integral_constant<int, 3>{});
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only in pair mode) =====================
     if (leader) {
@@ -267,6 +314,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
   } else {
     // ===================== epilogue (warps 2..5) =====================
     // (two warps per TMEM lane quarter were tried: measured 5-10% SLOWER, the extra warps compete with the issue warps)
+    griddep_wait();   // bias / alpha / residual / mask may be written by the preceding kernel (PDL)
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const int et = threadIdx.x - 64;  // 0..127
@@ -438,7 +486,6 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
   }
 }
 
-static int g_dbg_skip = 0;
 static int g_sub_mode_enabled = 1;
 static unsigned long long* g_dbg_buf = nullptr;
 static int g_pair_mode = -1;  // -1: from the environment (PESR_NO_PAIR=1 disables), 0: never, 1: whenever legal
@@ -449,8 +496,9 @@ using namespace pesr;
 
 // Bring-up / A-B hook: 0 = never use the CTA-pair kernel, 1 = whenever legal, -1 = re-read PESR_NO_PAIR.
 extern "C" void pesr_debug_pair_mode(int mode) {
-  if (mode >= 200) g_sub_mode_enabled = mode - 200;   // 200 / 201: disable / enable the multi-sub-block stages
-  else if (mode >= 100) g_dbg_skip = mode - 100;
+  if (mode >= 300) set_pdl(mode - 300);                // 300 / 301: programmatic dependent launch off / on
+  else if (mode >= 200) g_sub_mode_enabled = mode - 200;   // 200 / 201: disable / enable the multi-sub-block stages
+  else if (mode >= 100) { /* load-skip experiment of the bring-up phase: removed */ }
   else g_pair_mode = mode;
 }
 
@@ -592,7 +640,7 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
   k.ksplit = ksplit;
   k.num_tiles = k.mn_tiles * ksplit;
   k.b_mn_major = d->b_mn_major ? 1 : 0;
-  k.dbg_skip = g_dbg_skip;
+  k.pdl_early_b = (pdl_enabled() && weights_settled()) ? 1 : 0;
   k.dbg = g_dbg_buf;
   k.split_stride32 = d->split_stride32;
   k.kblocks_per_tap = d->cin / kKBlock;
@@ -644,29 +692,42 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
   }
   const bool prof = profiling_enabled();
   if (prof) profile_begin(0, 2.0 * d->nb * d->h * d->w * (double)d->cout * d->cin * d->ntaps, stream);
-  if (pair) {
-    int clusters = k.num_tiles < num_sms() / 2 ? k.num_tiles : num_sms() / 2;
+  {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * clusters);
     cfg.blockDim = dim3(kNumThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pair) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 2;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      na++;
+    }
+    if (pdl_enabled()) {
+      // the kernel's prologue (barriers, TMEM, first weight boxes) overlaps the tail of the preceding kernel
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      na++;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, maps, k);
+    cfg.numAttrs = na;
+    cudaError_t e;
+    if (pair) {
+      const int clusters = k.num_tiles < num_sms() / 2 ? k.num_tiles : num_sms() / 2;
+      cfg.gridDim = dim3(2 * clusters);
+      e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, maps, k);
+    } else {
+      cfg.gridDim = dim3(k.num_tiles < num_sms() ? k.num_tiles : num_sms());
+      e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false>, maps, k);
+    }
     if (e != cudaSuccess) {
-      set_error("conv_igemm: pair launch failed: %s", cudaGetErrorString(e));
+      set_error("conv_igemm: launch failed: %s", cudaGetErrorString(e));
       return (int)e;
     }
-  } else {
-    int grid = k.num_tiles < num_sms() ? k.num_tiles : num_sms();
-    conv_igemm_kernel<false><<<grid, kNumThreads, smem, stream>>>(maps, k);
   }
   if (prof) profile_end(0, stream);
   count_launch();

@@ -83,6 +83,9 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
   if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // PDL: everything above overlapped the tail of the preceding kernel; both operands depend on it
+  griddep_wait();
+  griddep_launch();
 
   unsigned long long* dbg = (p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
   if (dbg && threadIdx.x == 0) {
@@ -264,6 +267,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int ntaps, int m_total, int n_total,
                                     int map_mode, int co, int ci, float scale, const float* __restrict__ inv_scale_dev,
                                     int accumulate, float* __restrict__ grad) {
+  griddep_wait();   // PDL: see launch_pdl
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)co * ci;
   if (idx >= total) return;
@@ -319,6 +323,7 @@ __global__ void __launch_bounds__(256)
 wgrad_reduce_rows_kernel(const float* __restrict__ part, int splits, int m_total, int n_total, int map_mode, int co,
                          int ci, float scale, const float* __restrict__ div_dev, int accumulate,
                          float* __restrict__ grad) {
+  griddep_wait();   // PDL: see launch_pdl
   extern __shared__ float row_s[];   // [ci][9]
   const int m = blockIdx.x;
   if (div_dev) scale /= __ldg(div_dev);
@@ -470,29 +475,41 @@ extern "C" int pesr_conv_wgrad(const pesr_wgrad_desc* d, int32_t* splits_out, vo
   }
   const bool prof = profiling_enabled();
   if (prof) profile_begin(1, 2.0 * d->nb * d->h * d->w * (double)d->m_total * d->n_total * d->ntaps, stream);
-  if (pair) {
-    int clusters = k.num_items < num_sms() / 2 ? k.num_items : num_sms() / 2;
+  {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * clusters);
     cfg.blockDim = dim3(kWgThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pair) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 2;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      na++;
+    }
+    if (pdl_enabled()) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      na++;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<true>, maps, k);
+    cfg.numAttrs = na;
+    cudaError_t e;
+    if (pair) {
+      const int clusters = k.num_items < num_sms() / 2 ? k.num_items : num_sms() / 2;
+      cfg.gridDim = dim3(2 * clusters);
+      e = cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<true>, maps, k);
+    } else {
+      cfg.gridDim = dim3(k.num_items < num_sms() ? k.num_items : num_sms());
+      e = cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<false>, maps, k);
+    }
     if (e != cudaSuccess) {
-      set_error("conv_wgrad: pair launch failed: %s", cudaGetErrorString(e));
+      set_error("conv_wgrad: launch failed: %s", cudaGetErrorString(e));
       return (int)e;
     }
-  } else {
-    int grid = k.num_items < num_sms() ? k.num_items : num_sms();
-    conv_wgrad_kernel<false><<<grid, kWgThreads, smem, stream>>>(maps, k);
   }
   if (prof) profile_end(1, stream);
   count_launch();
@@ -516,8 +533,8 @@ extern "C" int pesr_wgrad_reduce(const float* partials, int32_t splits, int32_t 
   if (map_mode == PESR_WMAP_COL_OUT)
     PESR_CHECK_ARG(ci <= m_total && 9 * co <= n_total && ntaps == 1, "wgrad_reduce: COL_OUT shape mismatch");
   if ((map_mode == PESR_WMAP_OIHW || map_mode == PESR_WMAP_OIHW_PS) && ntaps == 9 && ci * 9 * sizeof(float) <= 48 * 1024) {
-    wgrad_reduce_rows_kernel<<<co, 256, ci * 9 * sizeof(float), stream>>>(partials, splits, m_total, n_total, map_mode, co,
-                                                                         ci, scale, inv_scale_dev, accumulate, grad_oihw);
+    launch_pdl(wgrad_reduce_rows_kernel, co, 256, ci * 9 * sizeof(float), stream, partials, splits, m_total, n_total, map_mode,
+               co, ci, scale, inv_scale_dev, accumulate, grad_oihw);
     count_launch();
     PESR_CHECK_LAUNCH("wgrad_reduce");
     return 0;
@@ -525,7 +542,7 @@ extern "C" int pesr_wgrad_reduce(const float* partials, int32_t splits, int32_t 
   const long long total = (long long)co * ci;
   const int threads = 256;
   const int blocks = (int)((total + threads - 1) / threads);
-  wgrad_reduce_kernel<<<blocks, threads, 0, stream>>>(partials, splits, ntaps, m_total, n_total, map_mode, co, ci,
+  launch_pdl(wgrad_reduce_kernel, blocks, threads, 0, stream, partials, splits, ntaps, m_total, n_total, map_mode, co, ci,
                                                      scale, inv_scale_dev, accumulate, grad_oihw);
   count_launch();
   PESR_CHECK_LAUNCH("wgrad_reduce");

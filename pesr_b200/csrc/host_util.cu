@@ -1,4 +1,5 @@
 // Error reporting, launch counter, device query and the TMA tensor-map cache.
+#include <cstdlib>
 #include "host_util.cuh"
 
 #include <stdarg.h>
@@ -20,7 +21,24 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static int g_since_weight_write = 1 << 20;
+static int g_pdl = -1;
+void count_launch(int n) {
+  g_launches.fetch_add(n, std::memory_order_relaxed);
+  if (g_since_weight_write < (1 << 20)) g_since_weight_write += n;
+}
+// Packed weights are written by pack_weights / cast16 launches.  A PDL consumer may prefetch weights before its
+// dependency wait only if the writer is not its immediate predecessor in the stream (see conv_igemm.cu).
+void note_weight_write() { g_since_weight_write = 0; }
+bool weights_settled() { return g_since_weight_write >= 1; }
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("PESR_NO_PDL");
+    g_pdl = (e && e[0] == '1') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+void set_pdl(int on) { g_pdl = on; }
 
 int num_sms() {
   static int cached[64] = {0};

@@ -12,6 +12,10 @@ namespace pesr {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void note_weight_write();
+bool weights_settled();
+bool pdl_enabled();
+void set_pdl(int on);
 int num_sms();
 
 // Optional per-launch profiling of the tensor-core kernels (bench.py's roofline leg): when enabled, the
@@ -26,6 +30,26 @@ void profile_end(int kind, cudaStream_t stream);
 // Returns 0 or a PESR_E_* code.
 int get_tensor_map(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box);
+
+// Launch with programmatic stream serialization: the grid may become resident while its predecessor in the stream is
+// still draining, which hides the launch latency between the ~600 short dependent kernels of a training step.
+// EVERY kernel launched through this helper starts with griddep_wait() (common.cuh) before touching global memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 #define PESR_CHECK_ARG(cond, ...)      \
   do {                                 \

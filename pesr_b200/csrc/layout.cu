@@ -123,6 +123,7 @@ __device__ __forceinline__ float pack_fetch(const float* __restrict__ w, int co,
 __global__ void im2col3_kernel(const float* __restrict__ src, int nb, int h, int w, const float* __restrict__ aff_a,
                                const float* __restrict__ aff_b, const float* __restrict__ mul_dev, int sgn,
                                int pad_affine, int bf, uint4* __restrict__ col) {
+  griddep_wait();   // PDL: see launch_pdl
   const long long total = (long long)nb * h * w * 4;
   float A[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   float B[3] = {0, 0, 0};
@@ -183,6 +184,7 @@ __global__ void col2im3_kernel(const float* __restrict__ z, int ldz, int nb, int
                                const float* __restrict__ bias, const float* __restrict__ aff_a,
                                const float* __restrict__ aff_b, float mul, const float* __restrict__ div_dev, int sgn,
                                float* __restrict__ pre, float* __restrict__ out) {
+  griddep_wait();   // PDL: see launch_pdl
   const long long total = (long long)nb * h * w;
   const long long plane = (long long)h * w;
   float A[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -222,6 +224,7 @@ __global__ void col2im3_kernel(const float* __restrict__ z, int ldz, int nb, int
 // ------------------------------------------------------------------------------------------
 __global__ void nchw32_to_nhwc16_kernel(const float* __restrict__ src, int c, long long hw, int ldc,
                                         const float* __restrict__ mul_dev, int bf, uint16_t* __restrict__ dst) {
+  griddep_wait();   // PDL: see launch_pdl
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -242,6 +245,7 @@ __global__ void nchw32_to_nhwc16_kernel(const float* __restrict__ src, int c, lo
 
 __global__ void nhwc16_to_nchw32_kernel(const uint16_t* __restrict__ src, int c, long long hw, int ldc, float mul,
                                         const float* __restrict__ div_dev, int bf, float* __restrict__ dst) {
+  griddep_wait();   // PDL: see launch_pdl
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -266,6 +270,7 @@ __global__ void nhwc16_to_nchw32_kernel(const uint16_t* __restrict__ src, int c,
 // ------------------------------------------------------------------------------------------
 __global__ void colsum16_kernel(const uint16_t* __restrict__ x, long long npix, int c, int ldc, float mul,
                                 const float* __restrict__ div_dev, int bf, float* __restrict__ out) {
+  griddep_wait();   // PDL: see launch_pdl
   __shared__ float red[8][64];
   const int lane = threadIdx.x & 31;
   const int rowi = threadIdx.x >> 5;
@@ -295,6 +300,7 @@ __global__ void colsum16_kernel(const uint16_t* __restrict__ x, long long npix, 
 __global__ void __launch_bounds__(256)
 colsum16_vec_kernel(const uint4* __restrict__ x, long long npix, int c, int ldv, float mul,
                     const float* __restrict__ div_dev, int bf, float* __restrict__ out) {
+  griddep_wait();   // PDL: see launch_pdl
   __shared__ float red[2048];       // [row-in-pass][channel], rows-per-pass * c == 2048
   const int tpr = c >> 3, rpp = 256 / tpr;
   const int v = threadIdx.x % tpr, r = threadIdx.x / tpr;
@@ -322,6 +328,7 @@ colsum16_vec_kernel(const uint4* __restrict__ x, long long npix, int c, int ldv,
 // dynamic gradient scale
 // ------------------------------------------------------------------------------------------
 __global__ void amax_kernel(const float* __restrict__ x, long long n, unsigned int* __restrict__ ws) {
+  griddep_wait();   // PDL: see launch_pdl
   float m = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     m = fmaxf(m, fabsf(x[i]));
@@ -336,6 +343,7 @@ __global__ void amax_kernel(const float* __restrict__ x, long long n, unsigned i
   }
 }
 __global__ void amax_finalize_kernel(float* ws, float target) {
+  griddep_wait();   // PDL: see launch_pdl
   const float m = __uint_as_float(*reinterpret_cast<unsigned int*>(ws));
   float scale = 1.f;
   if (m > 0.f && isfinite(m)) {
@@ -355,6 +363,7 @@ __global__ void amax_finalize_kernel(float* ws, float target) {
 // ------------------------------------------------------------------------------------------
 __global__ void moments3_kernel(const float* __restrict__ a, const float* __restrict__ b, int nb, long long hw,
                                 float* __restrict__ sums) {
+  griddep_wait();   // PDL: see launch_pdl
   float acc[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) acc[i] = 0.f;
@@ -475,6 +484,7 @@ extern "C" int pesr_pack_weights(const float* w, int32_t co, int32_t ci, int32_t
   pack_weights_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(w, co, ci, taps, mode, pad_to, dtype,
                                                                   reinterpret_cast<uint16_t*>(out), total, rows, kdim);
   count_launch();
+  note_weight_write();
   PESR_CHECK_LAUNCH("pack_weights");
   return 0;
 }
@@ -519,6 +529,7 @@ extern "C" int pesr_pack_weights_multi(const int64_t* jobs_host, int32_t njobs, 
   }
   pack_weights_multi_kernel<<<nblocks, 256, 0, stream>>>(reinterpret_cast<const PackJob*>(jobs_dev), njobs, dtype);
   count_launch();
+  note_weight_write();
   PESR_CHECK_LAUNCH("pack_weights_multi");
   return 0;
 }
@@ -530,7 +541,7 @@ extern "C" int pesr_im2col3(const float* src, int32_t nb, int32_t h, int32_t w, 
   PESR_CHECK_ARG(src && col && nb > 0 && h > 0 && w > 0, "im2col3: bad arguments");
   PESR_CHECK_ARG(sgn == 1 || sgn == -1, "im2col3: sgn must be +-1");
   const long long total = (long long)nb * h * w * 4;
-  im2col3_kernel<<<blocks_for(total, 256, 148 * 32), 256, 0, stream>>>(src, nb, h, w, aff_a, aff_b, mul_dev, sgn,
+  launch_pdl(im2col3_kernel, blocks_for(total, 256, 148 * 32), 256, 0, stream, src, nb, h, w, aff_a, aff_b, mul_dev, sgn,
                                                                       pad_affine, dtype, reinterpret_cast<uint4*>(col));
   count_launch();
   PESR_CHECK_LAUNCH("im2col3");
@@ -544,7 +555,7 @@ extern "C" int pesr_col2im3(const float* z, int32_t ldz, int32_t nb, int32_t h, 
   PESR_CHECK_ARG(z && out && nb > 0 && h > 0 && w > 0 && ldz >= 27, "col2im3: bad arguments");
   PESR_CHECK_ARG(sgn == 1 || sgn == -1, "col2im3: sgn must be +-1");
   const long long total = (long long)nb * h * w;
-  col2im3_kernel<<<blocks_for(total, 256, 148 * 32), 256, 0, stream>>>(z, ldz, nb, h, w, bias, aff_a, aff_b, mul_host,
+  launch_pdl(col2im3_kernel, blocks_for(total, 256, 148 * 32), 256, 0, stream, z, ldz, nb, h, w, bias, aff_a, aff_b, mul_host,
                                                                       div_dev, sgn, pre, out);
   count_launch();
   PESR_CHECK_LAUNCH("col2im3");
@@ -558,7 +569,7 @@ extern "C" int pesr_nchw32_to_nhwc16(const float* src, int32_t nb, int32_t c, in
   PESR_CHECK_ARG(nb <= 65535, "nchw32_to_nhwc16: nb too large");
   const long long hw = (long long)h * w;
   dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((ldc + 31) / 32), (unsigned)nb);
-  nchw32_to_nhwc16_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, c, hw, ldc, mul_dev, dtype,
+  launch_pdl(nchw32_to_nhwc16_kernel, grid, dim3(32, 8), 0, stream, src, c, hw, ldc, mul_dev, dtype,
                                                            reinterpret_cast<uint16_t*>(dst));
   count_launch();
   PESR_CHECK_LAUNCH("nchw32_to_nhwc16");
@@ -572,7 +583,7 @@ extern "C" int pesr_nhwc16_to_nchw32(const void* src, int32_t nb, int32_t c, int
   PESR_CHECK_ARG(nb <= 65535, "nhwc16_to_nchw32: nb too large");
   const long long hw = (long long)h * w;
   dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)nb);
-  nhwc16_to_nchw32_kernel<<<grid, dim3(32, 8), 0, stream>>>(reinterpret_cast<const uint16_t*>(src), c, hw, ldc,
+  launch_pdl(nhwc16_to_nchw32_kernel, grid, dim3(32, 8), 0, stream, reinterpret_cast<const uint16_t*>(src), c, hw, ldc,
                                                            mul_host, div_dev, dtype, dst);
   count_launch();
   PESR_CHECK_LAUNCH("nhwc16_to_nchw32");
@@ -590,17 +601,19 @@ extern "C" int pesr_colsum16(const void* x, int64_t npix, int32_t c, int32_t ldc
   const int tpr = c / 8;
   if (c % 8 == 0 && ldc % 8 == 0 && tpr <= 256 && 256 % tpr == 0 && ((uintptr_t)x % 16) == 0) {
     const int rpp = 256 / tpr;
+    // measured (tools/perf_helpers.py): 16 rows per thread beats more, smaller blocks on the short inputs (the kernel
+    // is launch/tail-latency-bound there); the 8-blocks-per-SM cap matters on the long ones (85 -> 68 us at 302 MB)
     long long bx = (npix + (long long)rpp * 16 - 1) / ((long long)rpp * 16);
-    if (bx > 148 * 4) bx = 148 * 4;
+    if (bx > 148 * 8) bx = 148 * 8;
     if (bx < 1) bx = 1;
-    colsum16_vec_kernel<<<(unsigned)bx, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), npix, c, ldc / 8, mul_host,
+    launch_pdl(colsum16_vec_kernel, (unsigned)bx, 256, 0, stream, reinterpret_cast<const uint4*>(x), npix, c, ldc / 8, mul_host,
                                                          div_dev, dtype, out);
   } else {
     long long bx = (npix + 8 * 64 - 1) / (8 * 64);
     if (bx > 1024) bx = 1024;
     if (bx < 1) bx = 1;
     dim3 grid((unsigned)bx, (unsigned)((c + 63) / 64));
-    colsum16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(x), npix, c, ldc, mul_host, div_dev,
+    launch_pdl(colsum16_kernel, grid, 256, 0, stream, reinterpret_cast<const uint16_t*>(x), npix, c, ldc, mul_host, div_dev,
                                              dtype, out);
   }
   count_launch();
@@ -611,8 +624,8 @@ extern "C" int pesr_colsum16(const void* x, int64_t npix, int32_t c, int32_t ldc
 extern "C" int pesr_amax_scale(const float* x, int64_t n, float target, float* ws3, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PESR_CHECK_ARG(x && ws3 && n > 0 && target > 0.f, "amax_scale: bad arguments");
-  amax_kernel<<<blocks_for(n, 256, 148 * 4), 256, 0, stream>>>(x, n, reinterpret_cast<unsigned int*>(ws3));
-  amax_finalize_kernel<<<1, 1, 0, stream>>>(ws3, target);
+  launch_pdl(amax_kernel, blocks_for(n, 256, 148 * 4), 256, 0, stream, x, n, reinterpret_cast<unsigned int*>(ws3));
+  launch_pdl(amax_finalize_kernel, 1, 1, 0, stream, ws3, target);
   count_launch(2);
   PESR_CHECK_LAUNCH("amax_scale");
   return 0;
@@ -623,7 +636,7 @@ extern "C" int pesr_moments3(const float* a, const float* b, int32_t nb, int64_t
   PESR_CHECK_ARG(a && b && sums12 && nb > 0 && hw > 0, "moments3: bad arguments");
   cudaError_t e = cudaMemsetAsync(sums12, 0, sizeof(float) * 12, stream);
   if (e != cudaSuccess) { set_error("moments3: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
-  moments3_kernel<<<blocks_for((long long)nb * hw, 256, 148 * 4), 256, 0, stream>>>(a, b, nb, hw, sums12);
+  launch_pdl(moments3_kernel, blocks_for((long long)nb * hw, 256, 148 * 4), 256, 0, stream, a, b, nb, hw, sums12);
   count_launch();
   PESR_CHECK_LAUNCH("moments3");
   return 0;

@@ -18,6 +18,7 @@ namespace pesr {
 __global__ void bn_reduce_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y, long long npix, int c,
                                  const float* __restrict__ mean, const float* __restrict__ rstd, int mode, int bf,
                                  double* __restrict__ sums) {
+  griddep_wait();   // PDL: see launch_pdl
   __shared__ double red[2][8][64];
   const int lane = threadIdx.x & 31;
   const int rowi = threadIdx.x >> 5;
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(256)
 bn_reduce_vec_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, long long npix, int c,
                      const float* __restrict__ mean, const float* __restrict__ rstd, int mode, int bf,
                      double* __restrict__ sums) {
+  griddep_wait();   // PDL: see launch_pdl
   __shared__ double red[2][2048];   // [quantity][row-in-pass * c + channel], rows-per-pass * c == 2048
   const int tpr = c >> 3;           // threads per pixel row
   const int rpp = 256 / tpr;        // pixel rows per pass
@@ -123,6 +125,7 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, int c, double n, f
                                    float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ run_mean,
                                    float* __restrict__ run_var, long long* __restrict__ num_batches,
                                    const float* __restrict__ run_shift) {
+  griddep_wait();   // PDL: see launch_pdl
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < c) {
     const double m = sums[i] / n;
@@ -145,6 +148,7 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, int c, double n, f
 __global__ void bn_lrelu_fwd_kernel(const uint4* __restrict__ y, long long nvec, int c, const float* __restrict__ mean,
                                     const float* __restrict__ rstd, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, float slope, int bf, uint4* __restrict__ a) {
+  griddep_wait();   // PDL: see launch_pdl
   __shared__ float sc[512], sh[512];
   for (int i = threadIdx.x; i < c; i += blockDim.x) {
     const float k = gamma[i] * rstd[i];
@@ -179,6 +183,7 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* _
                                     const float* __restrict__ gamma, const double* __restrict__ sums, float gmul,
                                     const float* __restrict__ gdiv_dev, int bf, uint4* __restrict__ dy,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  griddep_wait();   // PDL: see launch_pdl
   __shared__ float ka[512], kb[512], kc[512];
   const int cv = c >> 3;
   if (blockIdx.x == 0 && dgamma) {
@@ -213,6 +218,7 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* _
 }
 
 __global__ void zero_doubles_kernel(double* p, int n) {
+  griddep_wait();   // PDL: see launch_pdl
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0;
 }
@@ -224,6 +230,7 @@ __global__ void zero_doubles_kernel(double* p, int n) {
 // ------------------------------------------------------------------------------------------
 __global__ void maxpool2_fwd_kernel(const uint4* __restrict__ x, int nb, int h, int w, int c, int bf,
                                     uint4* __restrict__ y) {
+  griddep_wait();   // PDL: see launch_pdl
   const int cv = c >> 3, ho = h >> 1, wo = w >> 1;
   const long long total = (long long)nb * ho * wo * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -253,6 +260,7 @@ __global__ void maxpool2_fwd_kernel(const uint4* __restrict__ x, int nb, int h, 
 
 __global__ void maxpool2_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, int nb, int h, int w,
                                     int c, int relu_mask, int bf, uint4* __restrict__ dx) {
+  griddep_wait();   // PDL: see launch_pdl
   const int cv = c >> 3, ho = h >> 1, wo = w >> 1;
   const long long total = (long long)nb * ho * wo * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -367,6 +375,7 @@ linear_fwd_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ w
 __global__ void linear_finalize_kernel(const float* __restrict__ part, int ksplit, int nb, int o,
                                        const float* __restrict__ bias, int act, int bf, float* __restrict__ out32,
                                        uint16_t* __restrict__ out16) {
+  griddep_wait();   // PDL: see launch_pdl
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nb * o) return;
   float s = bias ? bias[i % o] : 0.f;
@@ -482,6 +491,7 @@ __global__ void cast16_kernel(const float* __restrict__ src, long long n, int bf
 // dir 0: dst[n][c*hw + p] = src[n][p][c].
 // dir 1 (backward): dst[n][p][c] = cvt(src32[n][c*hw + p] * mul) * lrelu'(mask[n][p][c])  with src32 fp32.
 __global__ void flatten_nchw_kernel(const uint16_t* __restrict__ src, int nb, int hw, int c, uint16_t* __restrict__ dst) {
+  griddep_wait();   // PDL: see launch_pdl
   const long long total = (long long)nb * hw * c;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int p = (int)(i % hw);
@@ -493,6 +503,7 @@ __global__ void flatten_nchw_kernel(const uint16_t* __restrict__ src, int nb, in
 __global__ void unflatten_nchw_kernel(const float* __restrict__ src32, const uint16_t* __restrict__ mask, int nb, int hw,
                                       int c, float mul, const float* __restrict__ mul_dev, float slope, int bf,
                                       uint16_t* __restrict__ dst) {
+  griddep_wait();   // PDL: see launch_pdl
   const long long total = (long long)nb * hw * c;
   if (mul_dev) mul *= __ldg(mul_dev);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -523,14 +534,14 @@ static void launch_bn_reduce(const void* x16, const void* y16, long long npix, i
     long long bx = (npix + (long long)rpp * 8 - 1) / ((long long)rpp * 8);
     if (bx > 148 * 4) bx = 148 * 4;
     if (bx < 1) bx = 1;
-    bn_reduce_vec_kernel<<<(unsigned)bx, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x16),
+    launch_pdl(bn_reduce_vec_kernel, (unsigned)bx, 256, 0, stream, reinterpret_cast<const uint4*>(x16),
                                                           reinterpret_cast<const uint4*>(y16), npix, c, mean, rstd,
                                                           mode, dtype, sums_ws);
   } else {
     long long bx = (npix + 8 * 64 - 1) / (8 * 64);
     if (bx > 1184) bx = 1184;
     dim3 grid((unsigned)bx, (unsigned)((c + 63) / 64));
-    bn_reduce_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(x16),
+    launch_pdl(bn_reduce_kernel, grid, 256, 0, stream, reinterpret_cast<const uint16_t*>(x16),
                                               reinterpret_cast<const uint16_t*>(y16), npix, c, mean, rstd, mode, dtype,
                                               sums_ws);
   }
@@ -544,7 +555,7 @@ extern "C" int pesr_bn_stats(const void* y16, int64_t npix, int32_t c, float eps
   PESR_CHECK_ARG(y16 && sums_ws && mean && rstd && npix > 0 && c > 0 && c % 8 == 0, "bn_stats: bad arguments");
   PESR_CHECK_ARG(c <= 512, "bn_stats: at most 512 channels");
   launch_bn_reduce(y16, nullptr, npix, c, nullptr, nullptr, 0, dtype, sums_ws, stream);
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(sums_ws, c, (double)npix, eps, momentum, mean, rstd,
+  launch_pdl(bn_finalize_kernel, (c + 127) / 128, 128, 0, stream, sums_ws, c, (double)npix, eps, momentum, mean, rstd,
                                                          running_mean, running_var,
                                                          reinterpret_cast<long long*>(num_batches_tracked),
                                                          running_mean_shift);
@@ -560,7 +571,7 @@ extern "C" int pesr_bn_lrelu_fwd(const void* y16, int64_t npix, int32_t c, const
   PESR_CHECK_ARG(y16 && a16 && mean && rstd && gamma && beta && npix > 0 && c % 8 == 0 && c <= 512,
                  "bn_lrelu_fwd: bad arguments");
   const long long nvec = npix * (c / 8);
-  bn_lrelu_fwd_kernel<<<nblocks(nvec, 256, 148 * 16), 256, 0, stream>>>(reinterpret_cast<const uint4*>(y16), nvec, c, mean,
+  launch_pdl(bn_lrelu_fwd_kernel, nblocks(nvec, 256, 148 * 16), 256, 0, stream, reinterpret_cast<const uint4*>(y16), nvec, c, mean,
                                                                        rstd, gamma, beta, slope, dtype,
                                                                        reinterpret_cast<uint4*>(a16));
   count_launch();
@@ -578,10 +589,10 @@ extern "C" int pesr_bn_lrelu_bwd(const void* dz16, const void* y16, int64_t npix
   PESR_CHECK_ARG(c <= 512, "bn_lrelu_bwd: at most 512 channels");
   launch_bn_reduce(dz16, y16, npix, c, mean, rstd, 1, dtype, sums_ws, stream);
   const long long nvec = npix * (c / 8);
-  bn_bwd_apply_kernel<<<nblocks(nvec, 256, 148 * 16), 256, 0, stream>>>(
+  launch_pdl(bn_bwd_apply_kernel, nblocks(nvec, 256, 148 * 16), 256, 0, stream, 
       reinterpret_cast<const uint4*>(dz16), reinterpret_cast<const uint4*>(y16), nvec, c, (double)npix, mean, rstd, gamma,
       sums_ws, grad_mul, grad_div_dev, dtype, reinterpret_cast<uint4*>(dy16), dgamma, dbeta);
-  zero_doubles_kernel<<<(2 * c + 255) / 256, 256, 0, stream>>>(sums_ws, 2 * c);
+  launch_pdl(zero_doubles_kernel, (2 * c + 255) / 256, 256, 0, stream, sums_ws, 2 * c);
   count_launch(3);
   PESR_CHECK_LAUNCH("bn_lrelu_bwd");
   return 0;
@@ -592,7 +603,7 @@ extern "C" int pesr_maxpool2_fwd(const void* x16, int32_t nb, int32_t h, int32_t
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PESR_CHECK_ARG(x16 && y16 && nb > 0 && h >= 2 && w >= 2 && c % 8 == 0, "maxpool2_fwd: bad arguments");
   const long long total = (long long)nb * (h / 2) * (w / 2) * (c / 8);
-  maxpool2_fwd_kernel<<<nblocks(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x16), nb, h, w, c, dtype,
+  launch_pdl(maxpool2_fwd_kernel, nblocks(total, 256), 256, 0, stream, reinterpret_cast<const uint4*>(x16), nb, h, w, c, dtype,
                                                               reinterpret_cast<uint4*>(y16));
   count_launch();
   PESR_CHECK_LAUNCH("maxpool2_fwd");
@@ -604,7 +615,7 @@ extern "C" int pesr_maxpool2_bwd(const void* x16, const void* dy16, int32_t nb, 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PESR_CHECK_ARG(x16 && dy16 && dx16 && nb > 0 && h >= 2 && w >= 2 && c % 8 == 0, "maxpool2_bwd: bad arguments");
   const long long total = (long long)nb * (h / 2) * (w / 2) * (c / 8);
-  maxpool2_bwd_kernel<<<nblocks(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x16),
+  launch_pdl(maxpool2_bwd_kernel, nblocks(total, 256), 256, 0, stream, reinterpret_cast<const uint4*>(x16),
                                                               reinterpret_cast<const uint4*>(dy16), nb, h, w, c,
                                                               relu_mask, dtype, reinterpret_cast<uint4*>(dx16));
   count_launch();
@@ -636,7 +647,7 @@ extern "C" int pesr_linear_skinny_fwd(const void* x16, const void* w16, const fl
   dim3 grid((unsigned)((o + 7) / 8), (unsigned)ks);
   linear_fwd_kernel<16><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(x16),
                                                   reinterpret_cast<const uint16_t*>(w16), nb, k, o, ks, dtype, workspace);
-  linear_finalize_kernel<<<(nb * o + 255) / 256, 256, 0, stream>>>(workspace, ks, nb, o, bias, act, dtype, out32,
+  launch_pdl(linear_finalize_kernel, (nb * o + 255) / 256, 256, 0, stream, workspace, ks, nb, o, bias, act, dtype, out32,
                                                                   reinterpret_cast<uint16_t*>(out16));
   count_launch(2);
   PESR_CHECK_LAUNCH("linear_fwd");
@@ -647,7 +658,7 @@ extern "C" int pesr_linear_finalize(const float* partials, int32_t ksplit, int32
                                     int32_t act, int32_t dtype, float* out32, void* out16, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PESR_CHECK_ARG(partials && ksplit >= 1 && nb > 0 && o > 0 && (out32 || out16), "linear_finalize: bad arguments");
-  linear_finalize_kernel<<<(nb * o + 255) / 256, 256, 0, stream>>>(partials, ksplit, nb, o, bias, act, dtype, out32,
+  launch_pdl(linear_finalize_kernel, (nb * o + 255) / 256, 256, 0, stream, partials, ksplit, nb, o, bias, act, dtype, out32,
                                                                   reinterpret_cast<uint16_t*>(out16));
   count_launch();
   PESR_CHECK_LAUNCH("linear_finalize");
@@ -692,6 +703,7 @@ extern "C" int pesr_cast16(const float* src, int64_t n, int32_t dtype, void* dst
   PESR_CHECK_ARG(src && dst && n > 0, "cast16: bad arguments");
   cast16_kernel<<<nblocks((n + 1) / 2, 256), 256, 0, stream>>>(src, n, dtype, reinterpret_cast<uint16_t*>(dst));
   count_launch();
+  note_weight_write();   // cast16 produces the 16-bit Linear weights the FC igemm reads as its B operand
   PESR_CHECK_LAUNCH("cast16");
   return 0;
 }
@@ -699,7 +711,7 @@ extern "C" int pesr_cast16(const float* src, int64_t n, int32_t dtype, void* dst
 extern "C" int pesr_flatten_nchw16(const void* src_nhwc16, int32_t nb, int32_t hw, int32_t c, void* dst, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PESR_CHECK_ARG(src_nhwc16 && dst && nb > 0 && hw > 0 && c > 0, "flatten_nchw16: bad arguments");
-  flatten_nchw_kernel<<<nblocks((long long)nb * hw * c, 256), 256, 0, stream>>>(
+  launch_pdl(flatten_nchw_kernel, nblocks((long long)nb * hw * c, 256), 256, 0, stream, 
       reinterpret_cast<const uint16_t*>(src_nhwc16), nb, hw, c, reinterpret_cast<uint16_t*>(dst));
   count_launch();
   PESR_CHECK_LAUNCH("flatten_nchw16");
@@ -711,7 +723,7 @@ extern "C" int pesr_unflatten_nchw16(const float* src32_nchw, const void* mask_n
                                      void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PESR_CHECK_ARG(src32_nchw && dst_nhwc16 && nb > 0 && hw > 0 && c > 0, "unflatten_nchw16: bad arguments");
-  unflatten_nchw_kernel<<<nblocks((long long)nb * hw * c, 256), 256, 0, stream>>>(
+  launch_pdl(unflatten_nchw_kernel, nblocks((long long)nb * hw * c, 256), 256, 0, stream, 
       src32_nchw, reinterpret_cast<const uint16_t*>(mask_nhwc16), nb, hw, c, mul, mul_dev, slope, dtype,
       reinterpret_cast<uint16_t*>(dst_nhwc16));
   count_launch();

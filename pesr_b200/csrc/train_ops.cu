@@ -23,6 +23,7 @@ __device__ __forceinline__ float block_sum(float v, float* sm) {
 // mode 1: MSE mean (value = mean (a-b)^2, grad = 2(a-b)/n)
 __global__ void diff_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, int mode,
                                  float* __restrict__ loss, float* __restrict__ grad) {
+  griddep_wait();   // PDL: see launch_pdl
   __shared__ float sm[32];
   const float inv_n = 1.f / (float)n;
   float acc = 0.f;
@@ -67,6 +68,7 @@ __global__ void diff_loss_kernel(const float* __restrict__ a, const float* __res
 __device__ __forceinline__ float sgn(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
 __global__ void tv_loss_kernel(const float* __restrict__ y, long long planes, int h, int w, float* __restrict__ loss,
                                float* __restrict__ grad) {
+  griddep_wait();   // PDL: see launch_pdl
   __shared__ float sm[32];
   const long long total = planes * h * w;
   float acc = 0.f;
@@ -192,7 +194,7 @@ extern "C" int pesr_loss_l1(const float* a, const float* b, int64_t n, float* lo
   PESR_CHECK_ARG(((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && (!grad || (uintptr_t)grad % 16 == 0),
                  "loss_l1: pointers must be 16-byte aligned");
   cudaMemsetAsync(loss, 0, sizeof(float), stream);
-  diff_loss_kernel<<<grid_for(n, 256, 16, 148 * 8), 256, 0, stream>>>(a, b, n, 0, loss, grad);
+  launch_pdl(diff_loss_kernel, grid_for(n, 256, 16, 148 * 8), 256, 0, stream, a, b, n, 0, loss, grad);
   count_launch();
   PESR_CHECK_LAUNCH("loss_l1");
   return 0;
@@ -204,7 +206,7 @@ extern "C" int pesr_loss_mse(const float* a, const float* b, int64_t n, float* l
   PESR_CHECK_ARG(((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && (!grad || (uintptr_t)grad % 16 == 0),
                  "loss_mse: pointers must be 16-byte aligned");
   cudaMemsetAsync(loss, 0, sizeof(float), stream);
-  diff_loss_kernel<<<grid_for(n, 256, 16, 148 * 8), 256, 0, stream>>>(a, b, n, 1, loss, grad);
+  launch_pdl(diff_loss_kernel, grid_for(n, 256, 16, 148 * 8), 256, 0, stream, a, b, n, 1, loss, grad);
   count_launch();
   PESR_CHECK_LAUNCH("loss_mse");
   return 0;
@@ -215,7 +217,7 @@ extern "C" int pesr_loss_tv(const float* y, int64_t planes, int32_t h, int32_t w
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PESR_CHECK_ARG(y && loss && planes > 0 && h > 0 && w > 0, "loss_tv: bad arguments");
   cudaMemsetAsync(loss, 0, sizeof(float), stream);
-  tv_loss_kernel<<<grid_for(planes * h * w, 256, 8, 148 * 8), 256, 0, stream>>>(y, planes, h, w, loss, grad);
+  launch_pdl(tv_loss_kernel, grid_for(planes * h * w, 256, 8, 148 * 8), 256, 0, stream, y, planes, h, w, loss, grad);
   count_launch();
   PESR_CHECK_LAUNCH("loss_tv");
   return 0;

@@ -26,7 +26,9 @@ def _ptr(t):
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    # raw cudaStream_t of torch's current stream on the current device; the C call is ~20x cheaper than
+    # torch.cuda.current_stream() (which walks the Python device-index helpers) and this runs once per launch
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _need_cuda(*ts):

@@ -73,6 +73,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Whole-warp wait with a warp-uniform loop condition (vote): control flow after it stays provably convergent, so the
+// compiler keeps the loop state of the single-issuer warps (stage index, smem addresses, descriptors) in uniform
+// registers instead of converting it with R2UR before every TMA / MMA instruction.
+__device__ __forceinline__ void mbar_wait_w(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    if (++spins > (1u << 24)) {
+      printf("pesr_b200: mbarrier timeout (block %d warp %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x >> 5,
+             smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
 // Same, with cluster-scope acquire (the arrivals come from the peer CTA of a pair).
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;

@@ -67,7 +67,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role branches and the
+  // single-issuer loops on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int rank = kPair ? (int)cluster_ctarank() : 0;
   const bool leader = rank == 0;
@@ -210,7 +212,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
           const int ww = MODE == 2 ? w0 - 1 : w0 + p.tap_dw[tap];
           const int brow = MODE == 2 ? n0 : p.tap_widx[tap] * p.cout + n0;
           for (; inner < inner_end && s < s1; inner += inner_step, s++) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait_w(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
             uint64_t* fb = &full_bar[stage];
             const bool with_b = npre == 0;     // else: the weights of this step were issued in the prologue
@@ -261,7 +263,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
         if (dbg && lane == 0) dbg[8 + (tile == worker ? 0 : 4)] = clock64();    // MMA warp: accumulator free
         if (!kPair && p.sub_mode) {
           for (int st = 0; st < p.steps_per_tile; st++) {
-            mbar_wait(&full_bar[stage], phase);
+            mbar_wait_w(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
             const uint32_t b_addr = a_addr + p.a_bytes;
@@ -282,7 +284,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
           continue;
         }
         for (int kb = kb0; kb < kb1; kb++) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_w(&full_bar[stage], phase);
           tc_fence_after();
           if (dbg && lane == 0 && kb == kb0) dbg[9 + (tile == worker ? 0 : 4)] = clock64();  // first stage landed
           {

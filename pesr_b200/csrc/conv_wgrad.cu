@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgK p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler (see conv_igemm.cu)
   const int lane = threadIdx.x & 31;
   const int rank = kPair ? (int)cluster_ctarank() : 0;
   const bool leader = rank == 0;
@@ -124,12 +124,13 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
         patch_range(split, p0, p1);
         const CUtensorMap* mb = &maps.b[p.tap_src[tap]];
         const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+        // patch -> (img, th, tw), walked incrementally (the producer loop is latency-critical: no per-step divisions)
+        int tw = p0 % p.tiles_w;
+        int th = (p0 / p.tiles_w) % p.tiles_h;
+        int img = p0 / (p.tiles_w * p.tiles_h);
         for (int pt = p0; pt < p1; pt++) {
-          const int tw = pt % p.tiles_w;
-          const int th = (pt / p.tiles_w) % p.tiles_h;
-          const int img = pt / (p.tiles_w * p.tiles_h);
           const int h0 = th * p.tile_h, w0 = tw * p.tile_w;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_w(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
           uint8_t* sb = sa + p.a_boxes * kWgBoxBytes;
           if (kPair) {
@@ -137,18 +138,12 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
             if (leader) mbar_expect_tx_w(&full_bar[stage], 2u * (uint32_t)p.stage_bytes);
             tma2_load_5d_w(sa, &maps.a, &full_bar[stage], 0, w0, h0, img, mt * 2);
             tma2_load_5d_w(sb, mb, &full_bar[stage], 0, w0 + dw, h0 + dh, img, nt * (p.block_n / 64) + rank * p.b_boxes);
-          } else if (p.dbg_skip && (pt - p0) >= p.stages) {
-            // bring-up experiment: after the ring is warm skip the A (1), B (2) or all (3) loads
-            const bool la = !(p.dbg_skip & 1), lb = !(p.dbg_skip & 2);
-            const uint32_t bytes = (la ? p.a_boxes : 0) * kWgBoxBytes + (lb ? p.b_boxes : 0) * kWgBoxBytes;
-            if (bytes) mbar_expect_tx_w(&full_bar[stage], bytes); else if (lane == 0) mbar_arrive(&full_bar[stage]);
-            if (la) tma_load_5d_w(sa, &maps.a, &full_bar[stage], 0, w0, h0, img, mt * 2);
-            if (lb) tma_load_5d_w(sb, mb, &full_bar[stage], 0, w0 + dw, h0 + dh, img, nt * (p.block_n / 64));
           } else {
             mbar_expect_tx_w(&full_bar[stage], (uint32_t)p.stage_bytes);
             tma_load_5d_w(sa, &maps.a, &full_bar[stage], 0, w0, h0, img, mt * 2);
             tma_load_5d_w(sb, mb, &full_bar[stage], 0, w0 + dw, h0 + dh, img, nt * (p.block_n / 64));
           }
+          if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; img++; } }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -167,7 +162,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kWgAccStride);
       for (int pt = p0; pt < p1; pt++) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait_w(&full_bar[stage], phase);
         tc_fence_after();
         if (dbg && lane == 0 && pt == p0) dbg[9] = clock64();
         if (dbg && lane == 0 && pt == p0 + 8) dbg[11] = clock64();

@@ -80,6 +80,11 @@ struct MapKey {
 
 int get_tensor_map(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box) {
+  return get_tensor_map_ex(out, base, dtype, 3, rank, dims, strides_bytes, box);
+}
+
+int get_tensor_map_ex(CUtensorMap* out, const void* base, int elem, int swizzle, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box) {
   static std::mutex mu;
   static std::map<MapKey, CUtensorMap> cache;
   int dev = 0;
@@ -87,7 +92,7 @@ int get_tensor_map(CUtensorMap* out, const void* base, int dtype, int rank, cons
   MapKey k;
   memset(&k, 0, sizeof(k));
   k.v[0] = (uint64_t)(uintptr_t)base;
-  k.v[1] = ((uint64_t)dtype << 8) | (uint64_t)rank | ((uint64_t)dev << 16);
+  k.v[1] = ((uint64_t)elem << 8) | (uint64_t)rank | ((uint64_t)dev << 16) | ((uint64_t)swizzle << 32);
   for (int i = 0; i < rank; i++) k.v[2 + i] = dims[i];
   for (int i = 0; i < rank - 1; i++) k.v[8 + i] = strides_bytes[i];
   for (int i = 0; i < rank; i++) k.v[14 + i] = box[i];
@@ -115,9 +120,12 @@ int get_tensor_map(CUtensorMap* out, const void* base, int dtype, int rank, cons
   }
   for (int i = 0; i < rank - 1; i++) gstr[i] = strides_bytes[i];
   CUtensorMap m;
-  CUresult r = fn(&m, dtype == PESR_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
-                  (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType et = elem == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : elem == PESR_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = swizzle == 3 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                              : swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(&m, et, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d): base %p rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]",
               (int)r, base, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),

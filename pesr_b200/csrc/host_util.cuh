@@ -30,6 +30,10 @@ void profile_end(int kind, cudaStream_t stream);
 // Returns 0 or a PESR_E_* code.
 int get_tensor_map(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box);
+// Same with the element type (PESR_DT_F16 / PESR_DT_BF16 / 2 = fp32) and the swizzle (0 none, 1 32B, 2 64B, 3 128B)
+// spelled out: used for the TMA-store maps of the staged epilogue.
+int get_tensor_map_ex(CUtensorMap* out, const void* base, int elem, int swizzle, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box);
 
 // Launch with programmatic stream serialization: the grid may become resident while its predecessor in the stream is
 // still draining, which hides the launch latency between the ~600 short dependent kernels of a training step.

@@ -168,6 +168,38 @@ if __name__ == "__main__":
                   f"CTA duration min/median/max {durs[0]:.1f}/{durs[len(durs)//2]:.1f}/{durs[-1]:.1f} us")
         lib.pesr_debug_timeline(0)
         lib.pesr_debug_pair_mode(1)
+    if what == "epi":      # chunk-level timeline of the LAST tile's epilogue of block 0 (trunk conv, light and heavy epilogue)
+        from pesr_b200._lib import lib
+        buf = torch.zeros(64 + 2 * 160, dtype=torch.int64, device="cuda")
+        lib.pesr_debug_timeline(buf.data_ptr())
+        nb, c, h, w = 16, 256, 48, 48
+        x16 = torch.randn(nb, h, w, c, device="cuda").half()
+        wp = (torch.randn(9 * c, c, device="cuda") / (3 * c ** 0.5)).half()
+        out16 = torch.empty(nb, h, w, c, device="cuda", dtype=torch.float16)
+        res32 = torch.randn(nb, h, w, c, device="cuda")
+        out32 = torch.empty(nb, h, w, c, device="cuda")
+        bias = torch.randn(c, device="cuda")
+        variants = {
+            "out16 + bias + relu": dict(bias=bias, act=1, out16=out16, ld_out16=c),
+            "res32 -> out32 + out16": dict(bias=bias, alpha=0.1, res32=res32, ld_res32=c, out32=out32, ld_out32=c, out16=out16, ld_out16=c),
+            "mask16 -> out16": dict(mask16=x16, ld_mask16=c, mask_mode=1, out16=out16, ld_out16=c),
+        }
+        for label, light, staged in (("specialised+staged", 501, 401), ("specialised direct", 501, 400), ("generic", 500, 400)):
+            lib.pesr_debug_pair_mode(light)
+            lib.pesr_debug_pair_mode(staged)
+            for name, epi in variants.items():
+                d = ops.make_conv_desc(dtype=0, nb=nb, h=h, w=w, cin=c, cout=c, srcs=[ops.nhwc_src(x16, nb, h, w, c)], wpacked=wp, **epi)
+                for flush in (True, False):
+                    ms = timeit(lambda: ops.conv_igemm(d), flush=flush)
+                    torch.cuda.synchronize()
+                    b = buf.cpu().tolist()
+                    t0 = b[0]
+                    print(f"{label:18s} {name:24s} flush={int(flush)}: {ms*1e3:.1f} us | tile0: acc complete {b[16]-t0}, epi done {b[17]-t0} | "
+                          f"last tile: acc complete {b[20]-t0}, chunks done at "
+                          + " ".join(f"+{b[25+i]-b[20]}" for i in range(8)) + f" | end {b[61]-t0}", flush=True)
+        lib.pesr_debug_timeline(0)
+        lib.pesr_debug_pair_mode(401)
+        lib.pesr_debug_pair_mode(501)
     if what == "timeline":
         from pesr_b200._lib import lib
         buf = torch.zeros(64, dtype=torch.int64, device="cuda")

@@ -157,6 +157,16 @@ int pesr_conv_wgrad(const pesr_wgrad_desc* d, int32_t* splits_out, void* stream)
 int pesr_wgrad_reduce(const float* partials, int32_t splits, int32_t ntaps, int32_t m_total, int32_t n_total,
                       int32_t map_mode, int32_t co, int32_t ci, float scale, const float* div_dev,
                       int32_t accumulate, float* grad_oihw, void* stream);
+
+/* pesr_wgrad_reduce for a 3x3 OIHW / OIHW_PS gradient fused with the bias gradient of the same layer (the column sums
+ * of dY, pesr_colsum16) in one launch: autograd's bias term of cuDNN backward-filter (model/basic.py:4-7).
+ * bias_grad must be zero on entry and receives bias_mul / *inv_scale_dev * sum_pixels dY; zero_next (may be NULL) is a
+ * buffer of zero_n floats that the call clears for the NEXT call of a chain to accumulate into. */
+int pesr_wgrad_reduce_bias(const float* partials, int32_t splits, int32_t ntaps, int32_t m_total, int32_t n_total,
+                           int32_t map_mode, int32_t co, int32_t ci, float scale, const float* inv_scale_dev,
+                           int32_t accumulate, float* grad_oihw, const void* dy16, int64_t npix, int32_t c, int32_t ldc,
+                           float bias_mul, int32_t dtype, float* bias_grad, float* zero_next, int32_t zero_n,
+                           void* stream);
 /* Bring-up hook: override the MN-major smem descriptor strides of pesr_conv_wgrad (0 = built-in). */
 void pesr_debug_wgrad_desc(int lbo_bytes, int sbo_bytes);
 void pesr_debug_wgrad_timeline(void* buf);   /* like pesr_debug_timeline, for pesr_conv_wgrad */

@@ -95,6 +95,8 @@ SIGNATURES = {
     "pesr_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), C.POINTER(_i32), _vp]),
     "pesr_debug_wgrad_desc": (None, [C.c_int, C.c_int]),
     "pesr_wgrad_reduce": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp, _vp]),
+    "pesr_wgrad_reduce_bias": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp,
+                                         _vp, _i64, _i32, _i32, _f32, _i32, _vp, _vp, _i32, _vp]),
     "pesr_pack_weights": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "pesr_pack_weights_multi": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp]),
     "pesr_im2col3": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),

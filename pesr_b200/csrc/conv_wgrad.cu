@@ -346,6 +346,73 @@ wgrad_reduce_rows_kernel(const float* __restrict__ part, int splits, int m_total
   for (int i = threadIdx.x; i < ci * 9; i += blockDim.x) g[i] = accumulate ? g[i] + row_s[i] : row_s[i];
 }
 
+// Split-K reduction of a 3x3 weight gradient AND the bias gradient (column sums of dY) in one launch: both are short,
+// latency-bound kernels that follow every wgrad launch, so they run side by side as one grid.  Blocks [0, co) reduce one
+// output-channel row each (as wgrad_reduce_rows_kernel); the remaining blocks column-sum dY (as colsum16_vec_kernel)
+// into a PRE-ZEROED bias gradient.  Block 0 also zeroes `zero_next`, the bias gradient the NEXT call accumulates into.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_bias_kernel(const float* __restrict__ part, int splits, int m_total, int n_total, int map_mode, int co, int ci,
+                         float scale, const float* __restrict__ div_dev, int accumulate, float* __restrict__ grad,
+                         const uint4* __restrict__ x, long long npix, int c, int ldv, float bmul, int bf,
+                         float* __restrict__ bias_out, float* __restrict__ zero_next, int zero_n) {
+  griddep_wait();   // PDL: see launch_pdl
+  extern __shared__ float row_s[];   // [ci][9]
+  __shared__ float red[2048];
+  float inv = 1.f;
+  if (div_dev) inv = 1.f / __ldg(div_dev);
+  if ((int)blockIdx.x < co) {
+    const int m = blockIdx.x;
+    scale *= inv;
+    if (m == 0 && zero_next)
+      for (int i = threadIdx.x; i < zero_n; i += blockDim.x) zero_next[i] = 0.f;
+    const long long tap_stride = (long long)m_total * n_total;
+    const long long split_stride = tap_stride * 9;
+    for (int n = threadIdx.x; n < ci; n += blockDim.x) {
+      float s[9];
+#pragma unroll
+      for (int t = 0; t < 9; t++) s[t] = 0.f;
+      const float* src = part + (long long)m * n_total + n;
+      for (int k = 0; k < splits; k++) {
+#pragma unroll
+        for (int t = 0; t < 9; t++) s[t] += src[k * split_stride + t * tap_stride];
+      }
+#pragma unroll
+      for (int t = 0; t < 9; t++) row_s[n * 9 + t] = s[t] * scale;
+    }
+    __syncthreads();
+    int o = m;
+    if (map_mode == PESR_WMAP_OIHW_PS) {
+      const int c_ps = co / 4;
+      o = (m % c_ps) * 4 + (m / c_ps);
+    }
+    float* g = grad + (long long)o * ci * 9;
+    for (int i = threadIdx.x; i < ci * 9; i += blockDim.x) g[i] = accumulate ? g[i] + row_s[i] : row_s[i];
+    return;
+  }
+  // ---- bias gradient: column sums of dY over this block's pixel rows
+  const int bid = blockIdx.x - co, nblk = gridDim.x - co;
+  const int tpr = c >> 3, rpp = 256 / tpr;
+  const int v = threadIdx.x % tpr, r = threadIdx.x / tpr;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) acc[j] = 0.f;
+  for (long long px = (long long)bid * rpp + r; px < npix; px += (long long)nblk * rpp) {
+    const uint4 u = x[px * ldv + v];
+    const float2 a = unpack2(u.x, bf), b = unpack2(u.y, bf), cc = unpack2(u.z, bf), d = unpack2(u.w, bf);
+    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+    acc[4] += cc.x; acc[5] += cc.y; acc[6] += d.x; acc[7] += d.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) red[r * c + v * 8 + j] = acc[j];
+  __syncthreads();
+  bmul *= inv;
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
+    float t = 0.f;
+    for (int k = 0; k < rpp; k++) t += red[k * c + ch];
+    atomicAdd(bias_out + ch, t * bmul);
+  }
+}
+
 static int g_dbg_lbo = 0, g_dbg_sbo = 0;
 static int g_wg_pair = 1;
 static unsigned long long* g_wg_dbg = nullptr;
@@ -541,5 +608,32 @@ extern "C" int pesr_wgrad_reduce(const float* partials, int32_t splits, int32_t 
                                                      scale, inv_scale_dev, accumulate, grad_oihw);
   count_launch();
   PESR_CHECK_LAUNCH("wgrad_reduce");
+  return 0;
+}
+
+extern "C" int pesr_wgrad_reduce_bias(const float* partials, int32_t splits, int32_t ntaps, int32_t m_total,
+                                      int32_t n_total, int32_t map_mode, int32_t co, int32_t ci, float scale,
+                                      const float* inv_scale_dev, int32_t accumulate, float* grad_oihw, const void* dy16,
+                                      int64_t npix, int32_t c, int32_t ldc, float bias_mul, int32_t dtype,
+                                      float* bias_grad, float* zero_next, int32_t zero_n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(partials && grad_oihw && dy16 && bias_grad, "wgrad_reduce_bias: null pointer");
+  PESR_CHECK_ARG(splits >= 1 && ntaps == 9 && (map_mode == PESR_WMAP_OIHW || map_mode == PESR_WMAP_OIHW_PS),
+                 "wgrad_reduce_bias: 3x3 OIHW gradients only (ntaps %d, map %d)", ntaps, map_mode);
+  PESR_CHECK_ARG(co <= m_total && ci <= n_total && ci * 9 * sizeof(float) <= 40 * 1024,
+                 "wgrad_reduce_bias: %dx%d does not fit partial %dx%d", co, ci, m_total, n_total);
+  const int tpr = c / 8;
+  PESR_CHECK_ARG(npix > 0 && c > 0 && c % 8 == 0 && ldc % 8 == 0 && tpr <= 256 && 256 % tpr == 0 &&
+                     ((uintptr_t)dy16 % 16) == 0,
+                 "wgrad_reduce_bias: dY must be 16-byte aligned with c in {8,16,...,2048} dividing 2048 (c %d, ldc %d)", c, ldc);
+  const int rpp = 256 / tpr;
+  long long bx = (npix + (long long)rpp * 16 - 1) / ((long long)rpp * 16);
+  if (bx > 148 * 4) bx = 148 * 4;
+  if (bx < 1) bx = 1;
+  launch_pdl(wgrad_reduce_bias_kernel, co + (unsigned)bx, 256, ci * 9 * sizeof(float), stream, partials, splits, m_total,
+             n_total, map_mode, co, ci, scale, inv_scale_dev, accumulate, grad_oihw, reinterpret_cast<const uint4*>(dy16),
+             (long long)npix, c, ldc / 8, bias_mul, dtype, bias_grad, zero_next, zero_n);
+  count_launch();
+  PESR_CHECK_LAUNCH("wgrad_reduce_bias");
   return 0;
 }

@@ -20,6 +20,8 @@ re-packs changed weights and issues the launches.
 """
 import ctypes as C
 
+import os
+
 import torch
 
 from . import ops
@@ -61,6 +63,9 @@ class _Plan:
 
 def _run_conv(desc, stream):
     check(lib.pesr_conv_igemm(C.byref(desc), stream), "pesr_conv_igemm")
+
+
+_FUSE_BIAS = os.environ.get("PESR_NO_FUSED_BIAS") != "1"    # A/B knob (tools/ab_env.sh)
 
 
 class GeneratorEngine:
@@ -258,7 +263,25 @@ class GeneratorEngine:
         wgrad(pl.dF0, Cn, Cn, pl.col_in, 64, 64, h, w, g.embed.weight, ops.WMAP_COL_IN, Cn, 3, taps=[(0, 0)])
         conv(h=h, w=w, cin=Cn, cout=32, taps=[(0, 0)], srcs=src(pl.dF0, h, w, Cn), wpacked=pk["embed_d"].buf,
              out32=pl.Zd, ld_out32=32)
-        pl.bwd = b
+        # a bias gradient (column sums of dY) followed by the 3x3 weight gradient of the same layer runs as ONE launch
+        # (pesr_wgrad_reduce_bias); each fused call also zeroes the bias gradient the next one accumulates into
+        fused, i = [], 0
+        while i < len(b):
+            op = b[i]
+            nxt = b[i + 1] if i + 1 < len(b) else None
+            if (_FUSE_BIAS and op[0] == "bias" and nxt is not None and nxt[0] == "wgrad" and op[1][5] == 0 and nxt[2][0] == 9
+                    and nxt[2][3] in (ops.WMAP_OIHW, ops.WMAP_OIHW_PS) and op[1][2] % 8 == 0 and op[1][3] % 8 == 0
+                    and 256 % (op[1][2] // 8) == 0 and nxt[2][5] * 36 <= 40 * 1024):
+                fused.append(["wgrad_bias", nxt[1], nxt[2], nxt[3], op[1], op[2], None])
+                i += 2
+            else:
+                fused.append(op)
+                i += 1
+        chain = [op for op in fused if op[0] == "wgrad_bias"]
+        for k in range(len(chain) - 1):
+            chain[k][6] = chain[k + 1][5]          # the bias parameter whose gradient this call zeroes for the next
+        pl.first_fused_bias = chain[0][5] if chain else None
+        pl.bwd = fused
         pl.scale = scale
         self.plans[key] = pl
         return pl
@@ -333,6 +356,8 @@ class GeneratorEngine:
         ops.amax_scale(dsr, ws, target=16.0)
         ops.im2col3(dsr, pl.dcol, affine_a=am_wt, mul_dev=scale, sgn=-1)
         splits_out = C.c_int32(0)
+        if pl.first_fused_bias is not None:
+            grads[pl.first_fused_bias].zero_()
         for op in pl.bwd:
             kind = op[0]
             if kind == "conv":
@@ -343,6 +368,15 @@ class GeneratorEngine:
                 check(lib.pesr_wgrad_reduce(pl.wg.data_ptr(), splits_out.value, ntaps, m_total, n_total, map_mode, co,
                                             ci, mul, scale.data_ptr(), 0, grads[param].data_ptr(), stream),
                       "pesr_wgrad_reduce")
+            elif kind == "wgrad_bias":
+                _, d, (ntaps, m_total, n_total, map_mode, co, ci, mul), param, (x16, npix, c, ldc, bmul, _p), bparam, znext = op
+                check(lib.pesr_conv_wgrad(C.byref(d), C.byref(splits_out), stream), "pesr_conv_wgrad")
+                zn = grads[znext] if znext is not None else None
+                check(lib.pesr_wgrad_reduce_bias(pl.wg.data_ptr(), splits_out.value, ntaps, m_total, n_total, map_mode, co,
+                                                 ci, mul, scale.data_ptr(), 0, grads[param].data_ptr(), x16.data_ptr(),
+                                                 npix, c, ldc, bmul, self.dt, grads[bparam].data_ptr(),
+                                                 zn.data_ptr() if zn is not None else 0, zn.numel() if zn is not None else 0,
+                                                 stream), "pesr_wgrad_reduce_bias")
             elif kind == "bias":
                 _, (x16, npix, c, ldc, mul, perm_c), param = op
                 if perm_c:

@@ -77,12 +77,13 @@ struct ConvK {
 //   2 mask     : (bias) * relu'/lrelu' mask of a saved 16-bit activation -> 16-bit output      (backward-data)
 //   3 residual : alpha * (acc + bias) + fp32 residual -> fp32 output + 16-bit copy              (residual stream)
 //   4          : 3 with coalesced global accesses, transposed through shared memory (CTA-pair kernel only)
+//   5, 6       : 1 with the PixelShuffle(2) / un-shuffle output addressing (upsampler forward / backward-data)
 template <bool kPair, int kEpi>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvK p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr bool kStaged = kEpi >= 4;
+  constexpr bool kStaged = kEpi == 4;
   constexpr bool kCtRes32 = kEpi == 3 || kEpi == 4, kCtMask = kEpi == 2;
   const bool has_res32 = kEpi ? kCtRes32 : p.res32 != nullptr;
   const bool has_out32 = kEpi ? kCtRes32 : p.out32 != nullptr;
@@ -493,8 +494,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     const uint16_t* const e_mask16 = has_mask ? p.mask16 : nullptr;
     float* const e_out32 = has_out32 ? p.out32 : nullptr;
     uint16_t* const e_out16 = has_out16 ? p.out16 : nullptr;
-    const int e_out_mode = kEpi ? (int)PESR_OUT_NORMAL : p.out_mode;
-    const int e_aux = kEpi ? 0 : p.aux_mode;
+    const int e_out_mode = kEpi == 5 ? (int)PESR_OUT_SHUFFLE2 : kEpi == 6 ? (int)PESR_OUT_UNSHUFFLE2
+                         : kEpi ? (int)PESR_OUT_NORMAL : p.out_mode;
+    const int e_aux = p.aux_mode;     // only changes the per-tile pixel index: stays a run-time value
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const int et = threadIdx.x - 64;  // 0..127
@@ -777,17 +779,22 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
 
   // staged epilogue (pair kernel): plain NHWC outputs on the GEMM's own pixel grid
   // epilogue specialisation (kEpi of the kernel template)
-  const bool plain_out = d->out_mode == PESR_OUT_NORMAL && !d->aux_mode && d->ksplit <= 1 && !d->res16 && d->out16 &&
-                         (d->out_h <= 0 || d->out_h == d->h) && (d->out_w <= 0 || d->out_w == d->w) && d->out_sy <= 1 &&
-                         d->out_sx <= 1 && d->out_oy == 0 && d->out_ox == 0;
+  const bool gemm_grid = !d->aux_mode && (d->out_h <= 0 || d->out_h == d->h) && (d->out_w <= 0 || d->out_w == d->w) &&
+                         d->out_sy <= 1 && d->out_sx <= 1 && d->out_oy == 0 && d->out_ox == 0;
+  const bool plain = d->ksplit <= 1 && !d->res16 && d->out16;
   int epi = 0;
-  if (g_light_enabled && plain_out) {
-    if (!d->res32 && !d->mask16 && !d->out32) epi = 1;
-    else if (d->mask16 && !d->res32 && !d->out32) epi = 2;
-    else if (d->res32 && d->out32 && !d->mask16) epi = 3;
+  if (g_light_enabled && plain) {
+    const bool light = !d->res32 && !d->mask16 && !d->out32;
+    if (d->out_mode == PESR_OUT_NORMAL) {
+      if (light) epi = 1;
+      else if (d->mask16 && !d->res32 && !d->out32) epi = 2;
+      else if (d->res32 && d->out32 && !d->mask16) epi = 3;
+    } else if (light && !d->aux_mode) {
+      epi = d->out_mode == PESR_OUT_SHUFFLE2 ? 5 : 6;
+    }
   }
-  // staged epilogue (pair kernel): coalesced residual / mask reads and TMA stores through shared memory
-  const bool staged = pair && epi == 3 && g_staged_enabled && 32 % d->tile_w == 0 && d->ld_out16 % 8 == 0 &&
+  // residual epilogue through shared memory (pair kernel, outputs on the GEMM's own pixel grid)
+  const bool staged = pair && epi == 3 && gemm_grid && g_staged_enabled && 32 % d->tile_w == 0 && d->ld_out16 % 8 == 0 &&
                       d->ld_out32 % 4 == 0 && d->ld_res32 % 4 == 0 && (long long)d->nb * d->h * d->w < (1ll << 31);
   if (staged) epi = 4;
 
@@ -910,15 +917,15 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
   if (smem < 120 * 1024) smem = 120 * 1024;
   // kernel variant: CTA pair x epilogue specialisation (see the template comment)
   typedef void (*KernelFn)(const ConvMaps, const ConvK);
-  static const KernelFn kernels[2][6] = {
+  static const KernelFn kernels[2][7] = {
       {conv_igemm_kernel<false, 0>, conv_igemm_kernel<false, 1>, conv_igemm_kernel<false, 2>, conv_igemm_kernel<false, 3>,
-       nullptr, nullptr},
+       nullptr, conv_igemm_kernel<false, 5>, conv_igemm_kernel<false, 6>},
       {conv_igemm_kernel<true, 0>, conv_igemm_kernel<true, 1>, conv_igemm_kernel<true, 2>, conv_igemm_kernel<true, 3>,
-       conv_igemm_kernel<true, 4>, nullptr}};
+       conv_igemm_kernel<true, 4>, conv_igemm_kernel<true, 5>, conv_igemm_kernel<true, 6>}};
   static bool attr_set = false;
   if (!attr_set) {
     for (int a = 0; a < 2; a++)
-      for (int b = 0; b < 6; b++) {
+      for (int b = 0; b < 7; b++) {
         if (!kernels[a][b]) continue;
         cudaError_t e = cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {

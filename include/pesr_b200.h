@@ -110,6 +110,10 @@ typedef struct pesr_conv_desc {
   int32_t ksplit;           /* > 1: split K across CTAs; raw fp32 partials go to out32 + split*split_stride32 */
   int32_t b_mn_major;       /* 1: wpacked is [K = cin][N = cout] (N contiguous), one tap: y = x * W without a transpose */
   int64_t split_stride32;   /* elements between the partial outputs of successive K splits */
+  double* bn_sums;          /* optional, light epilogue only (16-bit NHWC output, no residual / mask): 2*cout doubles that
+                               receive += sum and += sum of squares of the ROUNDED 16-bit outputs per channel - the
+                               train-mode BatchNorm statistics of model/basic.py:29 without a second pass over y
+                               (close with pesr_bn_stats(y16 = NULL, ...)) */
 } pesr_conv_desc;
 
 int pesr_conv_igemm(const pesr_conv_desc* d, void* stream);
@@ -273,7 +277,8 @@ int pesr_adam_multi(const int64_t* table_dev, int32_t nchunks, float lr, float b
  * 16-bit NHWC tensor y[npix][c]; updates running_mean / running_var (unbiased) with `momentum` and increments
  * num_batches_tracked when given.  running_mean_shift (optional, per channel) is added to the batch mean in the
  * running_mean update only (y was produced from a constant-shifted input).  sums_ws: 2*c doubles, zero on entry,
- * zero again on exit. */
+ * zero again on exit.  y16 == NULL: the sums were already accumulated by the producing convolution
+ * (pesr_conv_desc.bn_sums); only the finalisation runs. */
 int pesr_bn_stats(const void* y16, int64_t npix, int32_t c, float eps, float momentum, double* sums_ws, float* mean,
                   float* rstd, float* running_mean, float* running_var, int64_t* num_batches_tracked,
                   const float* running_mean_shift, int32_t dtype, void* stream);

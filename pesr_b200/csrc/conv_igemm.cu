@@ -34,6 +34,9 @@ struct ConvMaps {
 // Residual epilogue through shared memory (kEpi 4): per epilogue warp a ring of kEpiDepth 4 KB fp32 tiles (32 pixels x
 // 32 channels; the residual of the next chunks lands there by cp.async while the current one is processed) and one
 // 2 KB 16-bit transposition tile.
+// BatchNorm-statistics epilogue (kEpi 7): per epilogue warp one 4 KB fp32 transposition tile, then 2 x 512 floats of
+// per-CTA channel sums / sums of squares.
+constexpr int kBnEpiBytes = 4 * 4096 + 2 * 512 * 4;
 constexpr int kEpiDepth = 3;
 constexpr int kEpiWarpBytes = kEpiDepth * 4096 + 2048;
 constexpr int kEpiBytes = 4 * kEpiWarpBytes;
@@ -55,6 +58,7 @@ struct ConvK {
   uint16_t* out16; int ld_out16;
   int out_mode, out_h, out_w, out_sy, out_sx, out_oy, out_ox, out_coff, ps_c, aux_mode;
   int ksplit, b_mn_major, mn_tiles, pdl_early_b;
+  double* bn_sums;   // kEpi 7: [2][cout] global accumulators
   int staged;   // 1: epilogue through shared memory with coalesced loads and TMA stores (see the epilogue warps)
   // several K sub-blocks per pipeline stage, staged by ONE activation box + ONE weight box (TMA op count bounds the
   // small-N layers): sub_mode 1 = nsub consecutive 64-channel chunks of one tap, 2 = the three vertical taps of one
@@ -78,6 +82,7 @@ struct ConvK {
 //   3 residual : alpha * (acc + bias) + fp32 residual -> fp32 output + 16-bit copy              (residual stream)
 //   4          : 3 with coalesced global accesses, transposed through shared memory (CTA-pair kernel only)
 //   5, 6       : 1 with the PixelShuffle(2) / un-shuffle output addressing (upsampler forward / backward-data)
+//   7          : 1 plus per-channel sum / sum of squares of the rounded outputs (train-mode BatchNorm statistics)
 template <bool kPair, int kEpi>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvK p) {
@@ -102,7 +107,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
   const int b_rows = kPair ? p.block_n / 2 : p.block_n;                      // weight rows staged by this CTA
 
   uint8_t* epi_base = smem + (size_t)p.stages * p.stage_bytes;            // staging tiles of the staged epilogue
-  uint8_t* tail = epi_base + (kStaged ? kEpiBytes : 0);
+  uint8_t* tail = epi_base + (kStaged ? kEpiBytes : kEpi == 7 ? kBnEpiBytes : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full = empty_bar + kMaxStages;
@@ -497,6 +502,12 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     const int e_out_mode = kEpi == 5 ? (int)PESR_OUT_SHUFFLE2 : kEpi == 6 ? (int)PESR_OUT_UNSHUFFLE2
                          : kEpi ? (int)PESR_OUT_NORMAL : p.out_mode;
     const int e_aux = p.aux_mode;     // only changes the per-tile pixel index: stays a run-time value
+    // kEpi 7: channel statistics of this CTA, accumulated in shared memory over all its tiles
+    float* cta_sum = reinterpret_cast<float*>(epi_base + 4 * 4096);
+    float* cta_sq = cta_sum + 512;
+    if (kEpi == 7) {
+      for (int i = threadIdx.x - 64; i < 1024; i += 128) cta_sum[i] = 0.f;    // made visible by the first bar.sync 1
+    }
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const int et = threadIdx.x - 64;  // 0..127
@@ -577,6 +588,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
         }
         const bool stamp = dbg && et == 0 && tile != worker && ch == 2;
         if (stamp) dbg[40] = clock64();     // prefetch of chunk 3 issued
+        float yq[kEpi == 7 ? 32 : 1];      // kEpi 7: the rounded outputs of this row (zeros outside the image)
+        if (kEpi == 7) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) yq[kEpi == 7 ? j : 0] = 0.f;
+        }
         if (valid) {
           const int q0 = n0 + ch * 32;
           float f[32];
@@ -649,7 +665,37 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
             for (int j = 0; j < 16; j++) pk[j] = pack2(f[2 * j], f[2 * j + 1], bf);
             st256_b32(e_out16 + off, pk);
             st256_b32(e_out16 + off + 16, pk + 8);
+            if (kEpi == 7) {
+#pragma unroll
+              for (int j = 0; j < 16; j++) {
+                const float2 a = unpack2(pk[j], bf);
+                yq[kEpi == 7 ? 2 * j : 0] = a.x;
+                yq[kEpi == 7 ? 2 * j + 1 : 0] = a.y;
+              }
+            }
           }
+        }
+        if (kEpi == 7) {
+          // column sums over the warp's 32 rows: rows -> swizzled smem tile, then lane L reads column L of every row
+          const uint32_t tb = smem_u32(epi_base) + (uint32_t)quarter * 4096u;
+          const uint32_t xr = (uint32_t)(lane & 7);
+#pragma unroll
+          for (int c = 0; c < 8; c++)
+            sts128(tb + (uint32_t)lane * 128u + (((uint32_t)c ^ xr) << 4), __float_as_uint(yq[kEpi == 7 ? 4 * c : 0]),
+                   __float_as_uint(yq[kEpi == 7 ? 4 * c + 1 : 0]), __float_as_uint(yq[kEpi == 7 ? 4 * c + 2 : 0]),
+                   __float_as_uint(yq[kEpi == 7 ? 4 * c + 3 : 0]));
+          __syncwarp();
+          float s1 = 0.f, s2 = 0.f;
+          const uint32_t cpiece = (uint32_t)(lane >> 2), cword = (uint32_t)(lane & 3) * 4u;
+#pragma unroll
+          for (int r = 0; r < 32; r++) {
+            const float t = __uint_as_float(lds32(tb + (uint32_t)r * 128u + ((cpiece ^ (uint32_t)(r & 7)) << 4) + cword));
+            s1 += t;
+            s2 = fmaf(t, t, s2);
+          }
+          __syncwarp();
+          atomicAdd(cta_sum + n0 + ch * 32 + lane, s1);
+          atomicAdd(cta_sq + n0 + ch * 32 + lane, s2);
         }
         if (stamp) dbg[42] = clock64();     // stores issued
         if (more) {
@@ -672,6 +718,13 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       if (dbg && et == 0) dbg[17 + (tile == worker ? 0 : 4)] = clock64();       // epilogue of the tile done
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+    if (kEpi == 7) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = et; i < p.cout; i += 128) {
+        atomicAdd(p.bn_sums + i, (double)cta_sum[i]);
+        atomicAdd(p.bn_sums + p.cout + i, (double)cta_sq[i]);
+      }
     }
     }
   }
@@ -794,6 +847,11 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
     }
   }
   // residual epilogue through shared memory (pair kernel, outputs on the GEMM's own pixel grid)
+  if (d->bn_sums) {
+    PESR_CHECK_ARG(epi == 1 && d->cout <= 512, "conv_igemm: bn_sums needs the light epilogue (16-bit NHWC output only) and "
+                                               "cout <= 512");
+    epi = 7;
+  }
   const bool staged = pair && epi == 3 && gemm_grid && g_staged_enabled && 32 % d->tile_w == 0 && d->ld_out16 % 8 == 0 &&
                       d->ld_out32 % 4 == 0 && d->ld_res32 % 4 == 0 && (long long)d->nb * d->h * d->w < (1ll << 31);
   if (staged) epi = 4;
@@ -890,7 +948,9 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
     k.steps_per_tile = sub_mode == 2 ? 3 * (d->cin / kKBlock) : d->ntaps * (d->cin / kKBlock) / nsub;
   }
   k.staged = staged ? 1 : 0;
-  const int smem_budget = 227 * 1024 - 4096 - (staged ? kEpiBytes : 0);
+  k.bn_sums = d->bn_sums;
+  const int epi_smem = staged ? kEpiBytes : epi == 7 ? kBnEpiBytes : 0;
+  const int smem_budget = 227 * 1024 - 4096 - epi_smem;
   k.stages = smem_budget / k.stage_bytes;
   if (k.stages > kMaxStages) k.stages = kMaxStages;
   for (int t = 0; t < PESR_MAX_TAPS; t++) {
@@ -912,20 +972,20 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
   k.aux_mode = d->aux_mode;
 
   // >= 120 KB of dynamic smem also guarantees one CTA per SM, so the 512-column TMEM allocation never contends.
-  size_t smem = (size_t)k.stages * k.stage_bytes + (staged ? kEpiBytes : 0) + 1024 /*align*/ + 256 /*barriers*/ +
+  size_t smem = (size_t)k.stages * k.stage_bytes + epi_smem + 1024 /*align*/ + 256 /*barriers*/ +
                 2 * 256 * sizeof(float);
   if (smem < 120 * 1024) smem = 120 * 1024;
   // kernel variant: CTA pair x epilogue specialisation (see the template comment)
   typedef void (*KernelFn)(const ConvMaps, const ConvK);
-  static const KernelFn kernels[2][7] = {
+  static const KernelFn kernels[2][8] = {
       {conv_igemm_kernel<false, 0>, conv_igemm_kernel<false, 1>, conv_igemm_kernel<false, 2>, conv_igemm_kernel<false, 3>,
-       nullptr, conv_igemm_kernel<false, 5>, conv_igemm_kernel<false, 6>},
+       nullptr, conv_igemm_kernel<false, 5>, conv_igemm_kernel<false, 6>, conv_igemm_kernel<false, 7>},
       {conv_igemm_kernel<true, 0>, conv_igemm_kernel<true, 1>, conv_igemm_kernel<true, 2>, conv_igemm_kernel<true, 3>,
-       conv_igemm_kernel<true, 4>, conv_igemm_kernel<true, 5>, conv_igemm_kernel<true, 6>}};
+       conv_igemm_kernel<true, 4>, conv_igemm_kernel<true, 5>, conv_igemm_kernel<true, 6>, conv_igemm_kernel<true, 7>}};
   static bool attr_set = false;
   if (!attr_set) {
     for (int a = 0; a < 2; a++)
-      for (int b = 0; b < 7; b++) {
+      for (int b = 0; b < 8; b++) {
         if (!kernels[a][b]) continue;
         cudaError_t e = cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) {

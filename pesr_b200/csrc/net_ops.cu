@@ -552,9 +552,9 @@ extern "C" int pesr_bn_stats(const void* y16, int64_t npix, int32_t c, float eps
                              int64_t* num_batches_tracked, const float* running_mean_shift, int32_t dtype,
                              void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  PESR_CHECK_ARG(y16 && sums_ws && mean && rstd && npix > 0 && c > 0 && c % 8 == 0, "bn_stats: bad arguments");
+  PESR_CHECK_ARG(sums_ws && mean && rstd && npix > 0 && c > 0 && c % 8 == 0, "bn_stats: bad arguments");
   PESR_CHECK_ARG(c <= 512, "bn_stats: at most 512 channels");
-  launch_bn_reduce(y16, nullptr, npix, c, nullptr, nullptr, 0, dtype, sums_ws, stream);
+  if (y16) launch_bn_reduce(y16, nullptr, npix, c, nullptr, nullptr, 0, dtype, sums_ws, stream);
   launch_pdl(bn_finalize_kernel, (c + 127) / 128, 128, 0, stream, sums_ws, c, (double)npix, eps, momentum, mean, rstd,
                                                          running_mean, running_var,
                                                          reinterpret_cast<long long*>(num_batches_tracked),

@@ -11,6 +11,8 @@ NCHW flatten, Linear(512*s*s -> 1024), LeakyReLU, Linear(1024 -> 1).
 """
 import ctypes as C
 
+import os
+
 import torch
 
 from . import ops
@@ -53,6 +55,11 @@ class _Release:
 
     def __del__(self):
         self.plan.busy = False
+
+
+# A/B knob (tools/ab_env.sh): "1" = separate statistics pass for every layer, "2" = fused for every layer,
+# default = fused except conv0 (K = 64: its epilogue, not its MMAs, bounds that layer)
+_FUSE_BN_STATS = os.environ.get("PESR_NO_FUSED_BN", "0")
 
 
 class DiscriminatorEngine:
@@ -284,12 +291,15 @@ class DiscriminatorEngine:
         ops.im2col3(x, pl.col0, affine_b=self.img_shift, pad_affine=True)
         stream = torch.cuda.current_stream().cuda_stream
         for i in range(8):
+            # train mode: the conv epilogue accumulates the BatchNorm sums of its own (rounded) output
+            fuse_stats = training and _FUSE_BN_STATS != "1" and (i > 0 or _FUSE_BN_STATS == "2")
+            pl.fwd[i].bn_sums = self.bn_ws.data_ptr() if fuse_stats else None
             _run_conv(pl.fwd[i], stream)
             bn = d.features[i][1]
             hh, ww = pl.dims[i]
             npix, co = nb * hh * ww, D_LAYERS[i][1]
             if training:
-                ops.bn_stats(pl.Y[i], npix, co, self.bn_ws, pl.mean[i], pl.rstd[i], bn.running_mean, bn.running_var,
+                ops.bn_stats(None if fuse_stats else pl.Y[i], npix, co, self.bn_ws, pl.mean[i], pl.rstd[i], bn.running_mean, bn.running_var,
                              bn.num_batches_tracked, eps=bn.eps, momentum=bn.momentum,
                              running_mean_shift=self.c0_shift if i == 0 else None)
             else:

@@ -51,7 +51,8 @@ def make_conv_desc(*, dtype, nb, h, w, cin, cout, block_n=None, taps=TAPS_3X3, t
                    srcs, wpacked, bias=None, alpha=1.0, alpha_dev=None, res32=None, ld_res32=0, res16=None,
                    ld_res16=0, act=ACT_NONE, mask16=None, ld_mask16=0, mask_mode=0, out32=None, ld_out32=0,
                    out16=None, ld_out16=0, out_mode=OUT_NORMAL, out_h=0, out_w=0, out_sy=1, out_sx=1, out_oy=0,
-                   out_ox=0, out_coff=0, ps_c=0, tile=None, aux_mode=0, ksplit=0, b_mn_major=0, split_stride32=0):
+                   out_ox=0, out_coff=0, ps_c=0, tile=None, aux_mode=0, ksplit=0, b_mn_major=0, split_stride32=0,
+                   bn_sums=None):
     """Build a ``pesr_conv_desc``.
 
     ``srcs`` is a list of (tensor_or_ptr, src_h, src_w, stride_n, stride_h, stride_w) NHWC views (element
@@ -88,6 +89,7 @@ def make_conv_desc(*, dtype, nb, h, w, cin, cout, block_n=None, taps=TAPS_3X3, t
     d.out_sy, d.out_sx, d.out_oy, d.out_ox, d.out_coff, d.ps_c = out_sy, out_sx, out_oy, out_ox, out_coff, ps_c
     d.aux_mode = aux_mode
     d.ksplit, d.b_mn_major, d.split_stride32 = ksplit, b_mn_major, split_stride32
+    d.bn_sums = _ptr(bn_sums)
     return d
 
 
@@ -239,9 +241,10 @@ def adam_multi(table, nchunks, lr, beta1, beta2, eps, step, grad_mul=1.0):
 
 def bn_stats(y16, npix, c, sums_ws, mean, rstd, running_mean=None, running_var=None, num_batches=None, eps=1e-5,
              momentum=0.1, running_mean_shift=None):
+    # y16 = None: the sums come from the producing conv (make_conv_desc(bn_sums=...)); only the finalisation runs
     check(lib.pesr_bn_stats(_ptr(y16), npix, c, eps, momentum, _ptr(sums_ws), _ptr(mean), _ptr(rstd),
                             _ptr(running_mean), _ptr(running_var), _ptr(num_batches), _ptr(running_mean_shift),
-                            dt_code(y16.dtype), _stream()), "pesr_bn_stats")
+                            dt_code(y16.dtype) if y16 is not None else 0, _stream()), "pesr_bn_stats")
 
 
 def bn_lrelu_fwd(y16, npix, c, mean, rstd, gamma, beta, a16, slope=0.2):

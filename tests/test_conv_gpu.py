@@ -177,3 +177,34 @@ def test_im2col_col2im_roundtrip_and_moments():
     ops.moments3(a, b2, sums)
     assert rel_l2(sums[:9].view(3, 3), torch.einsum("nohw,nihw->oi", a, b2)) < 1e-5
     assert rel_l2(sums[9:], a.sum(dim=(0, 2, 3))) < 1e-5
+
+
+@pytest.mark.parametrize("nb,cin,cout,h,w", [(2, 64, 64, 24, 20), (16, 128, 256, 48, 48), (3, 64, 128, 7, 5)])
+def test_bn_statistics_epilogue(nb, cin, cout, h, w, pair_mode):
+    """pesr_conv_desc.bn_sums: per-channel sum / sum of squares of the ROUNDED 16-bit outputs, accumulated by the conv
+    epilogue (train-mode BatchNorm statistics, model/basic.py:29), against torch on the tensor the kernel stored."""
+    from pesr_b200 import ops
+    dtype = torch.float16
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(nb, cin, h, w, device="cuda", generator=g)
+    wt = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (3 * cin ** 0.5)
+    wp = torch.empty(9 * cout, cin, device="cuda", dtype=dtype)
+    ops.pack_weights(wt, 0, wp)
+    y = torch.empty(nb, h, w, cout, device="cuda", dtype=dtype)
+    sums = torch.zeros(2 * cout, device="cuda", dtype=torch.float64)
+    d = ops.make_conv_desc(dtype=0, nb=nb, h=h, w=w, cin=cin, cout=cout, srcs=[ops.nhwc_src(_nhwc16(x, dtype), nb, h, w, cin)],
+                           wpacked=wp, out16=y, ld_out16=cout, bn_sums=sums)
+    ops.conv_igemm(d)
+    ops.conv_igemm(d)          # accumulates: two passes = twice the sums
+    yd = y.double().reshape(-1, cout)
+    ref = torch.cat([yd.sum(0), (yd * yd).sum(0)]) * 2
+    assert rel_l2(_nchw32(y, nb, cout, h, w), F.conv2d(x.half().float(), wt.half().float(), None, padding=1)) < 3e-4
+    assert float((sums[:cout] - ref[:cout]).abs().max()) < 2e-4 * float(yd.abs().sum(0).max())
+    assert rel_l2(sums[cout:], ref[cout:]) < 1e-5
+    # finalisation only (y16 = None): mean / rstd from the accumulated sums, sums zeroed again
+    mean, rstd = torch.empty(cout, device="cuda"), torch.empty(cout, device="cuda")
+    sums.mul_(0.5)
+    ops.bn_stats(None, nb * h * w, cout, sums, mean, rstd)
+    assert float((mean.double() - yd.mean(0)).abs().max()) < 1e-5 * float(yd.abs().mean()) + 1e-6
+    assert rel_l2(rstd.double(), 1.0 / torch.sqrt(yd.var(0, unbiased=False) + 1e-5)) < 1e-5
+    assert float(sums.abs().max()) == 0.0

@@ -287,10 +287,11 @@ int pesr_bn_lrelu_fwd(const void* y16, int64_t npix, int32_t c, const float* mea
                       const float* gamma, const float* beta, float slope, int32_t dtype, void* a16, void* stream);
 /* BatchNorm backward given dz = dL/d(bn output) (LeakyReLU' already applied by the producer):
  *   dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)), dgamma = sum(dz*xhat), dbeta = sum(dz),
- * the parameter gradients multiplied by grad_mul / (*grad_div_dev). */
+ * the parameter gradients multiplied by grad_mul / (*grad_div_dev); accumulate != 0 adds them to dgamma / dbeta
+ * (second backward pass of one optimiser step, train.py:213-216). */
 int pesr_bn_lrelu_bwd(const void* dz16, const void* y16, int64_t npix, int32_t c, const float* mean, const float* rstd,
                       const float* gamma, double* sums_ws, float grad_mul, const float* grad_div_dev, int32_t dtype,
-                      void* dy16, float* dgamma, float* dbeta, void* stream);
+                      void* dy16, float* dgamma, float* dbeta, int32_t accumulate, void* stream);
 /* 2x2/2 max-pool (vgg19.features) on NHWC 16-bit; backward routes to the first maximum in scan order (PyTorch's
  * tie rule) and, with relu_mask, multiplies by relu'(x). */
 int pesr_maxpool2_fwd(const void* x16, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t dtype, void* y16, void* stream);

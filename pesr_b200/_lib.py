@@ -115,7 +115,7 @@ SIGNATURES = {
     "pesr_loss_gan": (C.c_int, [_vp, _vp, _i32, _f32, _f32, _f32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "pesr_bn_stats": (C.c_int, [_vp, _i64, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "pesr_bn_lrelu_fwd": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _i32, _vp, _vp]),
-    "pesr_bn_lrelu_bwd": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "pesr_bn_lrelu_bwd": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _i32, _vp]),
     "pesr_maxpool2_fwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "pesr_maxpool2_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "pesr_linear_workspace_floats": (C.c_int64, [_i32, _i32, _i32]),

@@ -182,7 +182,7 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* _
                                     double n, const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ gamma, const double* __restrict__ sums, float gmul,
                                     const float* __restrict__ gdiv_dev, int bf, uint4* __restrict__ dy,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
   griddep_wait();   // PDL: see launch_pdl
   __shared__ float ka[512], kb[512], kc[512];
   const int cv = c >> 3;
@@ -190,8 +190,9 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* _
     float mul = gmul;
     if (gdiv_dev) mul /= __ldg(gdiv_dev);
     for (int i = threadIdx.x; i < c; i += blockDim.x) {
-      dbeta[i] = (float)sums[i] * mul;
-      dgamma[i] = (float)sums[c + i] * mul;
+      const float db = (float)sums[i] * mul, dgm = (float)sums[c + i] * mul;
+      dbeta[i] = accumulate ? dbeta[i] + db : db;
+      dgamma[i] = accumulate ? dgamma[i] + dgm : dgm;
     }
   }
   for (int i = threadIdx.x; i < c; i += blockDim.x) {
@@ -582,7 +583,7 @@ extern "C" int pesr_bn_lrelu_fwd(const void* y16, int64_t npix, int32_t c, const
 extern "C" int pesr_bn_lrelu_bwd(const void* dz16, const void* y16, int64_t npix, int32_t c, const float* mean,
                                  const float* rstd, const float* gamma, double* sums_ws, float grad_mul,
                                  const float* grad_div_dev, int32_t dtype, void* dy16, float* dgamma, float* dbeta,
-                                 void* stream_) {
+                                 int32_t accumulate, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   PESR_CHECK_ARG(dz16 && y16 && dy16 && mean && rstd && gamma && sums_ws && npix > 0 && c % 8 == 0,
                  "bn_lrelu_bwd: bad arguments");
@@ -591,7 +592,7 @@ extern "C" int pesr_bn_lrelu_bwd(const void* dz16, const void* y16, int64_t npix
   const long long nvec = npix * (c / 8);
   launch_pdl(bn_bwd_apply_kernel, nblocks(nvec, 256, 148 * 16), 256, 0, stream, 
       reinterpret_cast<const uint4*>(dz16), reinterpret_cast<const uint4*>(y16), nvec, c, (double)npix, mean, rstd, gamma,
-      sums_ws, grad_mul, grad_div_dev, dtype, reinterpret_cast<uint4*>(dy16), dgamma, dbeta);
+      sums_ws, grad_mul, grad_div_dev, dtype, reinterpret_cast<uint4*>(dy16), dgamma, dbeta, accumulate);
   launch_pdl(zero_doubles_kernel, (2 * c + 255) / 256, 256, 0, stream, sums_ws, 2 * c);
   count_launch(3);
   PESR_CHECK_LAUNCH("bn_lrelu_bwd");

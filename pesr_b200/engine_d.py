@@ -57,9 +57,12 @@ class _Release:
         self.plan.busy = False
 
 
-# A/B knob (tools/ab_env.sh): "1" = separate statistics pass for every layer, "2" = fused for every layer,
-# default = fused except conv0 (K = 64: its epilogue, not its MMAs, bounds that layer)
-_FUSE_BN_STATS = os.environ.get("PESR_NO_FUSED_BN", "0")
+# PESR_FUSED_BN: "0" (default) = separate statistics pass over the conv output, "1" = accumulated by the conv epilogue
+# (pesr_conv_desc.bn_sums) for layers 1-7, "2" = for every layer.  Measured on the GAN step (tools/ab_env2.sh): 19.19 /
+# 19.14 / 19.38 ms, i.e. no gain - the statistics cost the MMA-bound layers' epilogue what the extra pass cost - and the
+# fp32 shared-memory atomics make the statistics (hence the logits, at the 1e-3 level after eight BatchNorm layers)
+# depend on the warp scheduling order, so the deterministic separate pass stays the default.
+_FUSE_BN_STATS = os.environ.get("PESR_FUSED_BN", "0")
 
 
 class DiscriminatorEngine:
@@ -292,7 +295,7 @@ class DiscriminatorEngine:
         stream = torch.cuda.current_stream().cuda_stream
         for i in range(8):
             # train mode: the conv epilogue accumulates the BatchNorm sums of its own (rounded) output
-            fuse_stats = training and _FUSE_BN_STATS != "1" and (i > 0 or _FUSE_BN_STATS == "2")
+            fuse_stats = training and _FUSE_BN_STATS != "0" and (i > 0 or _FUSE_BN_STATS == "2")
             pl.fwd[i].bn_sums = self.bn_ws.data_ptr() if fuse_stats else None
             _run_conv(pl.fwd[i], stream)
             bn = d.features[i][1]
@@ -327,7 +330,10 @@ class DiscriminatorEngine:
         return logits, None
 
     # ------------------------------------------------------------------ backward
-    def backward(self, state, dlogits, need_param_grads, need_input_grad):
+    def backward(self, state, dlogits, need_param_grads, need_input_grad, acc_flat=None, fire_hooks=True):
+        """acc_flat: the flat gradient buffer of an earlier backward pass of the same optimiser step; this pass ADDS its
+        parameter gradients to it (the D phase back-propagates D(hr) and D(sr) before one optimiser step,
+        train.py:213-216).  fire_hooks=False defers the data-parallel all-reduce to the pass that completes the sum."""
         pl, _rel, x = state
         d = self.disc
         nb, h, w = pl.nb, pl.h, pl.w
@@ -342,10 +348,11 @@ class DiscriminatorEngine:
         grads, flat, hook = {}, None, None
         off = self.offsets
         mark_hi = [self.flat_numel]
+        acc = acc_flat is not None
         if need_param_grads:
-            flat = torch.empty(self.flat_numel, device=dev, dtype=torch.float32)
+            flat = acc_flat if acc else torch.empty(self.flat_numel, device=dev, dtype=torch.float32)
             grads = {p: flat[off[p]:off[p] + p.numel()].view(p.shape) for p in self.param_list}
-            hook = self.grad_hook
+            hook = self.grad_hook if fire_hooks else None
 
         def mark(param):
             lo = off[param]
@@ -355,14 +362,20 @@ class DiscriminatorEngine:
 
         # ---- classifier (fp32 gradients, 16-bit operands)
         if need_param_grads:
-            ops.linear_wgrad(dlogits, pl.h1_16, nb, 1024, 1, grads[fc2.weight])
-            torch.sum(dlogits, dim=0, out=grads[fc2.bias])
+            ops.linear_wgrad(dlogits, pl.h1_16, nb, 1024, 1, grads[fc2.weight], accumulate=acc)
+            if acc:
+                grads[fc2.bias].add_(torch.sum(dlogits, dim=0))
+            else:
+                torch.sum(dlogits, dim=0, out=grads[fc2.bias])
             mark(fc2.weight)
         ops.linear_dgrad(dlogits, self.w2_16, nb, 1024, 1, sc.dh1)
         dz1 = sc.dh1 * torch.where(pl.h1_32 > 0, 1.0, 0.2)      # LeakyReLU'(h1), a 16x1024 tensor
         if need_param_grads:
-            ops.linear_wgrad(dz1, pl.flat7, nb, pl.kfc, 1024, grads[fc1.weight])
-            torch.sum(dz1, dim=0, out=grads[fc1.bias])
+            ops.linear_wgrad(dz1, pl.flat7, nb, pl.kfc, 1024, grads[fc1.weight], accumulate=acc)
+            if acc:
+                grads[fc1.bias].add_(torch.sum(dz1, dim=0))
+            else:
+                torch.sum(dz1, dim=0, out=grads[fc1.bias])
             mark(fc1.weight)
         if sc.fc1_dgrad is not None:
             ops.amax_scale(dz1, sc.scale1, target=16.0)
@@ -390,16 +403,16 @@ class DiscriminatorEngine:
                     dummy = torch.empty(2 * 512, device=dev, dtype=torch.float32)
                 dgam, dbet = dummy[:co], dummy[512:512 + co]
             ops.bn_lrelu_bwd(sc.dZ[i], pl.Y[i], npix, co, pl.mean[i], pl.rstd[i], bn.weight.detach(), self.bn_ws,
-                             sc.dY[i], dgam, dbet, grad_div_dev=scale)
+                             sc.dY[i], dgam, dbet, grad_div_dev=scale, accumulate=acc and need_param_grads)
             if need_param_grads:
                 check(lib.pesr_conv_wgrad(C.byref(wg[i]), C.byref(splits), stream), "pesr_conv_wgrad")
                 if i == 0:
                     check(lib.pesr_wgrad_reduce(sc.wg.data_ptr(), splits.value, 1, 64, 64, ops.WMAP_COL_IN, 64, 3, 1.0,
-                                                scale.data_ptr(), 0, grads[conv.weight].data_ptr(), stream),
+                                                scale.data_ptr(), 1 if acc else 0, grads[conv.weight].data_ptr(), stream),
                           "pesr_wgrad_reduce")
                 else:
                     check(lib.pesr_wgrad_reduce(sc.wg.data_ptr(), splits.value, 9, co, ci, ops.WMAP_OIHW, co, ci, 1.0,
-                                                scale.data_ptr(), 0, grads[conv.weight].data_ptr(), stream),
+                                                scale.data_ptr(), 1 if acc else 0, grads[conv.weight].data_ptr(), stream),
                           "pesr_wgrad_reduce")
                 mark(conv.weight)
             if i > 0 or need_input_grad:
@@ -414,4 +427,5 @@ class DiscriminatorEngine:
                 raise AssertionError("discriminator backward: gradient ranges did not cover the flat buffer")
             if hook is not None and self.grad_hook_finish is not None:
                 self.grad_hook_finish()
+        self.last_flat = flat
         return grads, dx

@@ -252,10 +252,11 @@ def bn_lrelu_fwd(y16, npix, c, mean, rstd, gamma, beta, a16, slope=0.2):
                                 dt_code(y16.dtype), _ptr(a16), _stream()), "pesr_bn_lrelu_fwd")
 
 
-def bn_lrelu_bwd(dz16, y16, npix, c, mean, rstd, gamma, sums_ws, dy16, dgamma, dbeta, grad_mul=1.0, grad_div_dev=None):
+def bn_lrelu_bwd(dz16, y16, npix, c, mean, rstd, gamma, sums_ws, dy16, dgamma, dbeta, grad_mul=1.0, grad_div_dev=None,
+                 accumulate=False):
     check(lib.pesr_bn_lrelu_bwd(_ptr(dz16), _ptr(y16), npix, c, _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(sums_ws),
                                 grad_mul, _ptr(grad_div_dev), dt_code(y16.dtype), _ptr(dy16), _ptr(dgamma),
-                                _ptr(dbeta), _stream()), "pesr_bn_lrelu_bwd")
+                                _ptr(dbeta), 1 if accumulate else 0, _stream()), "pesr_bn_lrelu_bwd")
 
 
 def maxpool2_fwd(x16, nb, h, w, c, y16):

@@ -38,6 +38,9 @@ class DataParallel(torch.nn.Module):
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)
 
+    def forward_pair(self, a, b):
+        return self.module.forward_pair(a, b)
+
     def _broadcast_parameters(self):
         with torch.no_grad():
             for t in list(self.module.parameters()) + list(self.module.buffers()):

@@ -3,9 +3,13 @@
 These are what train.py's loops call once per batch; bench.py times exactly these functions.
 Losses stay on the device: callers read them back when they want to log (train.py reads five scalars
 per iteration, train.py:262-266 -- here that is one optional stacked copy)."""
+import os
+
 import torch
 
 from . import losses
+
+_D_PAIR = os.environ.get("PESR_NO_D_PAIR") != "1"    # A/B knob (tools/ab_env.sh)
 
 
 def pretrain_step(G, optim_G, lr, hr, ddp=None):
@@ -29,9 +33,14 @@ def gan_step(G, D, vgg, optim_G, optim_D, lr, hr, cfg, ddp_g=None, ddp_d=None):
     for p in D.parameters():
         p.requires_grad = True
     optim_D.zero_grad(set_to_none=True)
-    pred_real = D(hr)
     sr = G(lr)
-    pred_fake = D(sr.detach())
+    if _D_PAIR and hasattr(D, "forward_pair"):
+        # D(hr) then D(sr.detach()) as in train.py:205-207 (same order of the BatchNorm running-statistics updates),
+        # with one gradient pass / one all-reduce for the parameters
+        pred_real, pred_fake = D.forward_pair(hr, sr.detach())
+    else:
+        pred_real = D(hr)
+        pred_fake = D(sr.detach())
     if cfg['gan_type'] == 'SGAN':
         bce = losses.BCEWithLogitsLoss()
         total_D_loss = bce(pred_real, t_real) + bce(pred_fake, t_fake)

@@ -64,6 +64,38 @@ def test_discriminator_forward_backward_and_running_stats():
         Discriminator({'patch_size': 16, 'spectral_norm': True})
 
 
+def test_discriminator_forward_pair_equals_two_calls():
+    """D.forward_pair(a, b) is two train-mode calls (separate BatchNorm statistics, running statistics updated twice in
+    order) whose parameter gradients come from one accumulated pass: same logits, same gradients, same buffers."""
+    from oracle import pesr_oracle as O
+    from pesr_b200.model import Discriminator
+    opt = {'patch_size': 16, 'spectral_norm': False}
+    sd = O.init_discriminator(opt, 0)
+    g = torch.Generator().manual_seed(2)
+    nb = 8
+    a = (torch.rand(nb, 3, 64, 64, generator=g) * 255).cuda()
+    b = (torch.rand(nb, 3, 64, 64, generator=g) * 255).cuda()
+    ra, rb = torch.randn(nb, 1, generator=g).cuda(), torch.randn(nb, 1, generator=g).cuda()
+    res = []
+    for pair in (False, True):
+        D = Discriminator(opt)
+        D.load_state_dict(sd)
+        D = D.cuda().train()
+        if pair:
+            ya, yb = D.forward_pair(a, b)
+        else:
+            ya, yb = D(a), D(b)
+        ((ya * ra).sum() + (yb * rb).sum()).backward()
+        res.append((ya.detach(), yb.detach(), {k: p.grad.clone() for k, p in D.named_parameters()},
+                    {k: v.clone() for k, v in D.state_dict().items() if "running" in k or "tracked" in k}))
+    (ya0, yb0, g0, s0), (ya1, yb1, g1, s1) = res
+    assert torch.equal(ya0, ya1) and torch.equal(yb0, yb1)
+    for k in g0:
+        assert rel_l2(g1[k], g0[k]) < 1e-6, k          # same kernels; only the order of one fp32 addition differs
+    for k in s0:
+        assert torch.equal(s0[k], s1[k]), k
+
+
 def test_vgg_features_and_input_gradient():
     from oracle import pesr_oracle as O
     from pesr_b200.model import VGG

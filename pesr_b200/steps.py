@@ -47,20 +47,23 @@ def gan_step(G, D, vgg, optim_G, optim_D, lr, hr, cfg, ddp_g=None, ddp_d=None):
     else:
         total_D_loss = losses.rsgan_bce(pred_real, pred_fake, t_real)
     total_D_loss.backward()
+    # The Generator-phase terms that do not involve D (train.py:240-247) are issued BEFORE waiting for D's gradient
+    # all-reduce: VGG's forward, L1 and TV depend on sr / hr only, so they keep the SMs busy while the 321 MB of
+    # Discriminator gradients are still on the wire.  Values are unchanged (nothing here reads D or its optimiser).
+    optim_G.zero_grad(set_to_none=True)
+    l1_loss = losses.l1_loss(sr, hr) * cfg['alpha_l1']
+    f_sr, f_hr = vgg(sr, hr)
+    vgg_loss = losses.mse_loss(f_sr, f_hr) * cfg['alpha_vgg']
+    tv_scale = cfg['alpha_tv'] * (ddp_g.world_size if ddp_g is not None else 1)  # TV is a batch SUM (train.py:137-140)
+    tv_loss = losses.tv_loss(sr) * tv_scale
     if ddp_d is not None:
         ddp_d.finish()
     optim_D.step()
     # ---- Generator phase (train.py:234-259)
     for p in D.parameters():
         p.requires_grad = False
-    optim_G.zero_grad(set_to_none=True)
     pred_fake = D(sr)
     pred_real = D(hr)
-    l1_loss = losses.l1_loss(sr, hr) * cfg['alpha_l1']
-    f_sr, f_hr = vgg(sr, hr)
-    vgg_loss = losses.mse_loss(f_sr, f_hr) * cfg['alpha_vgg']
-    tv_scale = cfg['alpha_tv'] * (ddp_g.world_size if ddp_g is not None else 1)  # TV is a batch SUM (train.py:137-140)
-    tv_loss = losses.tv_loss(sr) * tv_scale
     if cfg['gan_type'] == 'SGAN':
         if cfg['focal_loss']:
             G_loss = losses._GanLoss.apply(pred_fake, None, 1.0, 0.0, losses._uniform_target(t_real), 1,

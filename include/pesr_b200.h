@@ -81,7 +81,7 @@ typedef struct pesr_conv_desc {
   int32_t nb, h, w;         /* GEMM-M pixel grid */
   int32_t cin, cout;        /* cin multiple of 64 (per tap), cout multiple of block_n */
   int32_t block_n;          /* 32, 64, 128 or 256 */
-  int32_t tile_h, tile_w;   /* tile_h * tile_w == 128 */
+  int32_t tile_h, tile_w;   /* tile_n * tile_h * tile_w == 128 (tile_n: see the end of the struct) */
   int32_t ntaps;
   int8_t tap_dh[PESR_MAX_TAPS], tap_dw[PESR_MAX_TAPS], tap_src[PESR_MAX_TAPS], tap_widx[PESR_MAX_TAPS];
   /* sources: NHWC views; strides in elements, channel stride 1 */
@@ -110,6 +110,9 @@ typedef struct pesr_conv_desc {
   int32_t ksplit;           /* > 1: split K across CTAs; raw fp32 partials go to out32 + split*split_stride32 */
   int32_t b_mn_major;       /* 1: wpacked is [K = cin][N = cout] (N contiguous), one tap: y = x * W without a transpose */
   int64_t split_stride32;   /* elements between the partial outputs of successive K splits */
+  int32_t tile_n;           /* images per pixel tile (0 = 1): tile_n * tile_h * tile_w == 128.  Small feature maps (24x24,
+                               12x12) tile without padding rows as e.g. 2 x 8 x 8 or 8 x 4 x 4 */
+  int32_t reserved0;
   double* bn_sums;          /* optional, light epilogue only (16-bit NHWC output, no residual / mask): 2*cout doubles that
                                receive += sum and += sum of squares of the ROUNDED 16-bit outputs per channel - the
                                train-mode BatchNorm statistics of model/basic.py:29 without a second pass over y

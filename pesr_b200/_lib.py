@@ -48,6 +48,7 @@ class ConvDesc(C.Structure):
         ("out_sy", C.c_int32), ("out_sx", C.c_int32), ("out_oy", C.c_int32), ("out_ox", C.c_int32),
         ("out_coff", C.c_int32), ("ps_c", C.c_int32), ("aux_mode", C.c_int32),
         ("ksplit", C.c_int32), ("b_mn_major", C.c_int32), ("split_stride32", C.c_int64),
+        ("tile_n", C.c_int32), ("reserved0", C.c_int32),
         ("bn_sums", C.c_void_p),
     ]
 

@@ -44,6 +44,7 @@ constexpr int kEpiBytes = 4 * kEpiWarpBytes;
 struct ConvK {
   int dtype;
   int nb, h, w, cin, cout, block_n, tile_h, tile_w, ntaps;
+  int tile_n;   // images per pixel tile (rows of a tile are ordered image, y, x)
   int tiles_h, tiles_w, n_tiles, num_tiles, kblocks_per_tap;
   int stages, stage_bytes;
   int8_t tap_dh[PESR_MAX_TAPS], tap_dw[PESR_MAX_TAPS], tap_src[PESR_MAX_TAPS], tap_widx[PESR_MAX_TAPS];
@@ -228,7 +229,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
         seek(s0, t, cb);
         const int tw = m_tile % p.tiles_w;
         const int th = (m_tile / p.tiles_w) % p.tiles_h;
-        const int img = m_tile / (p.tiles_w * p.tiles_h);   // == nb for the padding tile of an odd pair: all OOB -> zeros
+        // first image of the tile; >= nb for the padding tile of an odd pair: all OOB -> zeros
+        const int img = (m_tile / (p.tiles_w * p.tiles_h)) * p.tile_n;
         const int h0 = th * p.tile_h, w0 = tw * p.tile_w, n0 = n_tile * p.block_n + rank * b_rows;
         int s = s0;
         while (s < s1) {
@@ -512,7 +514,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     const int row = quarter * 32 + lane;
     const int et = threadIdx.x - 64;  // 0..127
     const int ch_lo = 0, ch_hi = p.block_n / 32;
-    const int ty = row / p.tile_w, tx = row % p.tile_w;
+    const int px_img = p.tile_h * p.tile_w;            // pixels of one image inside the tile
+    const int tn_l = row / px_img, ty = (row % px_img) / p.tile_w, tx = row % p.tile_w;
     const int bf = p.dtype;
     float alpha = p.alpha;
     if (p.alpha_dev) alpha *= __ldg(p.alpha_dev);
@@ -523,7 +526,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       decode(tile, split, m_tile, n_tile);
       const int tw = m_tile % p.tiles_w;
       const int th = (m_tile / p.tiles_w) % p.tiles_h;
-      const int img = m_tile / (p.tiles_w * p.tiles_h);
+      const int img = (m_tile / (p.tiles_w * p.tiles_h)) * p.tile_n + tn_l;
       const int h = th * p.tile_h + ty, w = tw * p.tile_w + tx, n0 = n_tile * p.block_n;
       const bool valid = (h < p.h) && (w < p.w) && (img < p.nb);
       // pixel index used by res32 / res16 / mask16 / out32: the GEMM grid, or (aux_mode 1) the strided output grid
@@ -783,7 +786,8 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
     g_pair_mode = (e && e[0] == '1') ? 0 : 1;
   }
   if (dd.block_n == 256 && dd.tile_h > 0 && dd.tile_w > 0 && g_sub_mode_enabled && dd.ksplit <= 1 && !dd.b_mn_major) {
-    const int mt = dd.nb * ((dd.h + dd.tile_h - 1) / dd.tile_h) * ((dd.w + dd.tile_w - 1) / dd.tile_w);
+    const int tn0 = dd.tile_n > 0 ? dd.tile_n : 1;
+    const int mt = ((dd.nb + tn0 - 1) / tn0) * ((dd.h + dd.tile_h - 1) / dd.tile_h) * ((dd.w + dd.tile_w - 1) / dd.tile_w);
     const bool will_pair = g_pair_mode == 2 || (g_pair_mode == 1 && mt >= 256);
     if (!will_pair && (dd.ntaps == 9 || (dd.cin / kKBlock) % 2 == 0)) dd.block_n = 128;
   }
@@ -794,8 +798,9 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
                  "conv_igemm: block_n %d not in {32,64,128,256}", d->block_n);
   PESR_CHECK_ARG(d->cout > 0 && d->cout % d->block_n == 0, "conv_igemm: cout %d not a multiple of block_n %d",
                  d->cout, d->block_n);
-  PESR_CHECK_ARG(d->tile_h > 0 && d->tile_w > 0 && d->tile_h * d->tile_w == kTileM,
-                 "conv_igemm: tile %dx%d must cover 128 pixels", d->tile_h, d->tile_w);
+  const int tile_n = d->tile_n > 0 ? d->tile_n : 1;
+  PESR_CHECK_ARG(d->tile_h > 0 && d->tile_w > 0 && tile_n * d->tile_h * d->tile_w == kTileM,
+                 "conv_igemm: tile %dx%dx%d must cover 128 pixels", tile_n, d->tile_h, d->tile_w);
   PESR_CHECK_ARG(d->tile_w <= 256 && d->tile_h <= 256, "conv_igemm: tile too large for a TMA box");
   PESR_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= PESR_MAX_TAPS, "conv_igemm: ntaps %d", d->ntaps);
   PESR_CHECK_ARG(d->nsrc >= 1 && d->nsrc <= PESR_MAX_SRC, "conv_igemm: nsrc %d", d->nsrc);
@@ -824,7 +829,8 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
     const char* e = getenv("PESR_NO_PAIR");
     g_pair_mode = (e && e[0] == '1') ? 0 : 1;
   }
-  const int m_tiles_host = d->nb * ((d->h + d->tile_h - 1) / d->tile_h) * ((d->w + d->tile_w - 1) / d->tile_w);
+  const int img_groups = (d->nb + tile_n - 1) / tile_n;
+  const int m_tiles_host = img_groups * ((d->h + d->tile_h - 1) / d->tile_h) * ((d->w + d->tile_w - 1) / d->tile_w);
   // measured on B200 (tools/perf_conv.py pair): the pair kernel wins 4-6% on the 256-wide, many-tile layers (G trunk and
   // upsampler) and loses 8-16% on the small D / VGG layers, so it is used where it wins (mode 2 forces it for tests).
   const bool pair_legal = d->ksplit <= 1 && !d->b_mn_major && d->block_n >= 64 && m_tiles_host >= 2;
@@ -852,7 +858,7 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
                                                "cout <= 512");
     epi = 7;
   }
-  const bool staged = pair && epi == 3 && gemm_grid && g_staged_enabled && 32 % d->tile_w == 0 && d->ld_out16 % 8 == 0 &&
+  const bool staged = pair && epi == 3 && gemm_grid && g_staged_enabled && tile_n == 1 && 32 % d->tile_w == 0 && d->ld_out16 % 8 == 0 &&
                       d->ld_out32 % 4 == 0 && d->ld_res32 % 4 == 0 && (long long)d->nb * d->h * d->w < (1ll << 31);
   if (staged) epi = 4;
 
@@ -862,7 +868,7 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
     bool std9 = d->ntaps == 9 && d->nsrc == 1;
     for (int t = 0; std9 && t < 9; t++)
       std9 = d->tap_dh[t] == t / 3 - 1 && d->tap_dw[t] == t % 3 - 1 && d->tap_src[t] == 0 && d->tap_widx[t] == t;
-    if (std9 && d->w_rows == 9 * d->cout && d->block_n <= 128) { sub_mode = 2; nsub = 3; }
+    if (std9 && d->w_rows == 9 * d->cout && d->block_n <= 128 && tile_n == 1) { sub_mode = 2; nsub = 3; }
     else if ((d->cin / kKBlock) % 2 == 0) { sub_mode = 1; nsub = 2; }
   }
 
@@ -875,12 +881,13 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
     if (sub_mode == 1) {
       uint64_t dims[5] = {64, (uint64_t)d->src_w[ss], (uint64_t)d->src_h[ss], (uint64_t)d->nb, (uint64_t)(d->cin / 64)};
       uint64_t str[4] = {(uint64_t)d->src_sw[ss] * 2, (uint64_t)d->src_sh[ss] * 2, (uint64_t)d->src_sn[ss] * 2, 128};
-      uint32_t box[5] = {64, (uint32_t)d->tile_w, (uint32_t)d->tile_h, 1, (uint32_t)nsub};
+      uint32_t box[5] = {64, (uint32_t)d->tile_w, (uint32_t)d->tile_h, (uint32_t)tile_n, (uint32_t)nsub};
       r = get_tensor_map(&maps.a[s], d->src[ss], d->dtype, 5, dims, str, box);
     } else {
       uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)d->src_w[ss], (uint64_t)d->src_h[ss], (uint64_t)d->nb};
       uint64_t str[3] = {(uint64_t)d->src_sw[ss] * 2, (uint64_t)d->src_sh[ss] * 2, (uint64_t)d->src_sn[ss] * 2};
-      uint32_t box[4] = {(uint32_t)kKBlock, (uint32_t)d->tile_w, (uint32_t)(sub_mode == 2 ? d->tile_h + 2 : d->tile_h), 1};
+      uint32_t box[4] = {(uint32_t)kKBlock, (uint32_t)d->tile_w, (uint32_t)(sub_mode == 2 ? d->tile_h + 2 : d->tile_h),
+                         (uint32_t)tile_n};
       r = get_tensor_map(&maps.a[s], d->src[ss], d->dtype, 4, dims, str, box);
     }
     if (r) return r;
@@ -924,10 +931,11 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
   k.dtype = d->dtype;
   k.nb = d->nb; k.h = d->h; k.w = d->w; k.cin = d->cin; k.cout = d->cout; k.block_n = d->block_n;
   k.tile_h = d->tile_h; k.tile_w = d->tile_w; k.ntaps = d->ntaps;
+  k.tile_n = tile_n;
   k.tiles_h = (d->h + d->tile_h - 1) / d->tile_h;
   k.tiles_w = (d->w + d->tile_w - 1) / d->tile_w;
   k.n_tiles = d->cout / d->block_n;
-  const int m_tiles = d->nb * k.tiles_h * k.tiles_w;
+  const int m_tiles = img_groups * k.tiles_h * k.tiles_w;
   k.mn_tiles = (pair ? (m_tiles + 1) / 2 : m_tiles) * k.n_tiles;   // pair mode counts tiles of 2 x 128 pixels
   k.ksplit = ksplit;
   k.num_tiles = k.mn_tiles * ksplit;

@@ -37,11 +37,25 @@ def _need_cuda(*ts):
             raise _lib.PesrError("pesr_b200 has no CPU path: tensors must live on a CUDA device")
 
 
-def pick_tile(h, w):
-    """128-pixel spatial tile (tile_h, tile_w) for an h x w pixel grid."""
-    if w % 16 == 0 or w > 24:
-        return 8, 16
-    return 16, 8
+def pick_tile(h, w, nb=1, cin=0):
+    """128-pixel tile (tile_n, tile_h, tile_w) for nb images of h x w pixels.
+
+    One image per tile (8x16, or 16x8 for narrow maps) unless that pads more than 20% of the MMA rows and the layer
+    is wide enough (cin >= 128) for the multi-chunk pipeline stages that multi-image tiles use instead of halo stages:
+    then the tile spans several images, e.g. 2 x 8 x 8 for 24x24 maps and 8 x 4 x 4 for 12x12 maps (no padding)."""
+    def padded(tn, th, tw):
+        return -(-nb // tn) * tn * -(-h // th) * th * -(-w // tw) * tw
+    legacy = (1, 8, 16) if (w % 16 == 0 or w > 24) else (1, 16, 8)
+    best = legacy
+    if cin >= 128 and nb > 1:
+        for tn in (2, 4, 8, 16):
+            for tw in (16, 8, 4):
+                th = 128 // (tn * tw)
+                if th >= 1 and tn * th * tw == 128 and tn <= nb and padded(tn, th, tw) < padded(*best):
+                    best = (tn, th, tw)
+        if padded(*best) > 0.8 * padded(*legacy):
+            best = legacy
+    return best
 
 
 TAPS_3X3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
@@ -62,8 +76,9 @@ def make_conv_desc(*, dtype, nb, h, w, cin, cout, block_n=None, taps=TAPS_3X3, t
     d.dtype = dtype
     d.nb, d.h, d.w, d.cin, d.cout = nb, h, w, cin, cout
     d.block_n = block_n or min(cout, 256)
-    th, tw = tile or pick_tile(h, w)
-    d.tile_h, d.tile_w = th, tw
+    tl = tile or pick_tile(h, w, nb, cin if (ksplit <= 1 and not b_mn_major) else 0)
+    tn, th, tw = tl if len(tl) == 3 else (1,) + tuple(tl)
+    d.tile_n, d.tile_h, d.tile_w = tn, th, tw
     d.ntaps = len(taps)
     for t, (dh, dw) in enumerate(taps):
         d.tap_dh[t], d.tap_dw[t] = dh, dw

@@ -33,6 +33,8 @@ def _nchw32(x16, nb, c, h, w):
 CASES = [  # nb, cin, cout, h, w   (G trunk, upsampler, D/VGG channel counts, ragged and tiny grids)
     (2, 256, 256, 48, 48), (1, 256, 1024, 16, 16), (1, 64, 64, 40, 24), (1, 64, 128, 24, 24),
     (2, 128, 128, 13, 19), (1, 512, 512, 12, 12), (1, 128, 256, 5, 3), (3, 64, 64, 1, 1),
+    # multi-image pixel tiles (ops.pick_tile: 2 x 8 x 8 for 24x24 maps, 8 x 4 x 4 for 12x12), even and ragged batches
+    (4, 256, 512, 24, 24), (16, 512, 512, 12, 12), (3, 128, 128, 12, 12), (5, 256, 256, 6, 6),
 ]
 
 

@@ -55,7 +55,8 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
   const int worker = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int nworkers = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
-  uint8_t* tail = smem + (size_t)p.stages * p.stage_bytes;
+  uint8_t* epi_tiles = smem + (size_t)p.stages * p.stage_bytes;      // 4 x 2 KB transposition tiles of the epilogue warps
+  uint8_t* tail = epi_tiles + 4 * 2048;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kWgMaxStages;
   uint64_t* tmem_full = empty_bar + kWgMaxStages;
@@ -213,11 +214,43 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
       tc_fence_after();
       if (dbg && threadIdx.x == 64) dbg[16] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kWgAccStride);
+      // One thread per accumulator row would store 32 bytes to each of 32 different lines per instruction (the 128 KB
+      // tile then takes ~8.8 K cycles, all of it exposed: a CTA usually has a single work item).  The rows go through
+      // an XOR-swizzled 2 KB tile private to the warp instead and leave as 64-byte row segments.  (A 4 KB tile with
+      // 128-byte segments made the kernel itself 2% faster and the step slower: with 16 KB more shared memory the
+      // blocks of the PDL-launched reduction kernel that follows no longer fit beside the running CTA.)
+      const uint32_t tb = smem_u32(epi_tiles) + (uint32_t)quarter * 2048u;      // [32 rows][64 B] per warp
+      const uint32_t xr = (uint32_t)((lane >> 1) & 3);
+      const int c16 = lane & 3, r16 = lane >> 2;          // store pattern: 4 lanes per row (16 B each), rows i*8 + lane/4
+      float* dst_w = p.partials + (((long long)split * p.ntaps + tap) * p.m_total + mt * 128 + quarter * 32) * p.n_total +
+                     nt * p.block_n + c16 * 4;
+      const int rows_left = p.m_total - (mt * 128 + quarter * 32);      // rows of this warp inside the matrix
+      uint32_t v[32], vn[32];
+      tmem_ld32(taddr + ch_lo * 32, v);
+      tmem_ld_wait();
       for (int ch = ch_lo; ch < ch_hi; ch++) {
-        uint32_t v[32];
-        tmem_ld32(taddr + ch * 32, v);
-        tmem_ld_wait();
-        if (ch == ch_hi - 1) {
+        const bool more = ch + 1 < ch_hi;
+        if (more) tmem_ld32(taddr + (ch + 1) * 32, vn);
+#pragma unroll
+        for (int half = 0; half < 2; half++) {            // 16 columns per pass keep the tile at 2 KB per warp
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+            sts128(tb + (uint32_t)lane * 64u + (((uint32_t)c ^ xr) << 4), v[16 * half + 4 * c], v[16 * half + 4 * c + 1],
+                   v[16 * half + 4 * c + 2], v[16 * half + 4 * c + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const uint32_t rr = (uint32_t)(i * 8 + r16);
+            const uint4 o = lds128(tb + rr * 64u + (((uint32_t)c16 ^ ((rr >> 1) & 3u)) << 4));
+            if ((int)rr < rows_left) stg128(dst_w + (long long)rr * p.n_total + ch * 32 + half * 16, o);
+          }
+          __syncwarp();      // the tile is rewritten by the next pass
+        }
+        if (more) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = vn[j];
+        } else {
           tc_fence_before();
           if (kPair) {
             __syncwarp();
@@ -225,10 +258,6 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
           } else {
             mbar_arrive(&tmem_empty[acc]);
           }
-        }
-        if (m < p.m_total) {
-#pragma unroll
-          for (int j = 0; j < 4; j++) st256_b32(dst + ch * 32 + 8 * j, v + 8 * j);
         }
       }
       if (dbg && threadIdx.x == 64) dbg[17] = clock64();
@@ -489,7 +518,7 @@ extern "C" int pesr_conv_wgrad(const pesr_wgrad_desc* d, int32_t* splits_out, vo
   k.a_boxes = 2;
   k.b_boxes = pair ? d->block_n / 128 : d->block_n / 64;   // per CTA
   k.stage_bytes = (k.a_boxes + k.b_boxes) * kWgBoxBytes;
-  k.stages = (227 * 1024 - 4096) / k.stage_bytes;
+  k.stages = (227 * 1024 - 4096 - 4 * 2048) / k.stage_bytes;
   if (k.stages > kWgMaxStages) k.stages = kWgMaxStages;
   k.lbo = g_dbg_lbo ? g_dbg_lbo : kWgBoxBytes;
   k.sbo = g_dbg_sbo ? g_dbg_sbo : 1024;
@@ -522,7 +551,7 @@ extern "C" int pesr_conv_wgrad(const pesr_wgrad_desc* d, int32_t* splits_out, vo
     if (r) return r;
   }
 
-  size_t smem = (size_t)k.stages * k.stage_bytes + 1024 + 256;
+  size_t smem = (size_t)k.stages * k.stage_bytes + 4 * 2048 + 1024 + 256;
   if (smem < 120 * 1024) smem = 120 * 1024;
   static bool attr_set = false;
   if (!attr_set) {

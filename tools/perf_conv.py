@@ -105,8 +105,17 @@ def gen_step(nb=16, dtype=torch.float16):
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
-    if what == "one":       # single trunk-conv shape for `ncu --set full`
+    if what == "one":       # single trunk-conv shape for `ncu --set full` (tools/ncu_full.sh): light, residual, wgrad
         conv_case(16, 256, 256, 48, 48)
+        nb, c, h, w = 16, 256, 48, 48
+        x16 = torch.randn(nb, h, w, c, device="cuda").half()
+        wp = (torch.randn(9 * c, c, device="cuda") / (3 * c ** 0.5)).half()
+        out16 = torch.empty(nb, h, w, c, device="cuda", dtype=torch.float16)
+        s32 = torch.randn(nb, h, w, c, device="cuda")
+        d = ops.make_conv_desc(dtype=0, nb=nb, h=h, w=w, cin=c, cout=c, srcs=[ops.nhwc_src(x16, nb, h, w, c)], wpacked=wp,
+                               bias=torch.randn(c, device="cuda"), alpha=0.1, res32=s32, ld_res32=c, out32=s32, ld_out32=c,
+                               out16=out16, ld_out16=c)
+        print(f"residual-stream conv: {timeit(lambda: ops.conv_igemm(d))*1e3:.1f} us")
         wgrad_case(16, 256, 256, 48, 48)
     if what == "mma":
         from pesr_b200._lib import lib

@@ -3,6 +3,8 @@
 //    model/pesr.py:53-66), on NHWC 16-bit activations with fp32/fp64 statistics;
 //  * 2x2 max-pool forward/backward (torchvision vgg19.features, model/vgg.py:10);
 //  * the skinny (batch <= 16 rows per pass) weight-streaming Linear layers of model/pesr.py:71-73.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_util.cuh"
 
@@ -533,7 +535,14 @@ static void launch_bn_reduce(const void* x16, const void* y16, long long npix, i
   if (c == 64 || c == 128 || c == 256 || c == 512) {
     const int rpp = 256 / (c / 8);
     long long bx = (npix + (long long)rpp * 8 - 1) / ((long long)rpp * 8);
-    if (bx > 148 * 4) bx = 148 * 4;
+    // two blocks per SM: measured (tools/perf_helpers.py, PESR_BN_BLOCKS) 2-4 us faster per call than 4 or 8 - every
+    // block ends with 2*c double atomics onto the same addresses
+    static int cap = -1;
+    if (cap < 0) {
+      const char* e = getenv("PESR_BN_BLOCKS");
+      cap = e ? atoi(e) : 148 * 2;
+    }
+    if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     launch_pdl(bn_reduce_vec_kernel, (unsigned)bx, 256, 0, stream, reinterpret_cast<const uint4*>(x16),
                                                           reinterpret_cast<const uint4*>(y16), npix, c, mean, rstd,

@@ -60,7 +60,6 @@ struct ConvK {
   int out_mode, out_h, out_w, out_sy, out_sx, out_oy, out_ox, out_coff, ps_c, aux_mode;
   int ksplit, b_mn_major, mn_tiles, pdl_early_b;
   double* bn_sums;   // kEpi 7: [2][cout] global accumulators
-  int staged;   // 1: epilogue through shared memory with coalesced loads and TMA stores (see the epilogue warps)
   // several K sub-blocks per pipeline stage, staged by ONE activation box + ONE weight box (TMA op count bounds the
   // small-N layers): sub_mode 1 = nsub consecutive 64-channel chunks of one tap, 2 = the three vertical taps of one
   // kernel column out of a (tile_h + 2)-row halo box
@@ -955,7 +954,6 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
     k.stage_bytes = k.a_bytes + nsub * b_tile;
     k.steps_per_tile = sub_mode == 2 ? 3 * (d->cin / kKBlock) : d->ntaps * (d->cin / kKBlock) / nsub;
   }
-  k.staged = staged ? 1 : 0;
   k.bn_sums = d->bn_sums;
   const int epi_smem = staged ? kEpiBytes : epi == 7 ? kBnEpiBytes : 0;
   const int smem_budget = 227 * 1024 - 4096 - epi_smem;

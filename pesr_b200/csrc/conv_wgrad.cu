@@ -37,7 +37,6 @@ struct WgK {
   int8_t tap_dh[PESR_MAX_TAPS], tap_dw[PESR_MAX_TAPS], tap_src[PESR_MAX_TAPS];
   float* partials;
   unsigned long long* dbg;
-  int dbg_skip;
 };
 
 // kPair: a cluster of two CTAs drives one 256 (output channels) x block_n MMA (cta_group::2); CTA r stages its own
@@ -445,7 +444,6 @@ wgrad_reduce_bias_kernel(const float* __restrict__ part, int splits, int m_total
 static int g_dbg_lbo = 0, g_dbg_sbo = 0;
 static int g_wg_pair = 1;
 static unsigned long long* g_wg_dbg = nullptr;
-static int g_wg_skip = 0;
 
 }  // namespace pesr
 
@@ -456,7 +454,7 @@ extern "C" void pesr_debug_wgrad_timeline(void* buf) { g_wg_dbg = reinterpret_ca
 
 extern "C" void pesr_debug_wgrad_desc(int lbo_bytes, int sbo_bytes) {
   if (lbo_bytes == -1) { g_wg_pair = sbo_bytes; return; }
-  if (lbo_bytes == -2) { g_wg_skip = sbo_bytes; return; }   // (-2, mode): load-skip experiment   // (-1, 0/1): disable / enable the CTA-pair kernel
+  if (lbo_bytes == -2) return;   // (-2, mode): load-skip experiment of the bring-up phase, removed
   g_dbg_lbo = lbo_bytes;
   g_dbg_sbo = sbo_bytes;
 }
@@ -529,7 +527,6 @@ extern "C" int pesr_conv_wgrad(const pesr_wgrad_desc* d, int32_t* splits_out, vo
     PESR_CHECK_ARG(d->tap_src[t] >= 0 && d->tap_src[t] < d->nsrc, "conv_wgrad: tap %d reads source %d", t, d->tap_src[t]);
   k.partials = d->partials;
   k.dbg = g_wg_dbg;
-  k.dbg_skip = g_wg_skip;
 
   WgMaps maps;
   memset(&maps, 0, sizeof(maps));

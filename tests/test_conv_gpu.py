@@ -210,3 +210,33 @@ def test_bn_statistics_epilogue(nb, cin, cout, h, w, pair_mode):
     assert float((mean.double() - yd.mean(0)).abs().max()) < 1e-5 * float(yd.abs().mean()) + 1e-6
     assert rel_l2(rstd.double(), 1.0 / torch.sqrt(yd.var(0, unbiased=False) + 1e-5)) < 1e-5
     assert float(sums.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("nb,cin,cout,h,w", [(2, 256, 256, 48, 48), (1, 128, 256, 20, 20), (2, 64, 128, 7, 5)])
+def test_wgrad_reduce_fused_with_bias_gradient(nb, cin, cout, h, w):
+    """pesr_wgrad_reduce_bias: the split-K reduction of the 3x3 weight gradient and the bias gradient (column sums of
+    dY) of the same layer in one launch, against torch's conv2d_weight / a plain sum; the call also clears the buffer
+    the next call of a chain accumulates into."""
+    from pesr_b200 import ops
+    from pesr_b200._lib import check, lib
+    dtype = torch.float16
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.randn(nb, cin, h, w, device="cuda", generator=g)
+    dy = torch.randn(nb, cout, h, w, device="cuda", generator=g)
+    dy16 = _nhwc16(dy, dtype)
+    part = torch.empty(32 * 9 * cout * cin, device="cuda")
+    d = ops.make_wgrad_desc(dtype=0, nb=nb, h=h, w=w, a=dy16, a_c=cout, m_total=cout,
+                            b_srcs=[ops.nhwc_src(_nhwc16(x, dtype), nb, h, w, cin)], n_total=cin, partials=part)
+    splits = ops.conv_wgrad(d)
+    grad = torch.empty(cout, cin, 3, 3, device="cuda")
+    bias = torch.zeros(cout, device="cuda")
+    nxt = torch.full((cout + 3,), 7.0, device="cuda")
+    scale = torch.tensor([4.0], device="cuda")
+    check(lib.pesr_wgrad_reduce_bias(part.data_ptr(), splits, 9, cout, cin, ops.WMAP_OIHW, cout, cin, 0.5, scale.data_ptr(), 0,
+                                     grad.data_ptr(), dy16.data_ptr(), nb * h * w, cout, cout, 2.0, 0, bias.data_ptr(),
+                                     nxt.data_ptr(), cout, torch.cuda.current_stream().cuda_stream), "pesr_wgrad_reduce_bias")
+    ref_w = torch.nn.grad.conv2d_weight(x.half().float(), (cout, cin, 3, 3), dy.half().float(), padding=1)
+    assert rel_l2(grad, 0.125 * ref_w) < 2e-5
+    ref_b = dy.half().double().sum(dim=(0, 2, 3)) * 0.5
+    assert float((bias.double() - ref_b).abs().max()) < 1e-5 * float(dy.half().double().abs().sum(dim=(0, 2, 3)).max())
+    assert float(nxt[:cout].abs().max()) == 0.0 and float(nxt[cout:].min()) == 7.0

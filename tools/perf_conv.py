@@ -133,15 +133,6 @@ if __name__ == "__main__":
                         a, b = out.cpu().tolist()
                         print(f"mma rate pair={pair} N={n} blocks={blocks} stages={stages}: issue {a/(iters*4):.1f} cyc/MMA, "
                               f"complete {b/(iters*4):.1f} cyc/MMA (ideal {128*n/256:.0f})", flush=True)
-    if what == "wskip":
-        from pesr_b200._lib import lib
-        lib.pesr_debug_wgrad_desc(-1, 0)
-        for sk in (0, 1, 2, 3):
-            lib.pesr_debug_wgrad_desc(-2, sk)
-            print("wgrad skip", sk)
-            wgrad_case(16, 256, 256, 48, 48)
-        lib.pesr_debug_wgrad_desc(-2, 0)
-        lib.pesr_debug_wgrad_desc(-1, 1)
     if what == "wtimeline":
         from pesr_b200._lib import lib
         buf = torch.zeros(64 + 2 * 160, dtype=torch.int64, device="cuda")
@@ -253,15 +244,6 @@ if __name__ == "__main__":
             conv_case(16, 256, 256, 48, 48)
         lib.pesr_debug_pair_mode(1)
         lib.pesr_debug_pair_mode(201)
-    if what == "skip":
-        from pesr_b200._lib import lib
-        lib.pesr_debug_pair_mode(0)
-        for sk in (0, 1, 2, 3):
-            lib.pesr_debug_pair_mode(100 + sk)
-            print("skip mode", sk, "(1 = no A loads, 2 = no B loads, 3 = neither)")
-            conv_case(16, 256, 256, 48, 48)
-            conv_case(16, 256, 1024, 96, 96)
-        lib.pesr_debug_pair_mode(100)
     if what == "pair":
         from pesr_b200._lib import lib
         for mode in (0, 2):

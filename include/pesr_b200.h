@@ -193,7 +193,9 @@ int pesr_pack_weights(const float* w_oihw, int32_t co, int32_t ci, int32_t ksize
                       int32_t dtype, void* out, void* stream);
 
 /* All packs of one network in ONE launch.  jobs_host: njobs rows of 8 int64 {src fp32 OIHW, dst 16-bit, co, ci,
- * ksize, mode, pad_to, 0}; jobs_dev: caller-owned device scratch of njobs*64 bytes, (re)filled when upload != 0. */
+ * ksize, mode, pad_to, dst2}; jobs_dev: caller-owned device scratch of njobs*64 bytes, (re)filled when upload != 0.
+ * dst2 (0 = none): for a 3x3 mode-0 / mode-2 job with co % 64 == 0 and ci % 32 == 0, the backward-data layout of the
+ * same weight (mode 1 / mode 3) written from the same read of the fp32 tensor. */
 int pesr_pack_weights_multi(const int64_t* jobs_host, int32_t njobs, void* jobs_dev, int32_t upload, int32_t dtype,
                             void* stream);
 

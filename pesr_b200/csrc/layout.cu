@@ -79,22 +79,54 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int co, int ci,
 struct PackJob {
   const float* src;
   uint16_t* dst;
+  uint16_t* dst2;     // tiled jobs: backward-data layout (mode + 1) written from the same read, or nullptr
   int co, ci, taps, mode, pad_to, rows, kdim;
-  long long total;
   int first_block;
+  int tiled;          // 1: 3x3, mode 0 / 2, co % 64 == 0, ci % 32 == 0 -> one block per 64 (out) x 32 (in) x 9 tile
 };
 __device__ __forceinline__ float pack_fetch(const float* __restrict__ w, int co, int ci, int taps, int mode, int r, int k);
-__global__ void pack_weights_multi_kernel(const PackJob* __restrict__ jobs, int njobs, int bf) {
+__global__ void __launch_bounds__(256)
+pack_weights_multi_kernel(const PackJob* __restrict__ jobs, int njobs, int bf) {
   int lo = 0, hi = njobs - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
     if (jobs[mid].first_block <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
   }
   const PackJob j = jobs[lo];
+  if (j.tiled) {
+    // OIHW reads with one thread per packed element are strided by 9 floats (forward layout) or by 9*ci floats
+    // (backward layout): 1.4 TB/s.  Here a block reads 64 x (32 x 9) contiguous floats, keeps the tile in shared
+    // memory as 16-bit values and writes BOTH operand layouts in 64 / 128-byte runs.
+    __shared__ uint16_t tile[9][64][34];
+    const int tiles_i = j.ci >> 5;
+    const int tb = (int)blockIdx.x - j.first_block;
+    const int op0 = (tb / tiles_i) * 64, i0 = (tb % tiles_i) * 32;
+    const int c_ps = j.co >> 2;
+    for (int idx = threadIdx.x; idx < 64 * 288; idx += 256) {
+      const int op_l = idx / 288, rem = idx - op_l * 288;
+      const int i_l = rem / 9, t = rem - i_l * 9;
+      const int op = op0 + op_l;
+      const int o = j.mode == 2 ? (op % c_ps) * 4 + op / c_ps : op;      // packed PixelShuffle order -> OIHW row
+      tile[t][op_l][i_l] = from_f32(j.src[((long long)o * j.ci + i0) * 9 + rem], bf);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 9 * 64 * 32; idx += 256) {          // forward: [tap][out][in], in fastest
+      const int i_l = idx & 31, op_l = (idx >> 5) & 63, t = idx >> 11;
+      j.dst[((long long)t * j.co + op0 + op_l) * j.ci + i0 + i_l] = tile[t][op_l][i_l];
+    }
+    if (j.dst2) {
+      for (int idx = threadIdx.x; idx < 9 * 32 * 64; idx += 256) {        // backward: [8 - tap][in][out], out fastest
+        const int op_l = idx & 63, i_l = (idx >> 6) & 31, t = idx >> 11;
+        j.dst2[((long long)(8 - t) * j.ci + i0 + i_l) * j.co + op0 + op_l] = tile[t][op_l][i_l];
+      }
+    }
+    return;
+  }
+  const long long total = (long long)j.rows * j.kdim;
   const long long base = (long long)((int)blockIdx.x - j.first_block) * 4096;
   for (int t = threadIdx.x; t < 4096; t += blockDim.x) {
     const long long idx = base + t;
-    if (idx >= j.total) break;
+    if (idx >= total) break;
     const int k = (int)(idx % j.kdim), r = (int)(idx / j.kdim);
     j.dst[idx] = from_f32(pack_fetch(j.src, j.co, j.ci, j.taps, j.mode, r, k), bf);
   }
@@ -489,7 +521,7 @@ extern "C" int pesr_pack_weights(const float* w, int32_t co, int32_t ci, int32_t
   return 0;
 }
 
-// jobs_host: njobs rows of 8 int64 {src, dst, co, ci, ksize, mode, pad_to, unused}; jobs_dev: device scratch of
+// jobs_host: njobs rows of 8 int64 {src, dst, co, ci, ksize, mode, pad_to, dst2}; jobs_dev: device scratch of
 // njobs * 64 bytes that the call fills (kept by the caller so that repeated calls can skip the upload).
 extern "C" int pesr_pack_weights_multi(const int64_t* jobs_host, int32_t njobs, void* jobs_dev, int32_t upload,
                                        int32_t dtype, void* stream_) {
@@ -503,6 +535,7 @@ extern "C" int pesr_pack_weights_multi(const int64_t* jobs_host, int32_t njobs, 
     PackJob j;
     j.src = reinterpret_cast<const float*>(r[0]);
     j.dst = reinterpret_cast<uint16_t*>(r[1]);
+    j.dst2 = reinterpret_cast<uint16_t*>(r[7]);
     j.co = (int)r[2]; j.ci = (int)r[3];
     const int ksize = (int)r[4];
     j.taps = ksize * ksize; j.mode = (int)r[5]; j.pad_to = (int)r[6];
@@ -515,9 +548,12 @@ extern "C" int pesr_pack_weights_multi(const int64_t* jobs_host, int32_t njobs, 
       case 6: j.rows = j.pad_to; j.kdim = j.co; break;
       default: j.rows = j.ci; j.kdim = j.pad_to; break;
     }
-    j.total = (long long)j.rows * j.kdim;
+    j.tiled = (ksize == 3 && (j.mode == 0 || j.mode == 2) && j.co % 64 == 0 && j.ci % 32 == 0) ? 1 : 0;
+    PESR_CHECK_ARG(j.dst2 == nullptr || j.tiled,
+                   "pack_weights_multi: job %d: a companion backward layout needs a 3x3 mode-0/2 job with co %% 64 == 0, "
+                   "ci %% 32 == 0", i);
     j.first_block = nblocks;
-    nblocks += (int)((j.total + 4095) / 4096);
+    nblocks += j.tiled ? (j.co / 64) * (j.ci / 32) : (int)(((long long)j.rows * j.kdim + 4095) / 4096);
     jobs[i] = j;
   }
   if (upload) {

@@ -66,6 +66,7 @@ def _run_conv(desc, stream):
 
 
 _FUSE_BIAS = os.environ.get("PESR_NO_FUSED_BIAS") != "1"    # A/B knob (tools/ab_env.sh)
+_DUAL_PACK = os.environ.get("PESR_NO_DUAL_PACK") != "1"     # A/B knob: forward + backward weight layouts in one pass
 
 
 class GeneratorEngine:
@@ -113,9 +114,13 @@ class GeneratorEngine:
         pk["up4_f"] = PackedWeight(g.upsample[4].weight, 5, dt, pad_to=32)
         pk["up4_d"] = PackedWeight(g.upsample[4].weight, 7, dt, pad_to=64)
         self.packed = pk
+        # one launch packs the forward operands and, from the same read of each fp32 weight, the backward-data
+        # operands of the 3x3 layers; the remaining backward packs (embed / last conv, GEMM layouts) run before backward
         self.fwd_packs = [v for k, v in pk.items() if k.endswith("_f")]
-        self.bwd_packs = [v for k, v in pk.items() if k.endswith("_d")]
-        self.fwd_multi = ops.MultiPack(self.fwd_packs, device, dt)
+        comp = [pk[k[:-2] + "_d"] if (v.mode in (0, 2) and _DUAL_PACK) else None for k, v in pk.items() if k.endswith("_f")]
+        paired = {id(c) for c in comp if c is not None}
+        self.bwd_packs = [v for k, v in pk.items() if k.endswith("_d") and id(v) not in paired]
+        self.fwd_multi = ops.MultiPack(self.fwd_packs, device, dt, companions=comp)
         self.bwd_multi = ops.MultiPack(self.bwd_packs, device, dt)
         self.scale_ws = torch.zeros(4, device=device, dtype=torch.float32)
         C_ = g.n_feats

@@ -321,15 +321,27 @@ def unflatten_nchw16(src32, mask16, nb, hw, c, dst16, mul=1.0, mul_dev=None, slo
 
 
 class MultiPack:
-    """All weight packs of one network as one launch (re-run only when a parameter version changed)."""
+    """All weight packs of one network as one launch (re-run only when a parameter version changed).
 
-    def __init__(self, packed_weights, device, dtype):
+    ``companions``: optional list parallel to ``packed_weights`` holding, per forward pack (mode 0 / 2), the
+    backward-data pack (mode 1 / 3) of the same parameter or None: both layouts are then written from one read of
+    the fp32 tensor (pesr_pack_weights_multi's dst2)."""
+
+    def __init__(self, packed_weights, device, dtype, companions=None):
         import numpy as np
         self.pws = list(packed_weights)
+        self.companions = list(companions) if companions is not None else [None] * len(self.pws)
         rows = []
-        for pw in self.pws:
+        for pw, cw in zip(self.pws, self.companions):
             p = pw.param
-            rows.append([p.data_ptr(), pw.buf.data_ptr(), p.shape[0], p.shape[1], p.shape[2], pw.mode, pw.pad_to, 0])
+            if cw is not None:
+                ok = (cw.param is p and cw.mode == pw.mode + 1 and pw.mode in (0, 2) and p.shape[2] == 3
+                      and p.shape[0] % 64 == 0 and p.shape[1] % 32 == 0)
+                if not ok:
+                    raise ValueError("MultiPack: companion must be the mode+1 pack of the same 3x3 parameter "
+                                     "(out channels % 64 == 0, in channels % 32 == 0)")
+            rows.append([p.data_ptr(), pw.buf.data_ptr(), p.shape[0], p.shape[1], p.shape[2], pw.mode, pw.pad_to,
+                         cw.buf.data_ptr() if cw is not None else 0])
         self.host = np.ascontiguousarray(np.array(rows, dtype=np.int64))
         self.dev = torch.empty(len(rows) * 64, device=device, dtype=torch.uint8)
         self.dt = dt_code(dtype)
@@ -344,5 +356,7 @@ class MultiPack:
                                           0 if self.uploaded else 1, self.dt, _stream()), "pesr_pack_weights_multi")
         self.uploaded = True
         self.key = key
-        for pw, v in zip(self.pws, key):
+        for pw, cw, v in zip(self.pws, self.companions, key):
             pw.key = (pw.param.data_ptr(), v)
+            if cw is not None:
+                cw.key = (cw.param.data_ptr(), v)

@@ -240,3 +240,23 @@ def test_wgrad_reduce_fused_with_bias_gradient(nb, cin, cout, h, w):
     ref_b = dy.half().double().sum(dim=(0, 2, 3)) * 0.5
     assert float((bias.double() - ref_b).abs().max()) < 1e-5 * float(dy.half().double().abs().sum(dim=(0, 2, 3)).max())
     assert float(nxt[:cout].abs().max()) == 0.0 and float(nxt[cout:].min()) == 7.0
+
+
+@pytest.mark.parametrize("co,ci,mode", [(256, 256, 0), (1024, 256, 2), (64, 64, 0), (128, 96, 0)])
+def test_multi_pack_writes_both_layouts_from_one_read(co, ci, mode):
+    """pesr_pack_weights_multi with a companion destination (tiled kernel): forward layout (mode 0 / 2) and
+    backward-data layout (mode 1 / 3) bit-identical to the single-job packs."""
+    from pesr_b200 import ops
+    from pesr_b200.engine_g import PackedWeight
+    g = torch.Generator(device="cuda").manual_seed(co + ci + mode)
+    w = torch.nn.Parameter(torch.randn(co, ci, 3, 3, device="cuda", generator=g))
+    for dtype in (torch.float16, torch.bfloat16):
+        f, b = PackedWeight(w, mode, dtype), PackedWeight(w, mode + 1, dtype)
+        f.buf.fill_(9.0), b.buf.fill_(9.0)
+        ops.MultiPack([f], w.device, dtype, companions=[b]).run()
+        ref_f = torch.empty_like(f.buf)
+        ref_b = torch.empty_like(b.buf)
+        ops.pack_weights(w.detach(), mode, ref_f)
+        ops.pack_weights(w.detach(), mode + 1, ref_b)
+        assert torch.equal(f.buf, ref_f) and torch.equal(b.buf, ref_b)
+        assert b.key == (w.data_ptr(), w._version)

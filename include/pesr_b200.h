@@ -209,7 +209,9 @@ int pesr_pack_weights_multi(const int64_t* jobs_host, int32_t njobs, void* jobs_
  * MeanShift, model/basic.py:9-17, composes with the zero padding of the following conv); A/b NULL =
  * identity.  pad_affine = 1 instead applies the affine to the padded zeros too (out-of-image taps read b): a
  * constant shift of the conv input, used to centre the 0..255 image ahead of the Discriminator's first
- * conv + BatchNorm (which is invariant to it).  mul_dev: optional device scalar multiplied into the result.
+ * conv + BatchNorm (which is invariant to it).  pad_affine bit 1 (value 2): columns 32..63 of `col` already hold zeros
+ * (a buffer that is zeroed once and reused) and are not written, which halves the bytes stored.
+ * mul_dev: optional device scalar multiplied into the result.
  * Feeds the Cin=3 convs (model/pesr.py:23,54; vgg19.features[0]) and, with sgn=-1, the backward of
  * the Cout=3 conv (model/basic.py:60). */
 int pesr_im2col3(const float* src_nchw, int32_t nb, int32_t h, int32_t w, const float* affine_a,

@@ -169,9 +169,17 @@ __global__ void im2col3_kernel(const float* __restrict__ src, int nb, int h, int
        idx += (long long)gridDim.x * blockDim.x) {
     const int q = (int)(idx & 3);
     const long long p = idx >> 2;
-    const int x = (int)(p % w);
-    const int y = (int)((p / w) % h);
-    const int n = (int)(p / plane);
+    int x, y, n;
+    if (total < (1ll << 31)) {      // 32-bit divisions: the 64-bit ones were a third of this kernel's instructions
+      const unsigned pu = (unsigned)p, wu = (unsigned)w, r = pu / wu;
+      x = (int)(pu - r * wu);
+      n = (int)(r / (unsigned)h);
+      y = (int)(r - (unsigned)n * (unsigned)h);
+    } else {
+      x = (int)(p % w);
+      y = (int)((p / w) % h);
+      n = (int)(p / plane);
+    }
     const float* base = src + (long long)n * 3 * plane;
     float vals[8];
 #pragma unroll
@@ -187,7 +195,7 @@ __global__ void im2col3_kernel(const float* __restrict__ src, int nb, int h, int
         v0 = (A[0] * s0 + A[1] * s1 + A[2] * s2 + B[0]) * mul;
         v1 = (A[3] * s0 + A[4] * s1 + A[5] * s2 + B[1]) * mul;
         v2 = (A[6] * s0 + A[7] * s1 + A[8] * s2 + B[2]) * mul;
-      } else if (pad_affine) {  // the affine of a zero-padded pixel (a constant shift of the conv input)
+      } else if (pad_affine & 1) {  // the affine of a zero-padded pixel (a constant shift of the conv input)
         v0 = B[0] * mul; v1 = B[1] * mul; v2 = B[2] * mul;
       }
       const int kb = tap * 3 - k0;  // column of channel 0 of this tap, relative to the chunk
@@ -205,7 +213,7 @@ __global__ void im2col3_kernel(const float* __restrict__ src, int nb, int h, int
     o.z = pack2(vals[4], vals[5], bf);
     o.w = pack2(vals[6], vals[7], bf);
     col[p * 8 + q] = o;
-    col[p * 8 + 4 + q] = make_uint4(0, 0, 0, 0);
+    if (!(pad_affine & 2)) col[p * 8 + 4 + q] = make_uint4(0, 0, 0, 0);   // bit 1: columns 32..63 are already zero
   }
 }
 
@@ -230,9 +238,17 @@ __global__ void col2im3_kernel(const float* __restrict__ z, int ldz, int nb, int
   if (bias) { b0 = __ldg(bias); b1 = __ldg(bias + 1); b2 = __ldg(bias + 2); }
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
        p += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(p % w);
-    const int y = (int)((p / w) % h);
-    const int n = (int)(p / plane);
+    int x, y, n;
+    if (total < (1ll << 31)) {
+      const unsigned pu = (unsigned)p, wu = (unsigned)w, r = pu / wu;
+      x = (int)(pu - r * wu);
+      n = (int)(r / (unsigned)h);
+      y = (int)(r - (unsigned)n * (unsigned)h);
+    } else {
+      x = (int)(p % w);
+      y = (int)((p / w) % h);
+      n = (int)(p / plane);
+    }
     float s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
     for (int tap = 0; tap < 9; tap++) {

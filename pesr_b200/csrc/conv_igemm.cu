@@ -480,7 +480,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; j++) v[j] = vn[j];
-          } else {
+          } else if (tile + 2 * nworkers < p.num_tiles) {
+            // hand the accumulator back - only if this CTA will use it again: the cluster-scope release of the arrive
+            // waits for the epilogue's outstanding global stores (~1.5 K cycles on the exposed last tile)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
@@ -542,7 +544,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       if (dbg && et == 0) dbg[16 + (tile == worker ? 0 : 4)] = clock64();       // accumulator complete (MMAs done)
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccStride);
 
-      if (ch_lo == ch_hi) {   // nothing to drain (block_n == 32, upper half): still release the accumulator
+      const bool acc_reused = tile + 2 * nworkers < p.num_tiles;      // see the staged epilogue: skip the release otherwise
+      if (ch_lo == ch_hi && acc_reused) {   // nothing to drain (block_n == 32, upper half): still release the accumulator
         tc_fence_before();
         if (kPair) {
           __syncwarp();
@@ -705,7 +708,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
           if (stamp) dbg[43] = clock64();   // next chunk's TMEM load complete
 #pragma unroll
           for (int j = 0; j < 32; j++) v[j] = vn[j];
-        } else {
+        } else if (acc_reused) {
           // every accumulator column of this row has been read: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           if (kPair) {

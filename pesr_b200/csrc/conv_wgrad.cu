@@ -249,7 +249,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j++) v[j] = vn[j];
-        } else {
+        } else if (item + 2 * nworkers < p.num_items) {      // the accumulator is only handed back if it is used again
           tc_fence_before();
           if (kPair) {
             __syncwarp();

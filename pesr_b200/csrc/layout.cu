@@ -97,27 +97,36 @@ pack_weights_multi_kernel(const PackJob* __restrict__ jobs, int njobs, int bf) {
     // OIHW reads with one thread per packed element are strided by 9 floats (forward layout) or by 9*ci floats
     // (backward layout): 1.4 TB/s.  Here a block reads 64 x (32 x 9) contiguous floats, keeps the tile in shared
     // memory as 16-bit values and writes BOTH operand layouts in 64 / 128-byte runs.
-    __shared__ uint16_t tile[9][64][34];
+    // [tap][out][in] as 16-bit values; row stride 34 and plane stride 2178 halves keep the transposed accesses below
+    // off the same bank (a plane stride of 64*34 halves is a multiple of 32 words: 9-way conflicts on the fill)
+    constexpr int kRow = 34, kPlane = 64 * 34 + 2;
+    __shared__ __align__(16) uint16_t tile[9 * kPlane];
     const int tiles_i = j.ci >> 5;
     const int tb = (int)blockIdx.x - j.first_block;
     const int op0 = (tb / tiles_i) * 64, i0 = (tb % tiles_i) * 32;
     const int c_ps = j.co >> 2;
-    for (int idx = threadIdx.x; idx < 64 * 288; idx += 256) {
-      const int op_l = idx / 288, rem = idx - op_l * 288;
-      const int i_l = rem / 9, t = rem - i_l * 9;
+    for (int op_l = threadIdx.x >> 5; op_l < 64; op_l += 8) {            // one warp per OIHW row: 288 contiguous floats
       const int op = op0 + op_l;
-      const int o = j.mode == 2 ? (op % c_ps) * 4 + op / c_ps : op;      // packed PixelShuffle order -> OIHW row
-      tile[t][op_l][i_l] = from_f32(j.src[((long long)o * j.ci + i0) * 9 + rem], bf);
+      const int o = j.mode == 2 ? (op % c_ps) * 4 + op / c_ps : op;       // packed PixelShuffle order -> OIHW row
+      const float* row = j.src + ((long long)o * j.ci + i0) * 9;
+      for (int rem = threadIdx.x & 31; rem < 288; rem += 32) {
+        const int i_l = rem / 9, t = rem - i_l * 9;
+        tile[t * kPlane + op_l * kRow + i_l] = from_f32(row[rem], bf);
+      }
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < 9 * 64 * 32; idx += 256) {          // forward: [tap][out][in], in fastest
-      const int i_l = idx & 31, op_l = (idx >> 5) & 63, t = idx >> 11;
-      j.dst[((long long)t * j.co + op0 + op_l) * j.ci + i0 + i_l] = tile[t][op_l][i_l];
+    uint32_t* dst32 = reinterpret_cast<uint32_t*>(j.dst);
+    for (int idx = threadIdx.x; idx < 9 * 64 * 16; idx += 256) {          // forward: [tap][out][in], in fastest (pairs)
+      const int ip = idx & 15, op_l = (idx >> 4) & 63, t = idx >> 10;
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(&tile[t * kPlane + op_l * kRow + 2 * ip]);
+      dst32[(((long long)t * j.co + op0 + op_l) * j.ci + i0) / 2 + ip] = v;
     }
     if (j.dst2) {
-      for (int idx = threadIdx.x; idx < 9 * 32 * 64; idx += 256) {        // backward: [8 - tap][in][out], out fastest
-        const int op_l = idx & 63, i_l = (idx >> 6) & 31, t = idx >> 11;
-        j.dst2[((long long)(8 - t) * j.ci + i0 + i_l) * j.co + op0 + op_l] = tile[t][op_l][i_l];
+      uint32_t* d2 = reinterpret_cast<uint32_t*>(j.dst2);
+      for (int idx = threadIdx.x; idx < 9 * 32 * 32; idx += 256) {        // backward: [8 - tap][in][out], out fastest (pairs)
+        const int opp = idx & 31, i_l = (idx >> 5) & 31, t = idx >> 10;
+        const uint32_t lo = tile[t * kPlane + (2 * opp) * kRow + i_l], hi = tile[t * kPlane + (2 * opp + 1) * kRow + i_l];
+        d2[(((long long)(8 - t) * j.ci + i0 + i_l) * j.co + op0) / 2 + opp] = lo | (hi << 16);
       }
     }
     return;

@@ -1,0 +1,81 @@
+"""In-stream cost of the split-K reduction (+ bias gradient) that follows every wgrad launch: time a chain of
+[wgrad -> reduce] pairs with ONE event pair and subtract the wgrad-only chain (partials stay L2-hot, PDL active)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pesr_b200 import ops  # noqa: E402
+from pesr_b200._lib import check, lib  # noqa: E402
+
+nb, c, h, w = 16, 256, 48, 48
+dy16 = torch.randn(nb, h, w, c, device="cuda").half()
+x16 = torch.randn(nb, h, w, c, device="cuda").half()
+part = torch.empty(32 * 9 * c * c, device="cuda")
+d = ops.make_wgrad_desc(dtype=0, nb=nb, h=h, w=w, a=dy16, a_c=c, m_total=c, b_srcs=[ops.nhwc_src(x16, nb, h, w, c)], n_total=c,
+                        partials=part)
+grad = torch.empty(c, c, 3, 3, device="cuda")
+bias = torch.zeros(c, device="cuda")
+scale = torch.ones(1, device="cuda")
+st = torch.cuda.current_stream().cuda_stream
+
+
+def chain(mode, n=40):
+    for _ in range(n):
+        splits = ops.conv_wgrad(d)
+        if mode == 1:
+            check(lib.pesr_wgrad_reduce_bias(part.data_ptr(), splits, 9, c, c, 0, c, c, 1.0, scale.data_ptr(), 0, grad.data_ptr(),
+                                             dy16.data_ptr(), nb * h * w, c, c, 1.0, 0, bias.data_ptr(), bias.data_ptr(), c, st), "rb")
+        elif mode == 2:
+            ops.wgrad_reduce(part, splits, 9, c, c, 0, c, c, grad, div_dev=scale)
+        elif mode == 3:
+            ops.wgrad_reduce(part, splits, 9, c, c, 0, c, c, grad, div_dev=scale)
+            ops.colsum16(dy16, nb * h * w, c, c, bias, div_dev=scale)
+
+
+def timed(mode, n=40):
+    chain(mode, 5)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    chain(mode, n)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+
+
+base = timed(0)
+print(f"wgrad only: {base:.1f} us per launch")
+for mode, name in ((1, "wgrad + reduce_bias"), (2, "wgrad + reduce"), (3, "wgrad + reduce + colsum")):
+    t = timed(mode)
+    print(f"{name}: {t:.1f} us per pair -> helper costs {t - base:.1f} us in-stream")
+
+
+def chain_time(fn, n=40):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+
+
+print("BatchNorm kernels, back-to-back on L2-hot data (per call):")
+for npix, cc in ((16 * 192 * 192, 64), (16 * 96 * 96, 64), (16 * 96 * 96, 128), (16 * 48 * 48, 256), (16 * 24 * 24, 512), (16 * 12 * 12, 512)):
+    y = torch.randn(npix, cc, device="cuda").half()
+    dz = torch.randn(npix, cc, device="cuda").half()
+    a = torch.empty_like(y)
+    ws = torch.zeros(2 * cc, device="cuda", dtype=torch.float64)
+    mean, rstd = torch.zeros(cc, device="cuda"), torch.ones(cc, device="cuda")
+    gam, bet = torch.ones(cc, device="cuda"), torch.zeros(cc, device="cuda")
+    dg, db = torch.zeros(cc, device="cuda"), torch.zeros(cc, device="cuda")
+    t1 = chain_time(lambda: ops.bn_stats(y, npix, cc, ws, mean, rstd))
+    t2 = chain_time(lambda: ops.bn_lrelu_fwd(y, npix, cc, mean, rstd, gam, bet, a))
+    t3 = chain_time(lambda: ops.bn_lrelu_bwd(dz, y, npix, cc, mean, rstd, gam, ws, a, dg, db))
+    mb = npix * cc * 2 / 1e6
+    print(f"  {npix}x{cc} ({mb:.0f} MB): stats {t1:.1f} us, apply {t2:.1f} us, backward {t3:.1f} us")

@@ -79,3 +79,30 @@ for npix, cc in ((16 * 192 * 192, 64), (16 * 96 * 96, 64), (16 * 96 * 96, 128), 
     t3 = chain_time(lambda: ops.bn_lrelu_bwd(dz, y, npix, cc, mean, rstd, gam, ws, a, dg, db))
     mb = npix * cc * 2 / 1e6
     print(f"  {npix}x{cc} ({mb:.0f} MB): stats {t1:.1f} us, apply {t2:.1f} us, backward {t3:.1f} us")
+
+print("trunk conv variants, back-to-back chains of 40 launches (PDL on), per launch:")
+xa = torch.randn(nb, h, w, c, device="cuda").half()
+xb = torch.empty_like(xa)
+wp = (torch.randn(9 * c, c, device="cuda") / (3 * c ** 0.5)).half()
+bias_c = torch.randn(c, device="cuda")
+s32 = torch.randn(nb, h, w, c, device="cuda")
+src_a, src_b = [ops.nhwc_src(xa, nb, h, w, c)], [ops.nhwc_src(xb, nb, h, w, c)]
+mk = ops.make_conv_desc
+light = [mk(dtype=0, nb=nb, h=h, w=w, cin=c, cout=c, srcs=src_a, wpacked=wp, bias=bias_c, act=1, out16=xb, ld_out16=c),
+         mk(dtype=0, nb=nb, h=h, w=w, cin=c, cout=c, srcs=src_b, wpacked=wp, bias=bias_c, act=1, out16=xa, ld_out16=c)]
+resid = [mk(dtype=0, nb=nb, h=h, w=w, cin=c, cout=c, srcs=src_a, wpacked=wp, bias=bias_c, alpha=0.1, res32=s32, ld_res32=c,
+            out32=s32, ld_out32=c, out16=xb, ld_out16=c),
+         mk(dtype=0, nb=nb, h=h, w=w, cin=c, cout=c, srcs=src_b, wpacked=wp, bias=bias_c, alpha=0.1, res32=s32, ld_res32=c,
+            out32=s32, ld_out32=c, out16=xa, ld_out16=c)]
+mask = [mk(dtype=0, nb=nb, h=h, w=w, cin=c, cout=c, srcs=src_a, wpacked=wp, mask16=dy16, ld_mask16=c, mask_mode=1, out16=xb,
+           ld_out16=c),
+        mk(dtype=0, nb=nb, h=h, w=w, cin=c, cout=c, srcs=src_b, wpacked=wp, mask16=dy16, ld_mask16=c, mask_mode=1, out16=xa,
+           ld_out16=c)]
+fl = 2.0 * nb * h * w * c * c * 9
+for name, pair in (("light (bias+relu -> fp16)", light), ("residual (fp32 stream)", resid), ("mask (dgrad * relu')", mask)):
+    def two():
+        ops.conv_igemm(pair[0])
+        ops.conv_igemm(pair[1])
+    t = chain_time(two, 20) / 2
+    print(f"  {name}: {t:.1f} us ({fl / t / 1e6:.0f} TFLOP/s)")
+    xa.normal_()

@@ -6,7 +6,7 @@
     torchrun --nproc-per-node 8 train.py ...                      # one process per GPU (replaces nn.DataParallel)
 
 Additions to the reference's flags: --synthetic (random tensors instead of data/, for machines without the
-dataset), --max_iters, --log_every.  The dataset / tensorboard / validation plumbing of the reference is out of the
+dataset), --max_iters, --log_every, --vgg_random.  The dataset / tensorboard / validation plumbing of the reference is out of the
 hot path's scope; a minimal PNG-folder dataset with the reference's directory layout is
 provided so that the script is usable end to end.
 """
@@ -57,6 +57,8 @@ parser.add_argument('--alpha_tv', type=float, default=1e-6)
 parser.add_argument('--alpha_l1', type=float, default=0)
 parser.add_argument('--synthetic', action='store_true', help='random patches instead of data/origin/train/<dataset>')
 parser.add_argument('--max_iters', type=int, default=0, help='stop an epoch after this many iterations (0 = full epoch)')
+parser.add_argument('--vgg_random', action='store_true', help='random-init VGG19 instead of torchvision\'s ImageNet '
+                    'checkpoint (machines without network access)')
 parser.add_argument('--log_every', type=int, default=50)
 
 
@@ -134,7 +136,7 @@ def main():
     gan = args.phase != 'pretrain'
     if gan:
         D = DataParallel(Discriminator(opt).to(device))
-        vgg = VGG().to(device)
+        vgg = VGG(pretrained=not args.vgg_random).to(device)
         optim_D = Adam(D.parameters(), betas=(0.9, 0.999), lr=args.learning_rate)
         sched_D = torch.optim.lr_scheduler.StepLR(optim_D, step_size=args.lr_step, gamma=0.5)
         cfg = dict(alpha_l1=args.alpha_l1, alpha_vgg=args.alpha_vgg, alpha_gan=args.alpha_gan, alpha_tv=args.alpha_tv,

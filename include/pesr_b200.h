@@ -127,6 +127,9 @@ int pesr_debug_mma_rate(int32_t n, int32_t iters, int32_t stages, int32_t pair_a
                         unsigned long long* out_dev, void* stream);
 /* Bring-up hook: device buffer (64 x uint64) that block 0 of each pesr_conv_igemm launch fills with clock64 stamps. */
 void pesr_debug_timeline(void* buf);
+/* Probe: n_ctas CTAs that each pin one SM (200 KB of shared memory) and spin for usec microseconds on `stream`:
+ * what do a few unavailable SMs (a concurrent NCCL all-reduce) cost the one-CTA-per-SM kernels? (tools/sm_hog_probe.py) */
+int pesr_debug_sm_hog(int32_t n_ctas, int64_t usec, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Backward-filter as a split-K GEMM with both operands MN-major (pixels are K).

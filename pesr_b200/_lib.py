@@ -94,6 +94,7 @@ SIGNATURES = {
     "pesr_debug_timeline": (None, [_vp]),
     "pesr_debug_wgrad_timeline": (None, [_vp]),
     "pesr_debug_mma_rate": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "pesr_debug_sm_hog": (C.c_int, [_i32, _i64, _vp]),
     "pesr_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), C.POINTER(_i32), _vp]),
     "pesr_debug_wgrad_desc": (None, [C.c_int, C.c_int]),
     "pesr_wgrad_reduce": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp, _vp]),

@@ -84,3 +84,34 @@ extern "C" int pesr_debug_mma_rate(int32_t n, int32_t iters, int32_t stages, int
   PESR_CHECK_LAUNCH("mma_rate");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// SM-hog probe: n CTAs that each pin one SM (200 KB of dynamic shared memory: nothing of ours fits beside them) and
+// spin for `usec` microseconds.  Used by tools/sm_hog_probe.py to measure what a few unavailable SMs - e.g. the CTAs of
+// a concurrent NCCL all-reduce - cost the persistent one-CTA-per-SM kernels with their static tile assignment.
+// ------------------------------------------------------------------------------------------
+namespace pesr {
+__global__ void sm_hog_kernel(unsigned long long nsec) {
+  extern __shared__ uint8_t hog_smem[];
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    __nanosleep(2000);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < nsec);
+  if (nsec == 0) hog_smem[0] = 1;
+}
+}  // namespace pesr
+
+extern "C" int pesr_debug_sm_hog(int32_t n_ctas, int64_t usec, void* stream_) {
+  using namespace pesr;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(sm_hog_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  sm_hog_kernel<<<n_ctas, 32, 200 * 1024, stream>>>((unsigned long long)usec * 1000ull);
+  PESR_CHECK_LAUNCH("debug_sm_hog");
+  return 0;
+}

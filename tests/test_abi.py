@@ -72,3 +72,19 @@ def test_state_dict_surface_matches_reference_keys(L):
     for k, v in G.state_dict().items():
         assert torch.equal(v, sd[k]), k        # same construction order => same seeded init as the reference
     assert all(p.requires_grad for p in G.parameters())   # MeanShift stays trainable, model/basic.py:17
+
+
+def test_pick_tile_covers_128_pixels_and_prefers_unpadded_tiles():
+    """Host-side tile choice of the implicit-GEMM kernel (pure Python): every tile is 128 pixels; one image per tile
+    unless that pads > 20% of the MMA rows and the layer is wide enough for multi-chunk stages."""
+    from pesr_b200 import ops
+    for h, w, nb, cin in [(48, 48, 16, 256), (96, 96, 16, 128), (192, 192, 16, 64), (24, 24, 16, 512), (12, 12, 16, 512),
+                          (12, 12, 3, 128), (6, 6, 5, 256), (7, 5, 2, 64), (339, 510, 1, 256), (1, 1, 3, 64), (20, 20, 1, 128)]:
+        tn, th, tw = ops.pick_tile(h, w, nb, cin)
+        assert tn * th * tw == 128 and tn >= 1 and th >= 1 and tw >= 4
+        assert tn == 1 or (cin >= 128 and tn <= nb)
+    assert ops.pick_tile(48, 48, 16, 256) == (1, 8, 16)          # G trunk: exact, halo stages stay available
+    assert ops.pick_tile(24, 24, 16, 512) == (2, 8, 8)           # 25% padding as 8x16 -> two images per tile
+    assert ops.pick_tile(12, 12, 16, 512) == (8, 4, 4)           # 44% padding as 16x8 -> eight images per tile
+    assert ops.pick_tile(24, 24, 16, 64) == (1, 16, 8)           # narrow layers keep one image per tile
+    assert ops.pick_tile(339, 510, 1, 256) == (1, 8, 16)

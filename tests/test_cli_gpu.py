@@ -27,3 +27,30 @@ def test_train_py_pretrain_then_gan(tmp_path):
                ROOT)
     assert "Finish train [1/1]" in out and "Total G" in out
     assert (tmp_path / "ck" / "train" / "model_1.pt").exists()
+
+
+def test_test_py_writes_x4_images(tmp_path):
+    """test.py end to end (test.py:101-112): two random LR PNGs, random tiny checkpoints, alpha blend with the x8
+    self-ensemble of the PSNR model; the outputs are x4 PNGs."""
+    import numpy as np
+    import torch
+    from PIL import Image
+    from pesr_b200.model import Generator
+    lr_dir = tmp_path / "data" / "origin" / "test" / "Tiny" / "LR"
+    lr_dir.mkdir(parents=True)
+    rng = np.random.RandomState(0)
+    for name, (h, w) in (("a.png", (24, 20)), ("b.png", (17, 33))):
+        Image.fromarray(rng.randint(0, 256, size=(h, w, 3), dtype=np.uint8)).save(lr_dir / name)
+    opt = {'num_channels': 64, 'depth': 2, 'res_scale': 0.1}
+    for i, name in enumerate(("perc.pt", "psnr.pt")):
+        torch.manual_seed(i)
+        torch.save(Generator(opt).state_dict(), tmp_path / name)
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "test.py"), "--dataset", "Tiny", "--num_channels", "64",
+                        "--num_blocks", "2", "--perceptual_model", str(tmp_path / "perc.pt"), "--psnr_model",
+                        str(tmp_path / "psnr.pt"), "--alpha", "0.5", "--save_path", str(tmp_path / "out")],
+                       cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    for name, (h, w) in (("a.png", (24, 20)), ("b.png", (17, 33))):
+        out = np.asarray(Image.open(tmp_path / "out" / "Tiny" / name))
+        assert out.shape == (4 * h, 4 * w, 3) and out.dtype == np.uint8

@@ -120,16 +120,16 @@ typedef struct pesr_conv_desc {
 } pesr_conv_desc;
 
 int pesr_conv_igemm(const pesr_conv_desc* d, void* stream);
-/* A/B hook: 0 = never use the CTA-pair (cta_group::2) kernel, 1 = whenever legal (default), -1 = re-read PESR_NO_PAIR. */
-void pesr_debug_pair_mode(int mode);
-/* Bring-up microbenchmark: issue / completion cycles of iters*4 back-to-back tcgen05.mma (M=128 or pair 256, N=n). */
-int pesr_debug_mma_rate(int32_t n, int32_t iters, int32_t stages, int32_t pair_and_major, int32_t blocks,
-                        unsigned long long* out_dev, void* stream);
-/* Bring-up hook: device buffer (64 x uint64) that block 0 of each pesr_conv_igemm launch fills with clock64 stamps. */
-void pesr_debug_timeline(void* buf);
-/* Probe: n_ctas CTAs that each pin one SM (200 KB of shared memory) and spin for usec microseconds on `stream`:
- * what do a few unavailable SMs (a concurrent NCCL all-reduce) cost the one-CTA-per-SM kernels? (tools/sm_hog_probe.py) */
-int pesr_debug_sm_hog(int32_t n_ctas, int64_t usec, void* stream);
+
+/* Kernel-selection options of pesr_conv_igemm (process-wide; the defaults are the measured-fastest choices).  The
+ * parity tests use them to force every kernel variant onto small shapes.  Bring-up probes (timelines, MMA-rate and
+ * SM-occupancy microbenchmarks) are NOT part of this library: see include/pesr_b200_debug.h / tools/build_debug.sh. */
+#define PESR_OPT_PAIR_MODE 0        /* 0 never use the CTA-pair (cta_group::2) kernel, 1 where it wins (default), 2 whenever legal */
+#define PESR_OPT_SUB_STAGES 1       /* 0 one k-block per pipeline stage, 1 multi-k-block / halo stages (default), 2 also for N = 256 */
+#define PESR_OPT_PDL 2              /* programmatic dependent launch: 0 off, 1 on (default; PESR_NO_PDL=1 in the environment disables) */
+#define PESR_OPT_STAGED_EPILOGUE 3  /* residual epilogue through shared memory (pair kernel): 0 off, 1 on (default) */
+#define PESR_OPT_SPECIALISED_EPILOGUE 4 /* compile-time specialised epilogues: 0 generic kernel only, 1 on (default) */
+int pesr_set_option(int option, int value);
 
 /* ------------------------------------------------------------------------------------------------
  * Backward-filter as a split-K GEMM with both operands MN-major (pixels are K).
@@ -177,9 +177,6 @@ int pesr_wgrad_reduce_bias(const float* partials, int32_t splits, int32_t ntaps,
                            int32_t accumulate, float* grad_oihw, const void* dy16, int64_t npix, int32_t c, int32_t ldc,
                            float bias_mul, int32_t dtype, float* bias_grad, float* zero_next, int32_t zero_n,
                            void* stream);
-/* Bring-up hook: override the MN-major smem descriptor strides of pesr_conv_wgrad (0 = built-in). */
-void pesr_debug_wgrad_desc(int lbo_bytes, int sbo_bytes);
-void pesr_debug_wgrad_timeline(void* buf);   /* like pesr_debug_timeline, for pesr_conv_wgrad */
 
 /* Weight packing: fp32 OIHW parameter -> 16-bit K-major GEMM operand (tap = ky*3+kx; tapf = 8-tap).
  *  mode 0 fprop     : out[tap][o][i]                        (rows = 9*co, K = ci)
@@ -214,6 +211,8 @@ int pesr_pack_weights_multi(const int64_t* jobs_host, int32_t njobs, void* jobs_
  * constant shift of the conv input, used to centre the 0..255 image ahead of the Discriminator's first
  * conv + BatchNorm (which is invariant to it).  pad_affine bit 1 (value 2): columns 32..63 of `col` already hold zeros
  * (a buffer that is zeroed once and reused) and are not written, which halves the bytes stored.
+ * pad_affine bit 2 (value 4): src_nchw is really a uint8 HWC image batch [nb][h][w][3] (utils.imgs_to_tensors,
+ * utils.py:20-25, fused into the first kernel of the inference path).
  * mul_dev: optional device scalar multiplied into the result.
  * Feeds the Cin=3 convs (model/pesr.py:23,54; vgg19.features[0]) and, with sgn=-1, the backward of
  * the Cout=3 conv (model/basic.py:60). */
@@ -227,6 +226,18 @@ int pesr_im2col3(const float* src_nchw, int32_t nb, int32_t h, int32_t w, const 
 int pesr_col2im3(const float* z, int32_t ldz, int32_t nb, int32_t h, int32_t w, const float* bias,
                  const float* affine_a, const float* affine_b, float mul_host, const float* div_dev, int32_t sgn,
                  float* pre_nchw, float* out_nchw, void* stream);
+
+/* pesr_col2im3 through a shared-memory tile (8 x 32 pixels + halo per block: every z row is fetched once instead of
+ * nine times), with an optional fused uint8 HWC store out_u8[n][h][w][3] = uint8(rint(clamp(out, 0, 255))) -- the
+ * clip / round-half-even / transpose of utils.tensors_to_imgs (utils.py:13-18).  out_nchw or out_u8 may be NULL (not both).
+ * z must be 16-byte aligned with ldz %% 4 == 0 and ldz >= 28. */
+int pesr_col2im3_tiled(const float* z, int32_t ldz, int32_t nb, int32_t h, int32_t w, const float* bias,
+                       const float* affine_a, const float* affine_b, float mul_host, const float* div_dev, int32_t sgn,
+                       float* pre_nchw, float* out_nchw, uint8_t* out_u8, void* stream);
+
+/* MeanShift as a stand-alone op (model/basic.py:9-17): out[n][o][p] = sum_i w9[o*3+i] * x[n][i][p] + b3[o] on
+ * [nb][3][hw] fp32 tensors (b3 may be NULL). */
+int pesr_mean_shift(const float* x, int32_t nb, int64_t hw, const float* w9, const float* b3, float* out, void* stream);
 
 /* NCHW fp32 <-> NHWC 16-bit (generic; used at module boundaries and by the tests). */
 int pesr_nchw32_to_nhwc16(const float* src, int32_t nb, int32_t c, int32_t h, int32_t w, int32_t ldc,
@@ -258,6 +269,23 @@ int pesr_moments3(const float* a, const float* b, int32_t nb, int64_t hw, float*
 int pesr_blend_x8_to_u8(const float* perc, const float* ens, int32_t h, int32_t w, float alpha, int32_t n_ens,
                         float* out32, uint8_t* out8, void* stream);
 int pesr_u8hwc_to_f32nchw(const uint8_t* src, int32_t h, int32_t w, float* dst, void* stream);
+int pesr_u8hwc_to_f32nchw_batch(const uint8_t* src, int32_t nb, int32_t h, int32_t w, float* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Validation metric and input pipeline (train.py:281-295, utils.py:10-11,27-41, data.py:64-126).
+ * pesr_psnr_y_sse: sse[n] += sum over pixels of (Y(a) - Y(b))^2 for [nb][3][hw] fp32 images in 0..255, where
+ *   Y(v) = rint(clamp(rgb2y(rint(clamp(v, 0, 255))), 0, 255)) exactly as utils.compute_PSNR builds it
+ *   (rgb2y = (65.738 r + 129.057 g + 25.064 b) / 256 + 16, evaluated in exact integer arithmetic); the sum is a 64-bit
+ *   integer, so PSNR = 20 log10(255 / sqrt(sse / hw)) is bit-reproducible.  The caller zeroes sse.
+ * pesr_gather_patches: one launch builds a training batch from a device-resident uint8 HWC image cache: sample s =
+ *   LR crop [y, y+patch) x [x, x+patch) of its image and the aligned HR crop (scale * y, scale * x, scale * patch),
+ *   augmented as data.py:86-104 (k bit 2: transpose, then bit 1: vertical flip, then bit 0: horizontal flip), written
+ *   as NCHW fp32 lr [nb][3][patch][patch] and hr [nb][3][scale*patch][scale*patch].  table_dev: nb rows of 8 int64
+ *   {lr image ptr, hr image ptr, lr width, hr width, y, x, k, 0}.
+ * ------------------------------------------------------------------------------------------------ */
+int pesr_psnr_y_sse(const float* a, const float* b, int32_t nb, int64_t hw, unsigned long long* sse, void* stream);
+int pesr_gather_patches(const int64_t* table_dev, int32_t nb, int32_t patch, int32_t scale, float* lr, float* hr,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Loss reductions with the gradient produced in the same pass (train.py:131-140), all fp32.
@@ -279,6 +307,10 @@ int pesr_loss_gan(const float* a, const float* b, int32_t n, float sign_a, float
  * table_dev: nchunks rows of {p, g, m, v (device addresses), n} as int64; g is multiplied by grad_mul first. */
 int pesr_adam_multi(const int64_t* table_dev, int32_t nchunks, float lr, float beta1, float beta2, float eps,
                     int32_t step, float grad_mul, void* stream);
+/* Same with the learning rate and the (already incremented) step count read from device memory at run time, so that a
+ * captured CUDA graph of the training step replays with the right bias corrections (torch.optim.Adam(capturable=True)). */
+int pesr_adam_multi_dev(const int64_t* table_dev, int32_t nchunks, const float* lr_dev, float beta1, float beta2,
+                        float eps, const int32_t* step_dev, float grad_mul, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Discriminator / VGG layer kernels (HBM-bound).

@@ -144,28 +144,84 @@ def _qa(t, qdtype):
     return t if qdtype is None else _RoundSTE.apply(t, qdtype)
 
 
-def generator_forward(sd, x, depth, res_scale, qdtype=None):
+# ------------------------------------------------------------------------------------------------
+# forward-pinned evaluation (test infrastructure for the GRADIENT gates)
+#
+# Networks of ReLU / LeakyReLU / max-pool / BatchNorm layers are only piecewise linear: a forward deviation of eps
+# flips a fraction ~eps of the activation masks and perturbs the gradient by ~sqrt(eps).  Two evaluations of THIS
+# oracle that round at identical points and differ only in the accumulator width (fp32 vs fp64) already disagree by
+# 2e-3 in the Discriminator's logits and 6e-2 in its gradients (tests/test_oracle.py::test_rounding_noise_floor),
+# because a 1e-7 difference before a 16-bit rounding flips that rounding with probability ~1e-4 and the flips
+# compound layer by layer until both paths are, in effect, independently rounded.  A gradient gate against any
+# free-running oracle is therefore conditioning-limited, whatever the kernel quality.
+#
+# `pin` removes the conditioning from the comparison: a dict of activations saved by the implementation under test
+# (NCHW tensors, see the key names in each forward below).  The oracle then evaluates every layer at THOSE values
+# (identity gradient through the substitution, activation masks taken from the pinned post-activation tensors), so
+# its autograd gradient is the exact derivative of the reference network at the implementation's own forward point.
+# ------------------------------------------------------------------------------------------------
+class _PinAct(torch.autograd.Function):
+    """value := the pinned post-activation tensor; gradient := g * act'(pinned) with act' in {1, slope}."""
+
+    @staticmethod
+    def forward(ctx, pre, post, slope):
+        ctx.save_for_backward(post > 0)
+        ctx.slope = slope
+        return post.to(pre.dtype).clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return g * torch.where(mask, 1.0, ctx.slope).to(g.dtype), None, None
+
+
+def _pin(t, pin, key, trace=None):
+    """Substitute the pinned value for t (identity gradient); `trace` (dict) records the value used."""
+    if pin is not None and key in pin:
+        t = t + (pin[key].to(t.dtype) - t).detach()
+    if trace is not None and key is not None:
+        trace[key] = t.detach()
+    return t
+
+
+def _act(pre, pin, key, slope, trace=None):
+    """relu (slope 0) / leaky_relu(slope), evaluated at the pinned post-activation values when given."""
+    if pin is not None and key in pin:
+        out = _PinAct.apply(pre, pin[key], slope)
+    else:
+        out = F.relu(pre) if slope == 0 else F.leaky_relu(pre, slope)
+    if trace is not None:
+        trace[key] = out.detach()
+    return out
+
+
+def generator_forward(sd, x, depth, res_scale, qdtype=None, pin=None, trace=None):
     """model/pesr.py:28-38.  qdtype (torch.float16 / bfloat16) emulates 16-bit conv operands with the
-    fp32 residual stream the B200 schedule keeps (quantisation-matched oracle)."""
-    def conv(t, name):
-        return F.conv2d(_qa(t, qdtype), _q(sd[name + '.weight'], qdtype), sd[name + '.bias'], padding=1)
+    fp32 residual stream the B200 schedule keeps (quantisation-matched oracle).
+    pin keys (16-bit conv operands saved by the implementation): 'x{i}' = input of block i (i = depth: input of the
+    tail conv), 't{i}' = relu(conv1) of block i, 'u0' / 'u1' / 'u2' = inputs of upsample.0 / .2 / .4."""
+    def conv(t, name, key=None):
+        return F.conv2d(_pin(_qa(t, qdtype), pin, key, trace), _q(sd[name + '.weight'], qdtype), sd[name + '.bias'], padding=1)
 
     x = F.conv2d(x, sd['sub_mean.weight'], sd['sub_mean.bias'])               # :29
     x = conv(x, 'embed')                                                       # :31
     res = x
     for i in range(depth):                                                     # :32, model/basic.py:48-52
-        t = F.relu(conv(res, f'body.{i}.body.0'))
+        t = _act(conv(res, f'body.{i}.body.0', f'x{i}'), pin, f't{i}', 0.0, trace)
         res = conv(t, f'body.{i}.body.2') * res_scale + res
-    res = conv(res, f'body.{depth}') + x                                       # :32-33
-    u = F.pixel_shuffle(conv(res, 'upsample.0'), 2)                            # model/basic.py:56-57
-    u = F.pixel_shuffle(conv(u, 'upsample.2'), 2)                              # :58-59
-    u = conv(u, 'upsample.4')                                                  # :60
+    res = conv(res, f'body.{depth}', f'x{depth}') + x                          # :32-33
+    u = F.pixel_shuffle(conv(res, 'upsample.0', 'u0'), 2)                      # model/basic.py:56-57
+    u = F.pixel_shuffle(conv(u, 'upsample.2', 'u1'), 2)                        # :58-59
+    u = conv(u, 'upsample.4', 'u2')                                            # :60
     return F.conv2d(u, sd['add_mean.weight'], sd['add_mean.bias'])             # model/pesr.py:36
 
 
-def discriminator_forward(sd, x, eps=1e-5, qdtype=None, stats_out=None):
+def discriminator_forward(sd, x, eps=1e-5, qdtype=None, stats_out=None, pin=None, trace=None):
     """model/pesr.py:77-81 in train mode: BatchNorm uses the batch's own (biased) statistics
-    (model/basic.py:29).  stats_out (list) receives per-layer (mean, biased var) for the running-stat update."""
+    (model/basic.py:29).  stats_out (list) receives per-layer (mean, biased var) for the running-stat update.
+    pin keys: 'y{i}' = conv output of block i before BatchNorm (as stored, 16-bit), 'a{i}' = block output after
+    LeakyReLU (16-bit), 'h1' = classifier.1 output (fp32).  With qdtype the second Linear also sees 16-bit operands,
+    as on the B200 path."""
     for i, (_cin, _cout, stride) in enumerate(D_CHANNELS):
         if qdtype is not None and i == 0:
             # the B200 path feeds conv 0 the image minus 127.5 (padding included): BatchNorm cancels the shift
@@ -173,21 +229,23 @@ def discriminator_forward(sd, x, eps=1e-5, qdtype=None, stats_out=None):
             y = F.conv2d(xin, _q(sd['features.0.0.weight'], qdtype), None, stride=stride)
         else:
             y = F.conv2d(_qa(x, qdtype), _q(sd[f'features.{i}.0.weight'], qdtype), None, stride=stride, padding=1)
-        y = _qa(y, qdtype)   # the pre-BN tensor is stored in 16 bits by the B200 path
+        y = _pin(_qa(y, qdtype), pin, f'y{i}', trace)   # the pre-BN tensor is stored in 16 bits by the B200 path
         mean = y.mean(dim=(0, 2, 3))
         var = y.var(dim=(0, 2, 3), unbiased=False)
         if stats_out is not None:
             stats_out.append((mean.detach(), var.detach(), y.numel() // y.shape[1]))
         y = (y - mean.view(1, -1, 1, 1)) * torch.rsqrt(var.view(1, -1, 1, 1) + eps)
         y = y * sd[f'features.{i}.1.weight'].view(1, -1, 1, 1) + sd[f'features.{i}.1.bias'].view(1, -1, 1, 1)
-        x = F.leaky_relu(y, 0.2)
+        x = _act(y, pin, f'a{i}', 0.2, trace)
     f = x.reshape(x.shape[0], -1)                                              # NCHW flatten, model/pesr.py:79
-    h = F.leaky_relu(F.linear(_qa(f, qdtype), _q(sd['classifier.0.weight'], qdtype), sd['classifier.0.bias']), 0.2)
-    return F.linear(h, sd['classifier.2.weight'], sd['classifier.2.bias'])
+    h = _act(F.linear(_qa(f, qdtype), _q(sd['classifier.0.weight'], qdtype), sd['classifier.0.bias']), pin, 'h1', 0.2, trace)
+    return F.linear(_qa(h, qdtype), _q(sd['classifier.2.weight'], qdtype), sd['classifier.2.bias'])
 
 
-def vgg_features(sd, x, qdtype=None):
-    """model/vgg.py:18-22: sub_mean then vgg19.features[:35] (conv5_4 output, before its ReLU)."""
+def vgg_features(sd, x, qdtype=None, pin=None, trace=None):
+    """model/vgg.py:18-22: sub_mean then vgg19.features[:35] (conv5_4 output, before its ReLU).
+    pin keys: 'c{k}' = output of conv k (0-based) after its ReLU (the last one: the pre-ReLU features), 16-bit.
+    With qdtype the returned features are rounded to 16 bits as well (the B200 path stores them so)."""
     x = F.conv2d(x, sd['sub_mean.weight'], sd['sub_mean.bias'])
     idx = 0
     n_conv = sum(1 for v in VGG19_CFG if v != 'M')
@@ -200,14 +258,16 @@ def vgg_features(sd, x, qdtype=None):
         x = F.conv2d(_qa(x, qdtype), _q(sd[f'vgg.{idx}.weight'], qdtype), sd[f'vgg.{idx}.bias'], padding=1)
         k += 1
         if k < n_conv:
-            x = F.relu(x)
+            x = _act(x, pin, f'c{k - 1}', 0.0, trace)
+        else:
+            x = _pin(_qa(x, qdtype), pin, f'c{k - 1}', trace)
         idx += 2
     return x
 
 
-def vgg_forward(sd, sr, hr, qdtype=None):
-    """model/vgg.py:18-28: (features(sr), features(hr) without grad)."""
-    f_sr = vgg_features(sd, sr, qdtype)
+def vgg_forward(sd, sr, hr, qdtype=None, pin=None, trace=None):
+    """model/vgg.py:18-28: (features(sr), features(hr) without grad).  pin applies to the sr branch."""
+    f_sr = vgg_features(sd, sr, qdtype, pin, trace)
     with torch.no_grad():
         f_hr = vgg_features(sd, hr.detach(), qdtype)
     return f_sr, f_hr
@@ -285,21 +345,33 @@ def pretrain_step(g_sd, lr_img, hr_img, opt, dtype=torch.float32, qdtype=None):
 
 
 def gan_step(g_sd, d_sd, v_sd, lr_img, hr_img, opt, lr_rate=5e-5, alpha_l1=0.0, alpha_vgg=50.0, alpha_gan=1.0,
-             alpha_tv=1e-6, gamma=1.0, dtype=torch.float32, qdtype=None, focal_detach=False):
-    """train.py:202-259 (RSGAN + focal loss, the defaults of train.py:64-76), with one real Adam step
-    on D between the two phases as in train.py:229.  Returns a dict of losses, gradients and `sr`."""
+             alpha_tv=1e-6, gamma=1.0, dtype=torch.float32, qdtype=None, focal_detach=False, gan_type='RSGAN',
+             focal=True, pins=None):
+    """train.py:202-259 (defaults of train.py:64-76: RSGAN + focal loss; gan_type='SGAN' and focal=False select the
+    other branches of train.py:210-213 / :244-253), with one real Adam step on D between the two phases as in
+    train.py:229.  Returns a dict of losses, gradients and `sr`.
+    pins (forward-pinned evaluation, see above): {'g': pins of the Generator forward, 'd': [pins of the four
+    Discriminator forwards in the order D(hr), D(sr.detach()), D(sr), D(hr)], 'v': pins of the VGG sr branch,
+    'f_hr': the target features, 'sr': the Generator output}."""
     g = _leaf(g_sd, dtype)
     d = _leaf(d_sd, dtype)
     v = {k: t.detach().to(dtype) if t.is_floating_point() else t for k, t in v_sd.items()}
     lr_img, hr_img = lr_img.to(dtype), hr_img.to(dtype)
     d_train = [k for k in d if d[k].is_floating_point() and d[k].requires_grad]
     out = {}
+    pins = pins or {}
+    pd = pins.get('d', [None] * 4)
     # ---- D phase, train.py:202-229
-    pred_real = discriminator_forward(d, hr_img, qdtype=qdtype)
-    sr = generator_forward(g, lr_img, opt['depth'], opt['res_scale'], qdtype)
-    pred_fake = discriminator_forward(d, sr.detach(), qdtype=qdtype)
+    pred_real = discriminator_forward(d, hr_img, qdtype=qdtype, pin=pd[0])
+    sr = generator_forward(g, lr_img, opt['depth'], opt['res_scale'], qdtype, pin=pins.get('g'))
+    sr = _pin(sr, pins, 'sr')
+    pred_fake = discriminator_forward(d, sr.detach(), qdtype=qdtype, pin=pd[1])
     ones = torch.ones_like(pred_real)
-    d_loss = F.binary_cross_entropy_with_logits(pred_real - pred_fake, ones)   # train.py:213
+    if gan_type == 'SGAN':                                                     # train.py:210-211
+        d_loss = (F.binary_cross_entropy_with_logits(pred_real, ones) +
+                  F.binary_cross_entropy_with_logits(pred_fake, torch.zeros_like(pred_fake)))
+    else:
+        d_loss = F.binary_cross_entropy_with_logits(pred_real - pred_fake, ones)   # train.py:213
     d_grads = torch.autograd.grad(d_loss, [d[k] for k in d_train])
     out['d_loss'] = d_loss.detach()
     out['d_grads'] = dict(zip(d_train, d_grads))
@@ -309,13 +381,19 @@ def gan_step(g_sd, d_sd, v_sd, lr_img, hr_img, opt, lr_rate=5e-5, alpha_l1=0.0, 
             adam_update(d[k], gk, torch.zeros_like(gk), torch.zeros_like(gk), 1, lr_rate)
     out['d_params_after'] = {k: d[k].detach().clone() for k in d_train}
     # ---- G phase, train.py:234-259
-    pred_fake = discriminator_forward(d, sr, qdtype=qdtype)
-    pred_real = discriminator_forward(d, hr_img, qdtype=qdtype)
+    pred_fake = discriminator_forward(d, sr, qdtype=qdtype, pin=pd[2])
+    pred_real = discriminator_forward(d, hr_img, qdtype=qdtype, pin=pd[3])
     l1 = l1_loss(sr, hr_img) * alpha_l1
-    f_sr, f_hr = vgg_forward(v, sr, hr_img, qdtype)
+    f_sr, f_hr = vgg_forward(v, sr, hr_img, qdtype, pin=pins.get('v'))
+    if 'f_hr' in pins:
+        f_hr = pins['f_hr'].to(dtype)
     vgg_l = mse_loss(f_sr, f_hr) * alpha_vgg
     tv = tv_loss(sr) * alpha_tv
-    g_l = focal_loss(pred_fake - pred_real, ones, gamma, detach_weight=focal_detach) * alpha_gan
+    g_in = pred_fake if gan_type == 'SGAN' else pred_fake - pred_real          # train.py:244-253
+    if focal:
+        g_l = focal_loss(g_in, ones, gamma, detach_weight=focal_detach) * alpha_gan
+    else:
+        g_l = F.binary_cross_entropy_with_logits(g_in, ones) * alpha_gan
     total = l1 + vgg_l + g_l + tv
     g_names = [k for k in g]
     g_grads = torch.autograd.grad(total, [g[k] for k in g_names] + [sr], allow_unused=True)

@@ -90,13 +90,8 @@ SIGNATURES = {
     "pesr_profile_enable": (None, [C.c_int]),
     "pesr_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
     "pesr_conv_igemm": (C.c_int, [C.POINTER(ConvDesc), _vp]),
-    "pesr_debug_pair_mode": (None, [C.c_int]),
-    "pesr_debug_timeline": (None, [_vp]),
-    "pesr_debug_wgrad_timeline": (None, [_vp]),
-    "pesr_debug_mma_rate": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _vp, _vp]),
-    "pesr_debug_sm_hog": (C.c_int, [_i32, _i64, _vp]),
+    "pesr_set_option": (C.c_int, [C.c_int, C.c_int]),
     "pesr_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), C.POINTER(_i32), _vp]),
-    "pesr_debug_wgrad_desc": (None, [C.c_int, C.c_int]),
     "pesr_wgrad_reduce": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp, _vp]),
     "pesr_wgrad_reduce_bias": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp,
                                          _vp, _i64, _i32, _i32, _f32, _i32, _vp, _vp, _i32, _vp]),
@@ -111,6 +106,11 @@ SIGNATURES = {
     "pesr_moments3": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp]),
     "pesr_blend_x8_to_u8": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _i32, _vp, _vp, _vp]),
     "pesr_u8hwc_to_f32nchw": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
+    "pesr_u8hwc_to_f32nchw_batch": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "pesr_col2im3_tiled": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "pesr_mean_shift": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "pesr_psnr_y_sse": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp]),
+    "pesr_gather_patches": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "pesr_loss_l1": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "pesr_loss_mse": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "pesr_loss_tv": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
@@ -129,6 +129,7 @@ SIGNATURES = {
     "pesr_flatten_nchw16": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "pesr_unflatten_nchw16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _f32, _i32, _vp, _vp]),
     "pesr_adam_multi": (C.c_int, [_vp, _i32, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
+    "pesr_adam_multi_dev": (C.c_int, [_vp, _i32, _vp, _f32, _f32, _f32, _vp, _f32, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():
@@ -156,6 +157,14 @@ def profile_read(kind):
     ms, n, fl = C.c_double(0), C.c_longlong(0), C.c_double(0)
     check(lib.pesr_profile_read(kind, C.byref(ms), C.byref(n), C.byref(fl)), "pesr_profile_read")
     return ms.value, n.value, fl.value
+
+
+OPT_PAIR_MODE, OPT_SUB_STAGES, OPT_PDL, OPT_STAGED_EPILOGUE, OPT_SPECIALISED_EPILOGUE = 0, 1, 2, 3, 4
+
+
+def set_option(option, value):
+    """Kernel-selection options of pesr_conv_igemm (include/pesr_b200.h PESR_OPT_*)."""
+    check(lib.pesr_set_option(option, value), "pesr_set_option")
 
 
 def launch_count(reset=False):

@@ -25,6 +25,11 @@ static constexpr int kABytes = kTileM * kKBlock * 2;  // 16 KB
 static constexpr int kAccStride = 256;    // TMEM columns reserved per accumulator buffer
 static constexpr int kNumThreads = 192;
 static constexpr int kMaxStages = 8;
+#ifdef PESR_DEBUG_HOOKS
+static constexpr bool kDebugHooks = true;    // timeline stamps compiled in (libpesr_b200_debug.so only)
+#else
+static constexpr bool kDebugHooks = false;
+#endif
 
 struct ConvMaps {
   CUtensorMap a[PESR_MAX_SRC];
@@ -138,7 +143,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
   const uint32_t tmem_base = *tmem_ptr;
 
   const int total_kb = p.ntaps * p.kblocks_per_tap;
-  unsigned long long* dbg = (p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
+  unsigned long long* dbg = (kDebugHooks && p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
   unsigned long long t_begin = 0, g_begin = 0;
   if (dbg && threadIdx.x == 0) {
     t_begin = clock64();
@@ -146,7 +151,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     dbg[0] = t_begin;
     dbg[62] = g_begin;
   }
-  if (p.dbg && threadIdx.x == 0) {   // per-CTA start / end wall-clock stamps (all blocks)
+  if (kDebugHooks && p.dbg && threadIdx.x == 0) {   // per-CTA start / end wall-clock stamps (all blocks)
     unsigned long long g;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
     p.dbg[64 + 2 * blockIdx.x] = g;
@@ -742,7 +747,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     dbg[61] = clock64();
     dbg[63] = g_end;
   }
-  if (p.dbg && threadIdx.x == 0) {
+  if (kDebugHooks && p.dbg && threadIdx.x == 0) {
     unsigned long long g;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
     p.dbg[65 + 2 * blockIdx.x] = g;
@@ -763,18 +768,23 @@ static int g_pair_mode = -1;  // -1: from the environment (PESR_NO_PAIR=1 disabl
 
 using namespace pesr;
 
-// Bring-up / A-B hook: 0 = never use the CTA-pair kernel, 1 = whenever legal, -1 = re-read PESR_NO_PAIR.
-extern "C" void pesr_debug_pair_mode(int mode) {
-  if (mode >= 500) g_light_enabled = mode - 500;        // 500 / 501: compile-time specialised light epilogue off / on
-  else if (mode >= 400) g_staged_enabled = mode - 400;      // 400 / 401: staged (TMA-store) epilogue of the pair kernel off / on
-  else if (mode >= 300) set_pdl(mode - 300);                // 300 / 301: programmatic dependent launch off / on
-  else if (mode >= 200) g_sub_mode_enabled = mode - 200;   // 200 / 201: disable / enable the multi-sub-block stages
-  else if (mode >= 100) { /* load-skip experiment of the bring-up phase: removed */ }
-  else g_pair_mode = mode;
+// Kernel-selection options (include/pesr_b200.h PESR_OPT_*).
+extern "C" int pesr_set_option(int option, int value) {
+  switch (option) {
+    case PESR_OPT_PAIR_MODE: g_pair_mode = value; return 0;
+    case PESR_OPT_SUB_STAGES: g_sub_mode_enabled = value; return 0;
+    case PESR_OPT_PDL: set_pdl(value); return 0;
+    case PESR_OPT_STAGED_EPILOGUE: g_staged_enabled = value; return 0;
+    case PESR_OPT_SPECIALISED_EPILOGUE: g_light_enabled = value; return 0;
+  }
+  set_error("pesr_set_option: unknown option %d", option);
+  return PESR_E_ARG;
 }
 
+#ifdef PESR_DEBUG_HOOKS
 // Bring-up hook: device buffer of 64 uint64 that block 0 of every pesr_conv_igemm launch fills with a timeline.
 extern "C" void pesr_debug_timeline(void* buf) { g_dbg_buf = reinterpret_cast<unsigned long long*>(buf); }
+#endif
 
 extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

@@ -21,6 +21,11 @@ static constexpr int kWgBoxBytes = kWgKBlock * 128;  // one 64-channel x 64-pixe
 static constexpr int kWgThreads = 192;
 static constexpr int kWgMaxStages = 8;
 static constexpr int kWgAccStride = 256;
+#ifdef PESR_DEBUG_HOOKS
+static constexpr bool kWgDebugHooks = true;    // timeline stamps compiled in (libpesr_b200_debug.so only)
+#else
+static constexpr bool kWgDebugHooks = false;
+#endif
 
 struct WgMaps {
   CUtensorMap a;
@@ -87,14 +92,14 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
   griddep_wait();
   griddep_launch();
 
-  unsigned long long* dbg = (p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
+  unsigned long long* dbg = (kWgDebugHooks && p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
   if (dbg && threadIdx.x == 0) {
     unsigned long long g;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
     dbg[0] = clock64();
     dbg[62] = g;
   }
-  if (p.dbg && threadIdx.x == 0) {   // per-CTA start / end wall-clock stamps (all blocks)
+  if (kWgDebugHooks && p.dbg && threadIdx.x == 0) {   // per-CTA start / end wall-clock stamps (all blocks)
     unsigned long long g;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
     p.dbg[64 + 2 * blockIdx.x] = g;
@@ -273,7 +278,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
     dbg[61] = clock64();
     dbg[63] = g;
   }
-  if (p.dbg && threadIdx.x == 0) {
+  if (kWgDebugHooks && p.dbg && threadIdx.x == 0) {
     unsigned long long g;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
     p.dbg[65 + 2 * blockIdx.x] = g;
@@ -475,6 +480,7 @@ static unsigned long long* g_wg_dbg = nullptr;
 using namespace pesr;
 
 // Debug hook used by the bring-up tests only: override the MN-major descriptor strides (0 = default).
+#ifdef PESR_DEBUG_HOOKS
 extern "C" void pesr_debug_wgrad_timeline(void* buf) { g_wg_dbg = reinterpret_cast<unsigned long long*>(buf); }
 
 extern "C" void pesr_debug_wgrad_desc(int lbo_bytes, int sbo_bytes) {
@@ -483,6 +489,7 @@ extern "C" void pesr_debug_wgrad_desc(int lbo_bytes, int sbo_bytes) {
   g_dbg_lbo = lbo_bytes;
   g_dbg_sbo = sbo_bytes;
 }
+#endif
 
 extern "C" int pesr_conv_wgrad(const pesr_wgrad_desc* d, int32_t* splits_out, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

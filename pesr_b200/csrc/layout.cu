@@ -190,6 +190,7 @@ __global__ void im2col3_kernel(const float* __restrict__ src, int nb, int h, int
       n = (int)(p / plane);
     }
     const float* base = src + (long long)n * 3 * plane;
+    const uint8_t* base8 = reinterpret_cast<const uint8_t*>(src) + (long long)n * 3 * plane;   // flag 4: uint8 HWC source
     float vals[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) vals[j] = 0.f;
@@ -200,7 +201,13 @@ __global__ void im2col3_kernel(const float* __restrict__ src, int nb, int h, int
       float v0 = 0.f, v1 = 0.f, v2 = 0.f;
       if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
         const long long off = (long long)yy * w + xx;
-        const float s0 = __ldg(base + off), s1 = __ldg(base + plane + off), s2 = __ldg(base + 2 * plane + off);
+        float s0, s1, s2;
+        if (pad_affine & 4) {
+          const uint8_t* q8 = base8 + off * 3;
+          s0 = (float)q8[0]; s1 = (float)q8[1]; s2 = (float)q8[2];
+        } else {
+          s0 = __ldg(base + off); s1 = __ldg(base + plane + off); s2 = __ldg(base + 2 * plane + off);
+        }
         v0 = (A[0] * s0 + A[1] * s1 + A[2] * s2 + B[0]) * mul;
         v1 = (A[3] * s0 + A[4] * s1 + A[5] * s2 + B[1]) * mul;
         v2 = (A[6] * s0 + A[7] * s1 + A[8] * s2 + B[2]) * mul;

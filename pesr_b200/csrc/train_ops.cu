@@ -133,10 +133,8 @@ __global__ void gan_loss_kernel(const float* __restrict__ a, const float* __rest
 // ------------------------------------------------------------------------------------------
 // multi-tensor Adam: table rows = {p, g, m, v, n} (device pointers as int64), one row per chunk
 // ------------------------------------------------------------------------------------------
-__global__ void adam_multi_kernel(const long long* __restrict__ table, int nchunks, float lr, float beta1, float beta2,
-                                  float eps, float bc1, float bc2_sqrt, float grad_mul) {
-  const int c = blockIdx.x;
-  if (c >= nchunks) return;
+__device__ __forceinline__ void adam_chunk(const long long* __restrict__ table, int c, float lr, float beta1, float beta2,
+                                           float eps, float bc1, float bc2_sqrt, float grad_mul) {
   float* p = reinterpret_cast<float*>(table[c * 5 + 0]);
   const float* g = reinterpret_cast<const float*>(table[c * 5 + 1]);
   float* m = reinterpret_cast<float*>(table[c * 5 + 2]);
@@ -175,6 +173,26 @@ __global__ void adam_multi_kernel(const long long* __restrict__ table, int nchun
     v[i] = vj;
     p[i] -= step * mj / (sqrtf(vj) / bc2_sqrt + eps);
   }
+}
+
+__global__ void adam_multi_kernel(const long long* __restrict__ table, int nchunks, float lr, float beta1, float beta2,
+                                  float eps, float bc1, float bc2_sqrt, float grad_mul) {
+  const int c = blockIdx.x;
+  if (c >= nchunks) return;
+  adam_chunk(table, c, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_mul);
+}
+
+// Same with the step count and the learning rate read from device memory, so that a captured CUDA graph of the
+// training step replays with the right bias corrections (torch.optim.Adam(capturable=True) semantics).
+__global__ void adam_multi_dev_kernel(const long long* __restrict__ table, int nchunks, const float* __restrict__ lr_dev,
+                                      float beta1, float beta2, float eps, const int* __restrict__ step_dev,
+                                      float grad_mul) {
+  const int c = blockIdx.x;
+  if (c >= nchunks) return;
+  const double step = (double)__ldg(step_dev);
+  const float bc1 = (float)(1.0 - pow((double)beta1, step));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, step));
+  adam_chunk(table, c, __ldg(lr_dev), beta1, beta2, eps, bc1, bc2_sqrt, grad_mul);
 }
 
 }  // namespace pesr
@@ -244,5 +262,16 @@ extern "C" int pesr_adam_multi(const int64_t* table_dev, int32_t nchunks, float 
                                                  beta2, eps, (float)bc1, (float)sqrt(bc2), grad_mul);
   count_launch();
   PESR_CHECK_LAUNCH("adam_multi");
+  return 0;
+}
+
+extern "C" int pesr_adam_multi_dev(const int64_t* table_dev, int32_t nchunks, const float* lr_dev, float beta1,
+                                   float beta2, float eps, const int32_t* step_dev, float grad_mul, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(table_dev && nchunks > 0 && lr_dev && step_dev, "adam_multi_dev: bad arguments");
+  adam_multi_dev_kernel<<<nchunks, 256, 0, stream>>>(reinterpret_cast<const long long*>(table_dev), nchunks, lr_dev, beta1,
+                                                     beta2, eps, step_dev, grad_mul);
+  count_launch();
+  PESR_CHECK_LAUNCH("adam_multi_dev");
   return 0;
 }

@@ -17,7 +17,7 @@ import torch
 
 from . import ops
 from ._lib import check, lib
-from .engine_g import PackedWeight, _Plan, _run_conv
+from .engine_g import FlatGrads, PackedWeight, _Plan, _Release, _run_conv
 from .ops import ACT_LRELU
 
 D_LAYERS = [(3, 64, 1), (64, 64, 2), (64, 128, 1), (128, 128, 2), (128, 256, 1), (256, 256, 2), (256, 512, 1),
@@ -47,16 +47,6 @@ def _parity_planes(t, nb, h, w, c):
     return out
 
 
-class _Release:
-    """Returns a plan instance to its pool when the autograd node that holds it dies."""
-
-    def __init__(self, plan):
-        self.plan = plan
-
-    def __del__(self):
-        self.plan.busy = False
-
-
 # PESR_FUSED_BN: "0" (default) = separate statistics pass over the conv output, "1" = accumulated by the conv epilogue
 # (pesr_conv_desc.bn_sums) for layers 1-7, "2" = for every layer.  Measured on the GAN step (tools/ab_env2.sh): 19.19 /
 # 19.14 / 19.38 ms, i.e. no gain - the statistics cost the MMA-bound layers' epilogue what the extra pass cost - and the
@@ -76,6 +66,9 @@ class DiscriminatorEngine:
         self.grad_hook = None
         self.grad_hook_finish = None
         self.param_list = None
+        self.defer_finish = False  # True: the data-parallel wrapper waits for the all-reduce itself (DataParallel.finish)
+        self.last_flat = None
+        self.trace_hook = None     # callable(plan), called at the end of every forward (parity tests read the saved activations)
 
     # ------------------------------------------------------------------ parameters
     def _ensure_packed(self, device):
@@ -107,11 +100,16 @@ class DiscriminatorEngine:
         self.c0_key = None
         self.scale_ws = torch.zeros(4, device=device, dtype=torch.float32)
         self.bn_ws = torch.zeros(2 * 512, device=device, dtype=torch.float64)
-        self.offsets, off = {}, 0
-        for p in self.param_list:
-            self.offsets[p] = off
-            off += (p.numel() + 3) // 4 * 4
-        self.flat_numel = off
+        self.flat_grads = FlatGrads(self.param_list)
+        self.offsets, self.flat_numel = self.flat_grads.offsets, self.flat_grads.numel
+
+    def invalidate_packs(self):
+        """See GeneratorEngine.invalidate_packs."""
+        if self.packed is not None:
+            self.fwd_multi.key = None
+            self.bwd_multi.key = None
+            self.fc_key = None
+            self.c0_key = None
 
     def _pack_fc(self):
         fc1, fc2 = self.disc.classifier[0], self.disc.classifier[2]
@@ -280,8 +278,6 @@ class DiscriminatorEngine:
             raise ValueError(f"Discriminator expects [N,3,H,W], got {tuple(x.shape)}")
         x = x.contiguous().float()
         nb, _, h, w = x.shape
-        if nb > 16:
-            raise NotImplementedError("pesr_b200.Discriminator: per-call batch is limited to 16 (train.py:48 default)")
         self._ensure_packed(x.device)
         pl = self._acquire(nb, h, w)
         self.fwd_multi.run()
@@ -321,6 +317,8 @@ class DiscriminatorEngine:
                            out16=pl.h1_16, act=ACT_LRELU)
         logits = torch.empty(nb, 1, device=x.device, dtype=torch.float32)
         ops.linear_fwd(pl.h1_16, self.w2_16, fc2.bias.detach(), nb, 1024, 1, pl.fc_ws, out32=logits)
+        if self.trace_hook is not None:
+            self.trace_hook(pl)
         if save:
             if not training:
                 raise NotImplementedError("pesr_b200.Discriminator: backward in eval() mode is not on the PESR path")
@@ -350,7 +348,7 @@ class DiscriminatorEngine:
         mark_hi = [self.flat_numel]
         acc = acc_flat is not None
         if need_param_grads:
-            flat = acc_flat if acc else torch.empty(self.flat_numel, device=dev, dtype=torch.float32)
+            flat = acc_flat if acc else self.flat_grads.get(dev)
             grads = {p: flat[off[p]:off[p] + p.numel()].view(p.shape) for p in self.param_list}
             hook = self.grad_hook if fire_hooks else None
 
@@ -425,7 +423,7 @@ class DiscriminatorEngine:
         if need_param_grads:
             if mark_hi[0] != 0:
                 raise AssertionError("discriminator backward: gradient ranges did not cover the flat buffer")
-            if hook is not None and self.grad_hook_finish is not None:
+            if hook is not None and self.grad_hook_finish is not None and not self.defer_finish:
                 self.grad_hook_finish()
         self.last_flat = flat
         return grads, dx

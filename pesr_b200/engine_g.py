@@ -18,6 +18,7 @@ the NCCL all-reduce of a bucket while the rest of backward is still running.
 Launch descriptors are built once per (batch, height, width) plan and replayed; per step the host only
 re-packs changed weights and issues the launches.
 """
+import collections
 import ctypes as C
 
 import os
@@ -61,6 +62,102 @@ class _Plan:
     pass
 
 
+class _Release:
+    """Returns a plan instance to its pool when the autograd node that holds it dies."""
+
+    def __init__(self, plan):
+        self.plan = plan
+
+    def __del__(self):
+        self.plan.busy = False
+
+
+# Plan cache bounds.  A plan owns every activation buffer of one (batch, height, width) shape -- 16.5 KB per LR pixel
+# for an inference plan at 256 channels, i.e. 2.8 GB for one 510x339 image -- so the cache keeps the most recently used
+# shapes only (test.py walks datasets of arbitrary image sizes in constant memory in the reference).
+PLAN_CACHE_SHAPES = int(os.environ.get("PESR_PLAN_CACHE", "4"))
+MAX_LIVE_GRAPHS = 4           # live autograd graphs of one input shape (each owns a full set of saved activations)
+# eval-mode batches are processed in chunks of at most this many LR pixels (one plan of the chunk's shape is reused)
+INFER_CHUNK_PIXELS = int(os.environ.get("PESR_INFER_CHUNK_PIXELS", str(1 << 20)))
+
+
+class PlanCache:
+    """LRU over shapes; each shape owns a small pool of plan instances (one per live autograd graph)."""
+
+    def __init__(self, max_shapes=PLAN_CACHE_SHAPES, max_live=MAX_LIVE_GRAPHS, who="pesr_b200"):
+        self.map = collections.OrderedDict()
+        self.max_shapes, self.max_live, self.who = max_shapes, max_live, who
+        self.stamp = 0
+
+    def clear(self):
+        self.map.clear()
+
+    def __len__(self):
+        return len(self.map)
+
+    def __contains__(self, key):
+        return key in self.map
+
+    def __getitem__(self, key):
+        return self.map[key]
+
+    def acquire(self, key, factory):
+        pool = self.map.get(key)
+        if pool is None:
+            pool = self.map[key] = []
+        self.map.move_to_end(key)
+        pl = next((q for q in pool if not q.busy), None)
+        if pl is None:
+            if len(pool) >= self.max_live:
+                raise RuntimeError(f"{self.who}: more than {self.max_live} live autograd graphs of input shape {key}; "
+                                   "run backward (or drop the outputs) of earlier forwards first")
+            self._evict(keep=key)
+            pl = factory()
+            pl.busy = False
+            pool.append(pl)
+        self.stamp += 1
+        pl.stamp = self.stamp
+        return pl
+
+    def _evict(self, keep):
+        # called before a new plan is allocated: drop least-recently-used shapes with no live graph
+        while len(self.map) > self.max_shapes:
+            victim = next((k for k, pool in self.map.items() if k != keep and not any(q.busy for q in pool)), None)
+            if victim is None:
+                return
+            del self.map[victim]
+
+
+class FlatGrads:
+    """The flat fp32 gradient buffer of one network (parameter order, 16-byte aligned tensors).
+
+    One PERSISTENT buffer is reused from step to step, so gradient addresses are stable: the multi-tensor Adam keeps its
+    pointer table and a CUDA graph of the step can be replayed.  Reuse is only safe once the previous hand-out has been
+    consumed; the parameters' version counter tells (every optimiser step bumps it).  A second backward before the next
+    optimiser step (gradient accumulation, two separate D calls) gets a fresh buffer, as autograd may still hold views
+    of the first one in its input buffers."""
+
+    def __init__(self, param_list):
+        self.params = param_list
+        self.offsets, off = {}, 0
+        for p in param_list:
+            self.offsets[p] = off
+            off += (p.numel() + 3) // 4 * 4
+        self.numel = off
+        self.buf = None
+        self.handed_at = None
+
+    def get(self, device):
+        version = self.params[0]._version
+        if self.buf is None or self.buf.device != device:
+            self.buf = torch.empty(self.numel, device=device, dtype=torch.float32)
+            self.handed_at = None
+        if self.handed_at == version:
+            return torch.empty(self.numel, device=device, dtype=torch.float32)
+        self.handed_at = version
+        return self.buf
+
+
 def _run_conv(desc, stream):
     check(lib.pesr_conv_igemm(C.byref(desc), stream), "pesr_conv_igemm")
 
@@ -74,13 +171,15 @@ class GeneratorEngine:
         self.gen = gen
         self.dtype = dtype
         self.dt = ops.dt_code(dtype)
-        self.plans = {}
+        self.plans = PlanCache(who="pesr_b200.Generator")
         self.packed = None
         self.device = None
         self.grad_hook = None      # callable(lo, hi, flat) -> None
         self.grad_hook_finish = None
         self.param_list = None
-        self.last_flat_grad = None
+        self.last_flat = None
+        self.defer_finish = False  # True: the data-parallel wrapper waits for the all-reduce itself (DataParallel.finish)
+        self.trace_hook = None     # callable(plan), called at the end of every forward (parity tests read the saved activations)
 
     # ------------------------------------------------------------------ parameters
     def _convs(self):
@@ -95,7 +194,7 @@ class GeneratorEngine:
         self.sentinel = sentinel
         g, dt = self.gen, self.dtype
         self.device = device
-        self.plans = {}
+        self.plans.clear()
         trunk, tail = self._convs()
         pk = {}
         pk["embed_f"] = PackedWeight(g.embed.weight, 4, dt, pad_to=64)
@@ -127,18 +226,21 @@ class GeneratorEngine:
         self.bias_up0 = torch.empty(4 * C_, device=device, dtype=torch.float32)
         self.bias_up2 = torch.empty(4 * C_, device=device, dtype=torch.float32)
         # flat gradient layout: parameter order, each tensor starting on a 16-byte boundary
-        self.offsets, off = {}, 0
-        for p in self.param_list:
-            self.offsets[p] = off
-            off += (p.numel() + 3) // 4 * 4
-        self.flat_numel = off
+        self.flat_grads = FlatGrads(self.param_list)
+        self.offsets, self.flat_numel = self.flat_grads.offsets, self.flat_grads.numel
 
     # ------------------------------------------------------------------ plans
     def _plan(self, nb, h, w, train):
-        key = (nb, h, w, train)
-        pl = self.plans.get(key)
-        if pl is not None:
-            return pl
+        return self.plans.acquire((nb, h, w, train), lambda: self._new_plan(nb, h, w, train))
+
+    def invalidate_packs(self):
+        """Forget which parameter versions the packed 16-bit operands were made from (a CUDA-graph replay updates
+        the parameters without touching their Python-side version counters)."""
+        if self.packed is not None:
+            self.fwd_multi.key = None
+            self.bwd_multi.key = None
+
+    def _new_plan(self, nb, h, w, train):
         g = self.gen
         Cn, depth, rs = g.n_feats, g.n_resblock, float(g.res_scale)
         dev, tdt, dt = self.device, self.dtype, self.dt
@@ -158,12 +260,11 @@ class GeneratorEngine:
         pl.U2 = e16(16 * P, Cn)
         pl.Z = e32(16 * P, 32)
         pl.ypre = e32(nb, 3, 4 * h, 4 * w) if train else None
-        pl.generation = 0
         X = (lambda i: pl.X[i]) if train else (lambda i: pl.X[i % 2])
         T = (lambda i: pl.T[i]) if train else (lambda i: pl.T[0])
         trunk, tail = self._convs()
         up0, up2, up4 = g.upsample[0], g.upsample[2], g.upsample[4]
-        bn = min(Cn, 256)
+        bn = ops.default_block_n(Cn)
 
         def src(t, hh, ww, c):
             return [ops.nhwc_src(t, nb, hh, ww, c)]
@@ -195,7 +296,6 @@ class GeneratorEngine:
                                     ld_out32=32))
         pl.fwd = f
         if not train:
-            self.plans[key] = pl
             return pl
 
         # ---------------- backward buffers and launch list
@@ -288,21 +388,31 @@ class GeneratorEngine:
         pl.first_fused_bias = chain[0][5] if chain else None
         pl.bwd = fused
         pl.scale = scale
-        self.plans[key] = pl
         return pl
 
     # ------------------------------------------------------------------ forward
-    def forward(self, lr, train):
+    def forward(self, lr, train, out_u8=False):
+        """lr: fp32 NCHW [N,3,H,W] in 0..255, or (inference) a uint8 HWC batch [N,H,W,3] read directly by the first
+        kernel (utils.imgs_to_tensors fused).  out_u8 (inference): return the uint8 HWC image batch [N,4H,4W,3] written
+        by the last kernel (clip + round-half-even of utils.tensors_to_imgs fused) instead of the fp32 NCHW tensor."""
         g = self.gen
-        if lr.dim() != 4 or lr.shape[1] != 3:
-            raise ValueError(f"Generator expects [N,3,H,W], got {tuple(lr.shape)}")
+        u8_in = lr.dtype == torch.uint8
+        if lr.dim() != 4 or (lr.shape[3] if u8_in else lr.shape[1]) != 3:
+            raise ValueError(f"Generator expects [N,3,H,W] (or uint8 [N,H,W,3]), got {tuple(lr.shape)}")
+        if (u8_in or out_u8) and train:
+            raise ValueError("pesr_b200.Generator: uint8 input / output is an inference path (no autograd)")
         if g.n_resblock < 1:
             raise NotImplementedError("pesr_b200.Generator needs depth >= 1")
-        lr = lr.contiguous().float()
-        nb, _, h, w = lr.shape
+        lr = lr.contiguous() if u8_in else lr.contiguous().float()
+        nb, h, w = (lr.shape[0], lr.shape[1], lr.shape[2]) if u8_in else (lr.shape[0], lr.shape[2], lr.shape[3])
         self._ensure_packed(lr.device)
+        if not train and nb > 1 and nb * h * w > INFER_CHUNK_PIXELS:
+            # inference over a large batch: images are independent, so the batch runs through ONE plan of a smaller
+            # batch size (activation memory stays bounded; every chunk still fills the machine)
+            per = max(1, INFER_CHUNK_PIXELS // (h * w))
+            parts = [self.forward(lr[i:i + per], False, out_u8)[0] for i in range(0, nb, per)]
+            return torch.cat(parts, dim=0), None
         pl = self._plan(nb, h, w, train)
-        pl.generation += 1
         Cn = g.n_feats
         self.fwd_multi.run()
         up0, up2, up4 = g.upsample[0], g.upsample[2], g.upsample[4]
@@ -310,22 +420,32 @@ class GeneratorEngine:
         self.bias_up2.copy_(_shuffle_perm(up2.bias.detach(), Cn))
         sm_w = g.sub_mean.weight.detach().reshape(3, 3)
         am_w = g.add_mean.weight.detach().reshape(3, 3)
-        ops.im2col3(lr, pl.col_in, affine_a=sm_w, affine_b=g.sub_mean.bias.detach())
+        if u8_in:
+            ops.im2col3_u8(lr, pl.col_in, affine_a=sm_w, affine_b=g.sub_mean.bias.detach())
+        else:
+            ops.im2col3(lr, pl.col_in, affine_a=sm_w, affine_b=g.sub_mean.bias.detach())
         stream = torch.cuda.current_stream().cuda_stream
         for d in pl.fwd:
             _run_conv(d, stream)
-        sr = torch.empty(nb, 3, 4 * h, 4 * w, device=lr.device, dtype=torch.float32)
-        ops.col2im3(pl.Z, 32, nb, 4 * h, 4 * w, sr, bias=up4.bias.detach(), affine_a=am_w,
-                    affine_b=g.add_mean.bias.detach(), sgn=1, pre=pl.ypre)
-        return sr, (pl, pl.generation, lr)
+        if out_u8:
+            sr = torch.empty(nb, 4 * h, 4 * w, 3, device=lr.device, dtype=torch.uint8)
+            ops.col2im3(pl.Z, 32, nb, 4 * h, 4 * w, None, bias=up4.bias.detach(), affine_a=am_w,
+                        affine_b=g.add_mean.bias.detach(), sgn=1, out_u8=sr)
+        else:
+            sr = torch.empty(nb, 3, 4 * h, 4 * w, device=lr.device, dtype=torch.float32)
+            ops.col2im3(pl.Z, 32, nb, 4 * h, 4 * w, sr, bias=up4.bias.detach(), affine_a=am_w,
+                        affine_b=g.add_mean.bias.detach(), sgn=1, pre=pl.ypre)
+        if self.trace_hook is not None:
+            self.trace_hook(pl)
+        if not train:
+            return sr, None
+        pl.busy = True
+        return sr, (pl, _Release(pl), lr)
 
     # ------------------------------------------------------------------ backward
     def backward(self, state, dsr, need_input_grad=False):
         """Returns (grads: dict param -> fp32 gradient view in the reference layout, dlr or None)."""
-        pl, generation, lr = state
-        if generation != pl.generation:
-            raise RuntimeError("pesr_b200.Generator: backward through a forward whose activations were overwritten "
-                               "by a later forward of the same shape (keep one live graph per input shape)")
+        pl, _release, lr = state
         g = self.gen
         Cn = g.n_feats
         nb, h, w = pl.nb, pl.h, pl.w
@@ -333,8 +453,8 @@ class GeneratorEngine:
         dsr = dsr.contiguous().float()
         dev = dsr.device
         self.bwd_multi.run()
-        flat = torch.empty(self.flat_numel, device=dev, dtype=torch.float32)
-        self.last_flat_grad = flat
+        flat = self.flat_grads.get(dev)
+        self.last_flat = flat
         off = self.offsets
         grads = {p: flat[off[p]:off[p] + p.numel()].view(p.shape) for p in self.param_list}
         hook = self.grad_hook
@@ -398,7 +518,7 @@ class GeneratorEngine:
         mark(self.param_list[0])
         if mark_hi[0] != 0:
             raise AssertionError("generator backward: gradient ranges did not cover the flat buffer")
-        if hook is not None and self.grad_hook_finish is not None:
+        if hook is not None and self.grad_hook_finish is not None and not self.defer_finish:
             # autograd may copy the gradient views when it accumulates them: the reduced values must be in place
             self.grad_hook_finish()
         dlr = None

@@ -11,7 +11,7 @@ a no-op (model/vgg.py:16) are never consumed and are not computed here.
 import torch
 
 from . import ops
-from .engine_g import PackedWeight, _Plan, _run_conv
+from .engine_g import PackedWeight, PlanCache, _Plan, _Release, _run_conv
 from .ops import ACT_NONE, ACT_RELU
 
 VGG19_CFG = [64, 64, 'M', 128, 128, 'M', 256, 256, 256, 256, 'M', 512, 512, 512, 512, 'M', 512, 512, 512, 512]
@@ -22,9 +22,16 @@ class VGGEngine:
         self.vgg = vgg
         self.dtype = dtype
         self.dt = ops.dt_code(dtype)
-        self.plans = {}
+        self.plans = PlanCache(who="pesr_b200.VGG")
+        self.trace_hook = None     # callable(plan), called at the end of every forward (parity tests read the saved activations)
         self.packed = None
         self.device = None
+
+    def invalidate_packs(self):
+        """See GeneratorEngine.invalidate_packs."""
+        if self.packed is not None:
+            self.fwd_multi.key = None
+            self.bwd_multi.key = None
 
     def _conv_modules(self):
         return [m for m in self.vgg.vgg if isinstance(m, torch.nn.Conv2d)]
@@ -34,7 +41,8 @@ class VGGEngine:
         sentinel = (convs[0].weight.data_ptr(), convs[-1].bias.data_ptr())
         if self.packed is not None and self.device == device and self.sentinel == sentinel:
             return
-        self.sentinel, self.device, self.plans = sentinel, device, {}
+        self.sentinel, self.device = sentinel, device
+        self.plans.clear()
         dt = self.dtype
         self.pk_f = [PackedWeight(convs[0].weight, 4, dt, pad_to=64)] + [PackedWeight(c.weight, 0, dt) for c in convs[1:]]
         self.pk_d = [PackedWeight(convs[0].weight, 6, dt, pad_to=32)] + [PackedWeight(c.weight, 1, dt) for c in convs[1:]]
@@ -44,15 +52,14 @@ class VGGEngine:
         self.scale_ws = torch.zeros(4, device=device, dtype=torch.float32)
 
     def _plan(self, nb, h, w):
-        key = (nb, h, w)
-        pl = self.plans.get(key)
-        if pl is not None:
-            return pl
+        return self.plans.acquire((nb, h, w), lambda: self._new_plan(nb, h, w))
+
+    def _new_plan(self, nb, h, w):
         dev, tdt, dt = self.device, self.dtype, self.dt
         convs = self._conv_modules()
         nb2 = 2 * nb
         pl = _Plan()
-        pl.nb, pl.h, pl.w, pl.generation = nb, h, w, 0
+        pl.nb, pl.h, pl.w = nb, h, w
         e16 = lambda *s: torch.empty(*s, device=dev, dtype=tdt)  # noqa: E731
         pl.col0 = e16(nb2 * h * w, 64)
         # layer table: ("conv", idx, cin, cout, h, w, in_buf, out_buf) / ("pool", c, h, w, in_buf, out_buf)
@@ -112,7 +119,6 @@ class VGGEngine:
                 bwd.append(("pool", pin, g_in, nb, ph_, pw_, pc, g_out))
                 # after the pool backward the gradient lives in g_out again (at the pre-pool resolution)
         pl.bwd = bwd
-        self.plans[key] = pl
         return pl
 
     # ------------------------------------------------------------------ forward
@@ -124,7 +130,6 @@ class VGGEngine:
         nb, _, h, w = sr.shape
         self._ensure_packed(sr.device)
         pl = self._plan(nb, h, w)
-        pl.generation += 1
         self.fwd_multi.run()
         sm = self.vgg.sub_mean
         sm_w = sm.weight.detach().reshape(3, 3)
@@ -143,14 +148,16 @@ class VGGEngine:
         n_half = nb * pl.fh * pl.fw
         ops.nhwc16_to_nchw32(pl.feat16[:n_half], f_sr)
         ops.nhwc16_to_nchw32(pl.feat16[n_half:], f_hr)
-        return f_sr, f_hr, ((pl, pl.generation) if save else None)
+        if self.trace_hook is not None:
+            self.trace_hook(pl)
+        if not save:
+            return f_sr, f_hr, None
+        pl.busy = True
+        return f_sr, f_hr, (pl, _Release(pl))
 
     # ------------------------------------------------------------------ backward (to sr only)
     def backward(self, state, dfeat):
-        pl, generation = state
-        if generation != pl.generation:
-            raise RuntimeError("pesr_b200.VGG: backward through a forward whose activations were overwritten by a later "
-                               "forward of the same shape")
+        pl, _release = state
         self.bwd_multi.run()
         nb, h, w = pl.nb, pl.h, pl.w
         dfeat = dfeat.contiguous().float()

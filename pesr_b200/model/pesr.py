@@ -24,7 +24,11 @@ class _GeneratorFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, dsr):
         eng = ctx.engine
+        if ctx.state is None:
+            raise RuntimeError("pesr_b200.Generator: backward called twice through one forward (activations are "
+                               "released after the first backward; retain_graph is not supported)")
         grads, dlr = eng.backward(ctx.state, dsr, need_input_grad=ctx.needs_input_grad[1])
+        ctx.state = None        # hands the plan (the saved activations) back to the engine's pool
         out = [None, dlr]
         for i, p in enumerate(eng.param_list):
             out.append(grads.get(p) if ctx.needs_input_grad[2 + i] else None)

@@ -37,7 +37,11 @@ class _VGGFn(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dfeat, _unused):
-        return None, ctx.engine.backward(ctx.state, dfeat), None
+        if ctx.state is None:
+            raise RuntimeError("pesr_b200.VGG: backward called twice through one forward")
+        dsr = ctx.engine.backward(ctx.state, dfeat)
+        ctx.state = None
+        return None, dsr, None
 
 
 class VGG(nn.Module):

@@ -63,6 +63,14 @@ def pick_tile(h, w, nb=1, cin=0):
 TAPS_3X3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
 
 
+def default_block_n(c, choices=(256, 128, 64, 32)):
+    """Widest supported GEMM-N tile that divides c (e.g. 64 for 192 or 320 channels)."""
+    for bn in choices:
+        if c % bn == 0:
+            return bn
+    raise ValueError(f"pesr_b200: {c} channels is not a multiple of {choices[-1]}")
+
+
 def make_conv_desc(*, dtype, nb, h, w, cin, cout, block_n=None, taps=TAPS_3X3, tap_src=None, tap_widx=None,
                    srcs, wpacked, bias=None, alpha=1.0, alpha_dev=None, res32=None, ld_res32=0, res16=None,
                    ld_res16=0, act=ACT_NONE, mask16=None, ld_mask16=0, mask_mode=0, out32=None, ld_out32=0,
@@ -77,7 +85,7 @@ def make_conv_desc(*, dtype, nb, h, w, cin, cout, block_n=None, taps=TAPS_3X3, t
     d = ConvDesc()
     d.dtype = dtype
     d.nb, d.h, d.w, d.cin, d.cout = nb, h, w, cin, cout
-    d.block_n = block_n or min(cout, 256)
+    d.block_n = block_n or default_block_n(cout)
     tl = tile or pick_tile(h, w, nb, cin if (ksplit <= 1 and not b_mn_major) else 0)
     tn, th, tw = tl if len(tl) == 3 else (1,) + tuple(tl)
     d.tile_n, d.tile_h, d.tile_w = tn, th, tw
@@ -126,7 +134,7 @@ def make_wgrad_desc(*, dtype, nb, h, w, a, a_c, m_total, b_srcs, n_total, block_
     d.nb, d.h, d.w = nb, h, w
     d.m_total, d.n_total = m_total, n_total
     d.block_m = 128
-    d.block_n = block_n or min(n_total, 256)
+    d.block_n = block_n or default_block_n(n_total, (256, 128, 64))
     d.ntaps = len(taps)
     for t, (dh, dw) in enumerate(taps):
         d.tap_dh[t], d.tap_dw[t] = dh, dw
@@ -181,6 +189,16 @@ def packed_shape(co, ci, ksize, mode, pad_to=0):
     raise ValueError(mode)
 
 
+def im2col3_u8(src_u8, col, affine_a=None, affine_b=None):
+    """im2col3 straight from a uint8 HWC image batch [nb][h][w][3] (utils.imgs_to_tensors fused, utils.py:20-25)."""
+    _need_cuda(src_u8, col)
+    nb, h, w, c = src_u8.shape
+    assert c == 3 and src_u8.dtype == torch.uint8 and src_u8.is_contiguous()
+    check(lib.pesr_im2col3(_ptr(src_u8), nb, h, w, _ptr(affine_a), _ptr(affine_b), 0, 1, 4, dt_code(col.dtype),
+                           _ptr(col), _stream()), "pesr_im2col3")
+    return col
+
+
 def im2col3(src, col, affine_a=None, affine_b=None, mul_dev=None, sgn=1, pad_affine=False, upper_zeroed=False):
     """upper_zeroed: columns 32..63 of ``col`` already hold zeros (buffer created with torch.zeros and only ever written
     by this function) - they are not stored again.  Not used by the engines: measured on the GAN step it is 0.4 ms
@@ -195,10 +213,52 @@ def im2col3(src, col, affine_a=None, affine_b=None, mul_dev=None, sgn=1, pad_aff
     return col
 
 
-def col2im3(z, ldz, nb, h, w, out, bias=None, affine_a=None, affine_b=None, mul=1.0, div_dev=None, sgn=1, pre=None):
-    _need_cuda(z, out)
-    check(lib.pesr_col2im3(_ptr(z), ldz, nb, h, w, _ptr(bias), _ptr(affine_a), _ptr(affine_b), mul, _ptr(div_dev),
-                           sgn, _ptr(pre), _ptr(out), _stream()), "pesr_col2im3")
+_COL2IM_TILED = os.environ.get("PESR_COL2IM_TILED", "1") != "0"     # A/B knob: shared-memory col2im (default) vs per-pixel gather
+
+
+def col2im3(z, ldz, nb, h, w, out, bias=None, affine_a=None, affine_b=None, mul=1.0, div_dev=None, sgn=1, pre=None,
+            out_u8=None):
+    """out (fp32 NCHW) and / or out_u8 (uint8 HWC [nb][h][w][3], clip + round-half-even fused, utils.py:13-18)."""
+    _need_cuda(z, out if out is not None else out_u8)
+    if _COL2IM_TILED or out_u8 is not None:
+        check(lib.pesr_col2im3_tiled(_ptr(z), ldz, nb, h, w, _ptr(bias), _ptr(affine_a), _ptr(affine_b), mul,
+                                     _ptr(div_dev), sgn, _ptr(pre), _ptr(out), _ptr(out_u8), _stream()),
+              "pesr_col2im3_tiled")
+    else:
+        check(lib.pesr_col2im3(_ptr(z), ldz, nb, h, w, _ptr(bias), _ptr(affine_a), _ptr(affine_b), mul, _ptr(div_dev),
+                               sgn, _ptr(pre), _ptr(out), _stream()), "pesr_col2im3")
+    return out if out is not None else out_u8
+
+
+def mean_shift(x, w9, b3, out):
+    _need_cuda(x, out)
+    nb, c, h, w = x.shape
+    assert c == 3 and x.dtype == torch.float32 and x.is_contiguous()
+    check(lib.pesr_mean_shift(_ptr(x), nb, h * w, _ptr(w9), _ptr(b3), _ptr(out), _stream()), "pesr_mean_shift")
+    return out
+
+
+def psnr_y_sse(a, b, sse):
+    """sse[n] += exact integer sum of squared Y-channel differences of images a[n], b[n] (utils.py:27-41)."""
+    _need_cuda(a, b, sse)
+    nb, c, h, w = a.shape
+    assert c == 3 and a.shape == b.shape and a.dtype == b.dtype == torch.float32 and sse.dtype == torch.int64
+    assert a.is_contiguous() and b.is_contiguous() and sse.numel() >= nb
+    check(lib.pesr_psnr_y_sse(_ptr(a), _ptr(b), nb, h * w, _ptr(sse), _stream()), "pesr_psnr_y_sse")
+    return sse
+
+
+def gather_patches(table_dev, nb, patch, scale, lr, hr):
+    check(lib.pesr_gather_patches(_ptr(table_dev), nb, patch, scale, _ptr(lr), _ptr(hr), _stream()),
+          "pesr_gather_patches")
+
+
+def u8hwc_to_f32nchw(src_u8, out):
+    """uint8 HWC [nb][h][w][3] -> fp32 NCHW (utils.imgs_to_tensors, utils.py:20-25)."""
+    _need_cuda(src_u8, out)
+    nb, h, w, c = src_u8.shape
+    assert c == 3 and src_u8.dtype == torch.uint8 and src_u8.is_contiguous()
+    check(lib.pesr_u8hwc_to_f32nchw_batch(_ptr(src_u8), nb, h, w, _ptr(out), _stream()), "pesr_u8hwc_to_f32nchw_batch")
     return out
 
 
@@ -261,6 +321,11 @@ def adam_multi(table, nchunks, lr, beta1, beta2, eps, step, grad_mul=1.0):
           "pesr_adam_multi")
 
 
+def adam_multi_dev(table, nchunks, lr_dev, beta1, beta2, eps, step_dev, grad_mul=1.0):
+    check(lib.pesr_adam_multi_dev(_ptr(table), nchunks, _ptr(lr_dev), beta1, beta2, eps, _ptr(step_dev), grad_mul,
+                                  _stream()), "pesr_adam_multi_dev")
+
+
 def bn_stats(y16, npix, c, sums_ws, mean, rstd, running_mean=None, running_var=None, num_batches=None, eps=1e-5,
              momentum=0.1, running_mean_shift=None):
     # y16 = None: the sums come from the producing conv (make_conv_desc(bn_sums=...)); only the finalisation runs
@@ -294,9 +359,18 @@ def linear_workspace_floats(nb, k, o):
     return int(lib.pesr_linear_workspace_floats(nb, k, o))
 
 
+_LINEAR_ROWS = 16     # rows per pass of the skinny Linear kernels (pesr_linear_skinny_*); larger batches are chunked
+
+
 def linear_fwd(x16, w16, bias, nb, k, o, workspace, out32=None, out16=None, act=ACT_NONE):
-    check(lib.pesr_linear_skinny_fwd(_ptr(x16), _ptr(w16), _ptr(bias), nb, k, o, act, dt_code(x16.dtype),
-                                     _ptr(workspace), _ptr(out32), _ptr(out16), _stream()), "pesr_linear_skinny_fwd")
+    x16, out32, out16 = x16.view(nb, k), (out32.view(nb, o) if out32 is not None else None), \
+        (out16.view(nb, o) if out16 is not None else None)
+    for r in range(0, nb, _LINEAR_ROWS):
+        n = min(_LINEAR_ROWS, nb - r)
+        check(lib.pesr_linear_skinny_fwd(_ptr(x16[r:]), _ptr(w16), _ptr(bias), n, k, o, act, dt_code(x16.dtype),
+                                         _ptr(workspace), _ptr(out32[r:] if out32 is not None else None),
+                                         _ptr(out16[r:] if out16 is not None else None), _stream()),
+              "pesr_linear_skinny_fwd")
 
 
 def linear_finalize(partials, ksplit, nb, o, bias, dtype, out32=None, out16=None, act=ACT_NONE):
@@ -305,13 +379,20 @@ def linear_finalize(partials, ksplit, nb, o, bias, dtype, out32=None, out16=None
 
 
 def linear_dgrad(dy32, w16, nb, k, o, dx32):
-    check(lib.pesr_linear_skinny_dgrad(_ptr(dy32), _ptr(w16), nb, k, o, dt_code(w16.dtype), _ptr(dx32), _stream()),
-          "pesr_linear_skinny_dgrad")
+    dy32, dx32 = dy32.view(nb, o), dx32.view(nb, k)
+    for r in range(0, nb, _LINEAR_ROWS):
+        n = min(_LINEAR_ROWS, nb - r)
+        check(lib.pesr_linear_skinny_dgrad(_ptr(dy32[r:]), _ptr(w16), n, k, o, dt_code(w16.dtype), _ptr(dx32[r:]),
+                                           _stream()), "pesr_linear_skinny_dgrad")
 
 
 def linear_wgrad(dy32, x16, nb, k, o, dw, mul=1.0, div_dev=None, accumulate=False):
-    check(lib.pesr_linear_skinny_wgrad(_ptr(dy32), _ptr(x16), nb, k, o, mul, _ptr(div_dev), 1 if accumulate else 0,
-                                       dt_code(x16.dtype), _ptr(dw), _stream()), "pesr_linear_skinny_wgrad")
+    dy32, x16 = dy32.view(nb, o), x16.view(nb, k)
+    for r in range(0, nb, _LINEAR_ROWS):
+        n = min(_LINEAR_ROWS, nb - r)
+        check(lib.pesr_linear_skinny_wgrad(_ptr(dy32[r:]), _ptr(x16[r:]), n, k, o, mul, _ptr(div_dev),
+                                           1 if (accumulate or r > 0) else 0, dt_code(x16.dtype), _ptr(dw), _stream()),
+              "pesr_linear_skinny_wgrad")
 
 
 def cast16(src32, dst16):

@@ -18,7 +18,7 @@ import torch.distributed as dist
 class DataParallel(torch.nn.Module):
     """Wraps a pesr_b200 network; exposes ``.module`` like nn.DataParallel (train.py:303,309)."""
 
-    def __init__(self, module, process_group=None, bucket_mb=32):
+    def __init__(self, module, process_group=None, bucket_mb=32, defer_finish=True):
         super().__init__()
         self.module = module
         self.pg = process_group
@@ -27,6 +27,7 @@ class DataParallel(torch.nn.Module):
         self._pending = None      # (lo, hi, flat) accumulated, not yet reduced
         self._works = []
         self._comm_stream = None
+        self._engine = None
         if self.world_size > 1:
             self._broadcast_parameters()
             eng = getattr(module, "engine", None)
@@ -34,6 +35,11 @@ class DataParallel(torch.nn.Module):
                 e = module.engine()
                 e.grad_hook = self._on_range
                 e.grad_hook_finish = self.finish
+                # the step bodies (pesr_b200.steps) call finish() right before optimizer.step(): the kernels issued
+                # between backward and that call (e.g. the Generator-phase VGG forward while D's 321 MB are on the wire)
+                # overlap the all-reduce instead of waiting for it inside backward
+                e.defer_finish = defer_finish
+                self._engine = e
 
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)
@@ -87,7 +93,29 @@ class DataParallel(torch.nn.Module):
                 flat[lo:hi].div_(self.world_size)
             else:
                 torch.cuda.current_stream().wait_event(w)
+        had_work = bool(self._works)
         self._works = []
+        if had_work:
+            self._sync_grad_views()
+
+    def _sync_grad_views(self):
+        """The all-reduce ran in place on the engine's flat buffer.  Autograd normally keeps the views it was handed as
+        `.grad` (then there is nothing to do); if it copied them instead, bring the reduced values to the copies."""
+        e = self._engine
+        flat = getattr(e, "last_flat", None) if e is not None else None
+        if flat is None:
+            return
+        off = e.offsets
+        plist = [p for p in e.param_list if p.grad is not None]
+        if not plist:
+            return
+        base = flat.data_ptr()
+        if all(p.grad.data_ptr() == base + 4 * off[p] for p in (plist[0], plist[-1])):
+            return
+        with torch.no_grad():
+            for p in plist:
+                if p.grad.data_ptr() != base + 4 * off[p]:
+                    p.grad.copy_(flat[off[p]:off[p] + p.numel()].view_as(p))
 
     # ---- fallback for modules without a flat-gradient schedule
     def allreduce_grads(self):

@@ -48,8 +48,10 @@ def gan_step(G, D, vgg, optim_G, optim_D, lr, hr, cfg, ddp_g=None, ddp_d=None):
         total_D_loss = losses.rsgan_bce(pred_real, pred_fake, t_real)
     total_D_loss.backward()
     # The Generator-phase terms that do not involve D (train.py:240-247) are issued BEFORE waiting for D's gradient
-    # all-reduce: VGG's forward, L1 and TV depend on sr / hr only, so they keep the SMs busy while the 321 MB of
-    # Discriminator gradients are still on the wire.  Values are unchanged (nothing here reads D or its optimiser).
+    # all-reduce (DataParallel(defer_finish=True): backward returns with the last buckets still in flight and
+    # ddp_d.finish() below is the wait): VGG's forward, L1 and TV depend on sr / hr only, so they keep the SMs busy
+    # while the 321 MB of Discriminator gradients are on the wire.  Values are unchanged (nothing here reads D or its
+    # optimiser).
     optim_G.zero_grad(set_to_none=True)
     l1_loss = losses.l1_loss(sr, hr) * cfg['alpha_l1']
     f_sr, f_hr = vgg(sr, hr)

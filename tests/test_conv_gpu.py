@@ -41,10 +41,10 @@ CASES = [  # nb, cin, cout, h, w   (G trunk, upsampler, D/VGG channel counts, ra
 @pytest.fixture(params=[1, 2, 0], ids=["pair-auto", "pair-forced", "pair-off"])
 def pair_mode(request):
     """Runs a test with the CTA-pair (cta_group::2) kernel chosen automatically, forced wherever legal, and disabled."""
-    from pesr_b200._lib import lib
-    lib.pesr_debug_pair_mode(request.param)
+    from pesr_b200 import _lib
+    _lib.set_option(_lib.OPT_PAIR_MODE, request.param)
     yield request.param
-    lib.pesr_debug_pair_mode(1)
+    _lib.set_option(_lib.OPT_PAIR_MODE, 1)
 
 
 @pytest.mark.parametrize("nb,cin,cout,h,w", CASES)

@@ -18,6 +18,22 @@ from pesr_b200 import ops  # noqa: E402
 from pesr_b200._lib import lib  # noqa: E402
 
 
+
+# bring-up hooks live in the debug build only: run with PESR_B200_LIB=pesr_b200/libpesr_b200_debug.so (tools/build_debug.sh)
+from pesr_b200 import _debug as _dbg, _lib as _L   # noqa: E402
+_dbg.bind()
+
+
+def _set_pair_mode_compat(mode):
+    """round-1 encoding of the option hook: 0/1/2 pair mode, 20x sub stages, 30x PDL, 40x staged epilogue, 50x specialised epilogue"""
+    if mode >= 500: _L.set_option(_L.OPT_SPECIALISED_EPILOGUE, mode - 500)
+    elif mode >= 400: _L.set_option(_L.OPT_STAGED_EPILOGUE, mode - 400)
+    elif mode >= 300: _L.set_option(_L.OPT_PDL, mode - 300)
+    elif mode >= 200: _L.set_option(_L.OPT_SUB_STAGES, mode - 200)
+    elif mode >= 100: pass
+    else: _L.set_option(_L.OPT_PAIR_MODE, mode)
+
+
 def rel(a, b):
     return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
 
@@ -216,7 +232,7 @@ def vgg_debug(nb=2, side=64, seed=0, dtype=torch.float16):
     hr = torch.rand(nb, 3, side, side, generator=g) * 255
     with torch.no_grad():
         V(sr.cuda(), hr.cuda())
-    pl = V.engine().plans[(nb, side, side)]
+    pl = V.engine().plans[(nb, side, side)][-1]
     q = lambda t: t.to(dtype).double()
     x = F.conv2d(sr.double(), sd['sub_mean.weight'].double(), sd['sub_mean.bias'].double())
     idx, k = 0, 0

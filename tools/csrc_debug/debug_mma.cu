@@ -1,7 +1,8 @@
 // Bring-up microbenchmark: issue-rate of back-to-back tcgen05.mma (M=128, N=n, K=16, SS operands) with no loads and
 // no barriers inside the loop.  Tells the hardware floor the implicit-GEMM mainloop can be compared with.
-#include "common.cuh"
-#include "host_util.cuh"
+#include "../../pesr_b200/csrc/common.cuh"
+#include "../../pesr_b200/csrc/host_util.cuh"
+#include "../../include/pesr_b200_debug.h"
 
 namespace pesr {
 

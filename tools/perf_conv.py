@@ -11,6 +11,22 @@ from pesr_b200 import ops
 FLUSH = None
 
 
+
+# bring-up hooks live in the debug build only: run with PESR_B200_LIB=pesr_b200/libpesr_b200_debug.so (tools/build_debug.sh)
+from pesr_b200 import _debug as _dbg, _lib as _L   # noqa: E402
+_dbg.bind()
+
+
+def _set_pair_mode_compat(mode):
+    """round-1 encoding of the option hook: 0/1/2 pair mode, 20x sub stages, 30x PDL, 40x staged epilogue, 50x specialised epilogue"""
+    if mode >= 500: _L.set_option(_L.OPT_SPECIALISED_EPILOGUE, mode - 500)
+    elif mode >= 400: _L.set_option(_L.OPT_STAGED_EPILOGUE, mode - 400)
+    elif mode >= 300: _L.set_option(_L.OPT_PDL, mode - 300)
+    elif mode >= 200: _L.set_option(_L.OPT_SUB_STAGES, mode - 200)
+    elif mode >= 100: pass
+    else: _L.set_option(_L.OPT_PAIR_MODE, mode)
+
+
 def timeit(fn, iters=10, warm=3, flush=True):
     global FLUSH
     if FLUSH is None:
@@ -156,7 +172,7 @@ if __name__ == "__main__":
         buf2 = torch.zeros(64 + 2 * 160, dtype=torch.int64, device="cuda")
         lib.pesr_debug_timeline(buf2.data_ptr())
         for pm in (0, 2):
-            lib.pesr_debug_pair_mode(pm)
+            _set_pair_mode_compat(pm)
             conv_case(16, 256, 256, 48, 48)
             torch.cuda.synchronize()
             b = buf2.cpu().tolist()
@@ -167,7 +183,7 @@ if __name__ == "__main__":
             print(f"  fprop pair={pm} per-CTA: starts spread {(max(st)-t0)/1e3:.1f} us, first end {(min(en)-t0)/1e3:.1f}, last end {(max(en)-t0)/1e3:.1f} us, "
                   f"CTA duration min/median/max {durs[0]:.1f}/{durs[len(durs)//2]:.1f}/{durs[-1]:.1f} us")
         lib.pesr_debug_timeline(0)
-        lib.pesr_debug_pair_mode(1)
+        _set_pair_mode_compat(1)
     if what == "epi":      # chunk-level timeline of the LAST tile's epilogue of block 0 (trunk conv, light and heavy epilogue)
         from pesr_b200._lib import lib
         buf = torch.zeros(64 + 2 * 160, dtype=torch.int64, device="cuda")
@@ -185,8 +201,8 @@ if __name__ == "__main__":
             "mask16 -> out16": dict(mask16=x16, ld_mask16=c, mask_mode=1, out16=out16, ld_out16=c),
         }
         for label, light, staged in (("specialised+staged", 501, 401), ("specialised direct", 501, 400), ("generic", 500, 400)):
-            lib.pesr_debug_pair_mode(light)
-            lib.pesr_debug_pair_mode(staged)
+            _set_pair_mode_compat(light)
+            _set_pair_mode_compat(staged)
             for name, epi in variants.items():
                 d = ops.make_conv_desc(dtype=0, nb=nb, h=h, w=w, cin=c, cout=c, srcs=[ops.nhwc_src(x16, nb, h, w, c)], wpacked=wp, **epi)
                 for flush in (True, False):
@@ -198,8 +214,8 @@ if __name__ == "__main__":
                           f"last tile: acc complete {b[20]-t0}, chunks done at "
                           + " ".join(f"+{b[25+i]-b[20]}" for i in range(8)) + f" | end {b[61]-t0}", flush=True)
         lib.pesr_debug_timeline(0)
-        lib.pesr_debug_pair_mode(401)
-        lib.pesr_debug_pair_mode(501)
+        _set_pair_mode_compat(401)
+        _set_pair_mode_compat(501)
     if what == "timeline":
         from pesr_b200._lib import lib
         buf = torch.zeros(64, dtype=torch.int64, device="cuda")
@@ -208,7 +224,7 @@ if __name__ == "__main__":
                  10: "t0 MMAs issued", 12: "tL acc free", 13: "tL first stage landed", 14: "tL MMAs issued", 16: "t0 acc complete",
                  17: "t0 epilogue done", 20: "tL acc complete", 21: "tL epilogue done", 61: "end"}
         for pair in (0, 1):
-            lib.pesr_debug_pair_mode(pair)
+            _set_pair_mode_compat(pair)
             for shape in ((16, 256, 256, 48, 48), (16, 256, 1024, 96, 96), (16, 64, 64, 192, 192), (16, 512, 512, 24, 24)):
                 conv_case(*shape)
                 torch.cuda.synchronize()
@@ -232,9 +248,9 @@ if __name__ == "__main__":
             conv_case(32, 256, 256, 48, 48, block_n=bn)
     if what == "sub":
         from pesr_b200._lib import lib
-        lib.pesr_debug_pair_mode(0)
+        _set_pair_mode_compat(0)
         for mode in (201, 202):
-            lib.pesr_debug_pair_mode(mode)
+            _set_pair_mode_compat(mode)
             print("sub-block stages", mode - 200, "(pair off)")
             conv_case(16, 512, 512, 24, 24)
             conv_case(32, 512, 512, 24, 24)
@@ -242,12 +258,12 @@ if __name__ == "__main__":
             conv_case(32, 512, 512, 12, 12)
             conv_case(16, 128, 256, 48, 48)
             conv_case(16, 256, 256, 48, 48)
-        lib.pesr_debug_pair_mode(1)
-        lib.pesr_debug_pair_mode(201)
+        _set_pair_mode_compat(1)
+        _set_pair_mode_compat(201)
     if what == "pair":
         from pesr_b200._lib import lib
         for mode in (0, 2):
-            lib.pesr_debug_pair_mode(mode)
+            _set_pair_mode_compat(mode)
             print("pair mode", mode)
             conv_case(16, 256, 256, 48, 48)
             conv_case(16, 256, 1024, 96, 96)

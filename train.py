@@ -6,9 +6,10 @@
     torchrun --nproc-per-node 8 train.py ...                      # one process per GPU (replaces nn.DataParallel)
 
 Additions to the reference's flags: --synthetic (random tensors instead of data/, for machines without the
-dataset), --max_iters, --log_every, --vgg_random.  The dataset / tensorboard / validation plumbing of the reference is out of the
-hot path's scope; a minimal PNG-folder dataset with the reference's directory layout is
-provided so that the script is usable end to end.
+dataset), --max_iters, --log_every, --vgg_random, --resume.  Training patches come from a device-resident uint8 image
+cache through one gather kernel per batch (pesr_b200.data.PatchSource, data.py:64-126); validation (train.py:281-295)
+computes the Y-channel PSNR on the device (pesr_b200.utils, utils.py:27-41); besides the reference's G-only snapshots
+(model_<epoch>.pt, best_model.pt) a full resumable state is written.  tensorboard logging is not reproduced.
 """
 import argparse
 import glob
@@ -19,9 +20,12 @@ import torch
 import torch.distributed as dist
 
 from pesr_b200 import steps
+from pesr_b200.data import PatchSource
+from pesr_b200.infer import imgs_to_tensor
 from pesr_b200.model import VGG, Discriminator, Generator
 from pesr_b200.optim import Adam
 from pesr_b200.parallel import DataParallel
+from pesr_b200.utils import PSNRMeter
 
 
 def _bool(x):
@@ -60,6 +64,8 @@ parser.add_argument('--max_iters', type=int, default=0, help='stop an epoch afte
 parser.add_argument('--vgg_random', action='store_true', help='random-init VGG19 instead of torchvision\'s ImageNet '
                     'checkpoint (machines without network access)')
 parser.add_argument('--log_every', type=int, default=50)
+parser.add_argument('--resume', type=str, default='', help='full training state written by this script '
+                    '(<check_point>/<phase>/state_<epoch>.pt): networks, both Adam states, epoch, RNG')
 
 
 def read_png(path):
@@ -72,49 +78,52 @@ def read_png(path):
         return torch.from_numpy(np.asarray(Image.open(path).convert('RGB')).copy())
 
 
-class PatchSource:
-    """Aligned random LR/HR crops with the 8-way flip/transpose augmentation of data.py:64-126, produced on the GPU
-    from device-resident uint8 images (or random tensors with --synthetic)."""
+def load_pairs(root, device, limit=None):
+    """data.py:30-53: sorted LR/HR PNG pairs of one dataset directory, kept on the device as uint8 HWC."""
+    lr = sorted(glob.glob(os.path.join(root, 'LR', '*.png')))
+    hr = sorted(glob.glob(os.path.join(root, 'HR', '*.png')))
+    if not hr or len(lr) != len(hr):
+        raise Exception('No images found in %s (use --synthetic to train on random tensors)' % root)
+    if limit:
+        lr, hr = lr[:limit], hr[:limit]
+    return [(read_png(a).to(device), read_png(b).to(device)) for a, b in zip(lr, hr)]
 
-    def __init__(self, args, device):
-        self.args, self.device, self.images = args, device, None
-        if not args.synthetic:
-            root = os.path.join('data/origin/train', args.train_dataset)
-            lr = sorted(glob.glob(os.path.join(root, 'LR', '*.png')))
-            hr = sorted(glob.glob(os.path.join(root, 'HR', '*.png')))
-            if not hr or len(lr) != len(hr):
-                raise Exception('No images found (use --synthetic to train on random tensors)')
-            self.images = [(read_png(a).to(device), read_png(b).to(device)) for a, b in zip(lr, hr)]
-        self.per_epoch = (800 if self.images is None else len(self.images)) * args.num_repeats
 
-    def batch(self):
-        a, dev = self.args, self.device
-        p, s, b = a.patch_size, a.scale, a.batch_size
-        if self.images is None:
-            return torch.rand(b, 3, p, p, device=dev) * 255, torch.rand(b, 3, p * s, p * s, device=dev) * 255
-        lrs, hrs = [], []
-        for _ in range(b):
-            lr, hr = random.choice(self.images)
-            y, x = random.randrange(lr.shape[0] - p + 1), random.randrange(lr.shape[1] - p + 1)
-            l = lr[y:y + p, x:x + p].permute(2, 0, 1).float()
-            h = hr[y * s:(y + p) * s, x * s:(x + p) * s].permute(2, 0, 1).float()
-            k = random.randrange(8)
-            if k & 1:
-                l, h = l.flip(2), h.flip(2)
-            if k & 2:
-                l, h = l.flip(1), h.flip(1)
-            if k & 4:
-                l, h = l.transpose(1, 2), h.transpose(1, 2)
-            lrs.append(l)
-            hrs.append(h)
-        return torch.stack(lrs).contiguous(), torch.stack(hrs).contiguous()
+def rng_state():
+    import numpy as np
+    return {'python': random.getstate(), 'numpy': np.random.get_state(), 'torch': torch.get_rng_state(),
+            'cuda': torch.cuda.get_rng_state()}
+
+
+def set_rng_state(st):
+    import numpy as np
+    random.setstate(st['python'])
+    np.random.set_state(st['numpy'])
+    torch.set_rng_state(st['torch'])
+    torch.cuda.set_rng_state(st['cuda'])
+
+
+def save_full_state(path, epoch, best_psnr, G, optim_G, D=None, optim_D=None):
+    """Everything a resume needs (the reference only ever saves G, train.py:297-310): both networks incl. BatchNorm
+    running statistics, both Adam states, the epoch counter (which determines the learning rate), the best validation
+    PSNR and the random-number generator states."""
+    st = {'epoch': epoch, 'best_psnr': best_psnr, 'G': G.module.state_dict(), 'optim_G': optim_G.state_dict(),
+          'rng': rng_state()}
+    if D is not None:
+        st.update(D=D.module.state_dict(), optim_D=optim_D.state_dict())
+    tmp = path + '.tmp'
+    torch.save(st, tmp)
+    os.replace(tmp, path)
 
 
 def main():
     args = parser.parse_args()
     if args.GP:
-        raise NotImplementedError('--GP true (gradient penalty, train.py:216-226) needs second-order conv backward; '
-                                  'it is off by default in the reference and outside the B200 hot path')
+        raise NotImplementedError('--GP true (gradient penalty, train.py:216-226) differentiates D\'s backward pass a second '
+                                  'time (create_graph=True through conv / train-mode BatchNorm); the B200 schedules '
+                                  'implement first-order backward only. It is off by default in the reference.')
+    if args.num_channels % 64 != 0:
+        raise SystemExit('--num_channels must be a multiple of 64 (tensor-core K block)')
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -132,13 +141,12 @@ def main():
         G.load_state_dict(torch.load(args.pretrained_model, map_location='cpu'))
     G = DataParallel(G.to(device))
     optim_G = Adam([p for p in G.parameters() if p.requires_grad], betas=(0.9, 0.999), lr=args.learning_rate)
-    sched_G = torch.optim.lr_scheduler.StepLR(optim_G, step_size=args.lr_step, gamma=0.5)
     gan = args.phase != 'pretrain'
+    D = optim_D = None
     if gan:
         D = DataParallel(Discriminator(opt).to(device))
         vgg = VGG(pretrained=not args.vgg_random).to(device)
         optim_D = Adam(D.parameters(), betas=(0.9, 0.999), lr=args.learning_rate)
-        sched_D = torch.optim.lr_scheduler.StepLR(optim_D, step_size=args.lr_step, gamma=0.5)
         cfg = dict(alpha_l1=args.alpha_l1, alpha_vgg=args.alpha_vgg, alpha_gan=args.alpha_gan, alpha_tv=args.alpha_tv,
                    fl_gamma=args.fl_gamma, gan_type=args.gan_type, focal_loss=args.focal_loss,
                    target_real=torch.ones(args.batch_size, 1, device=device),
@@ -146,12 +154,42 @@ def main():
     check_point = os.path.join(args.check_point, args.phase)
     if rank == 0:
         os.makedirs(check_point, exist_ok=True)
-    data = PatchSource(args, device)
+    images = None if args.synthetic else load_pairs(os.path.join('data/origin/train', args.train_dataset), device)
+    data = PatchSource(images, args.patch_size, args.scale, args.batch_size, device, num_repeats=args.num_repeats)
+    # validation set (train.py:99-104): whole images, batch 1
+    if args.synthetic:
+        vside = 2 * args.patch_size
+        gen = torch.Generator().manual_seed(1234)
+        val = [((torch.rand(vside, vside, 3, generator=gen) * 255).to(torch.uint8).to(device),
+                (torch.rand(vside * args.scale, vside * args.scale, 3, generator=gen) * 255).to(torch.uint8).to(device))
+               for _ in range(min(args.num_valids, 2))]
+    else:
+        val = load_pairs(os.path.join('data/origin/valid', args.valid_dataset), device, limit=args.num_valids)
     iters = data.per_epoch // (args.batch_size * world)
     if args.max_iters:
         iters = min(iters, args.max_iters)
-    for epoch in range(1, args.num_epochs + 1):
-        cur_lr = optim_G.param_groups[0]['lr']
+    best_psnr, start_epoch = 0.0, 1
+    if args.resume:
+        st = torch.load(args.resume, map_location='cpu', weights_only=False)
+        G.module.load_state_dict(st['G'])
+        optim_G.load_state_dict(st['optim_G'])
+        if gan and 'D' in st:
+            D.module.load_state_dict(st['D'])
+            optim_D.load_state_dict(st['optim_D'])
+        best_psnr, start_epoch = st['best_psnr'], st['epoch'] + 1
+        set_rng_state(st['rng'])
+        if rank == 0:
+            print('Resumed from %s at epoch %d' % (args.resume, start_epoch))
+    for epoch in range(start_epoch, args.num_epochs + 1):
+        # train.py:156,185-186 call StepLR.step() at the START of every epoch.  Under the pinned torch 0.4 (README.md:22)
+        # the scheduler's counter starts at -1, so epoch e (1-based) runs at lr * 0.5 ** ((e - 1) // lr_step): the first
+        # halving takes effect in epoch lr_step + 1.  (The same script on torch >= 1.1 would halve one epoch earlier.)
+        # The rate is set explicitly so that it does not depend on the installed torch's scheduler semantics.
+        cur_lr = args.learning_rate * 0.5 ** ((epoch - 1) // args.lr_step)
+        for o in (optim_G, optim_D):
+            if o is not None:
+                for g in o.param_groups:
+                    g['lr'] = cur_lr
         if rank == 0:
             print('Model {}. Epoch [{}/{}]. Learning rate: {}'.format(check_point, epoch, args.num_epochs, cur_lr))
         running = torch.zeros(5 if gan else 1, device=device)
@@ -171,13 +209,32 @@ def main():
                       % (epoch, args.num_epochs, avr[0], avr[1], avr[2], avr[3], sum(avr[0:4]), avr[4]))
             else:
                 print('Finish train [%d/%d]. Loss: %.2f' % (epoch, args.num_epochs, avr[0]))
+        # ---- validation (train.py:281-295): G stays in train mode in the reference (it has no BatchNorm / dropout);
+        # Y-channel PSNR is accumulated on the device, one read-back per epoch
+        if rank == 0:
+            print('Validating...')
+            meter = PSNRMeter(device)
+            with torch.no_grad():
+                for lr_u8, hr_u8 in val:
+                    sr = G(imgs_to_tensor(lr_u8))
+                    h = min(sr.shape[2], hr_u8.shape[0])
+                    w = min(sr.shape[3], hr_u8.shape[1])
+                    meter.update(imgs_to_tensor(hr_u8)[:, :, :h, :w].contiguous(), sr[:, :, :h, :w].contiguous())
+            val_psnr = meter.value()
+            if not gan:
+                print('Finish valid [%d/%d]. Best PSNR: %.4fdB. Cur PSNR: %.4fdB' % (epoch, args.num_epochs, best_psnr, val_psnr))
+                if best_psnr < val_psnr:
+                    best_psnr = val_psnr
+                    torch.save(G.module.state_dict(), os.path.join(check_point, 'best_model.pt'))    # train.py:297-303
+                    print('Saved new best model.')
+            else:
+                print('Finish valid [%d/%d]. PSNR: %.4fdB' % (epoch, args.num_epochs, val_psnr))
             if epoch % args.snapshot_every == 0 or epoch == args.num_epochs:
-                model_path = os.path.join(check_point, 'model_{}.pt'.format(epoch))
-                torch.save(G.module.state_dict(), model_path)                     # train.py:303,309
+                torch.save(G.module.state_dict(), os.path.join(check_point, 'model_{}.pt'.format(epoch)))   # train.py:306-310
                 print('Saved snapshot model.')
-        sched_G.step()
-        if gan:
-            sched_D.step()
+                save_full_state(os.path.join(check_point, 'state_{}.pt'.format(epoch)), epoch, best_psnr, G, optim_G,
+                                D, optim_D)
+            print('')
     if world > 1:
         dist.destroy_process_group()
 

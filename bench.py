@@ -36,16 +36,18 @@ def step_gflop(workload):
 
 
 def measured_peaks():
+    """Roofline denominators: the driver-written MEASURED_PEAKS.json (cuBLAS bf16 8192^3: best-of-10 "burst" and 4 s
+    back-to-back "sustained"; torch copy bandwidth), else the fallback of B200_PROFILING.md."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         try:
             with open(path) as f:
                 d = json.load(f)
-            return dict(tflops=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), hbm=float(d["hbm_gbs"]),
-                        source="MEASURED_PEAKS.json bf16_tflops_sustained (of measured)")
+            return dict(tflops=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), burst=float(d["bf16_tflops"]),
+                        hbm=float(d["hbm_gbs"]), source="MEASURED_PEAKS.json bf16_tflops_sustained (of measured)")
         except Exception:
             pass
-    return dict(tflops=1400.0, hbm=6650.0, source="B200_PROFILING.md fallback, sustained (of fallback)")
+    return dict(tflops=1400.0, burst=1650.0, hbm=6650.0, source="B200_PROFILING.md fallback, sustained (of fallback)")
 
 
 class ClockSampler:
@@ -129,27 +131,33 @@ def cpu_step_time(workload, batch, reps=1, warm=0):
 
 
 def run_reference(args):
+    """CPU arm: the oracle port on every host core, FULL 16-sample batches (the same config as the B200 arm), `steps`
+    timed steps after `warmup` untimed ones; no rescaling of the measured time."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     cores = os.cpu_count() or 1
+    batch = BATCH
     t_probe = cpu_step_time(args.workload, 1)
-    budget = 150.0
-    total_steps = args.steps + args.warmup
-    batch = int(max(1, min(BATCH, budget / max(t_probe, 1e-3) / max(total_steps, 1))))
+    est = t_probe * BATCH * 0.8 * (args.steps + args.warmup)
+    note = ""
+    if est > 1500.0:      # only if someone asks for hundreds of CPU steps: keep the run bounded and say so
+        batch = int(max(1, min(BATCH, 1500.0 / (t_probe * 0.8 * (args.steps + args.warmup)))))
+        note = f" (batch reduced from {BATCH}: {args.steps + args.warmup} full-batch steps would take ~{est:.0f} s)"
     for _ in range(args.warmup):
         cpu_step_time(args.workload, batch)
     t = cpu_step_time(args.workload, batch, reps=args.steps)
     value = batch / t
-    sample = f"{args.steps} steps of a {batch}-sample batch (of {BATCH}) after {args.warmup} warm-up steps, fp32, torch CPU"
+    sample = (f"{args.steps} steps of a {batch}-sample batch after {args.warmup} warm-up steps, fp32, torch CPU "
+              f"({torch.get_num_threads()} threads){note}")
     line = {
         "impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3 * BATCH / batch, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(args.workload, args.gpus),
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample,
-                         "threads": torch.get_num_threads()},
+                         "threads": torch.get_num_threads(), "batch": batch},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -171,11 +179,25 @@ def config_dict(workload, n):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+def _event_timed(fn, k, barrier=None):
+    """CUDA-event time (ms) of k calls of fn(i), synchronised on both sides."""
+    import torch
+    (barrier or torch.cuda.synchronize)()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(k):
+        fn(i)
+    e1.record()
+    (barrier or torch.cuda.synchronize)()
+    return e0.elapsed_time(e1)
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
     import pesr_b200._lib as L
     from pesr_b200 import steps
+    from pesr_b200.graph import GraphedStep
     from pesr_b200.model import Generator
     from pesr_b200.optim import Adam
     from pesr_b200.parallel import DataParallel
@@ -196,8 +218,8 @@ def run_b200(args):
     if world > 1:
         Gw = DataParallel(G)
         ddp_g = Gw
-    optim_G = Adam([p for p in G.parameters() if p.requires_grad], lr=5e-5, betas=(0.9, 0.999))
-    cfg = None
+    optim_G = Adam([p for p in G.parameters() if p.requires_grad], lr=5e-5, betas=(0.9, 0.999), capturable=True)
+    cfg, D, vgg, optim_D = None, None, None, None
     if args.workload == "gan":
         from pesr_b200.model import VGG, Discriminator
         D = Discriminator(OPT).to(dev)
@@ -206,7 +228,7 @@ def run_b200(args):
         if world > 1:
             Dw = DataParallel(D)
             ddp_d = Dw
-        optim_D = Adam(D.parameters(), lr=5e-5, betas=(0.9, 0.999))
+        optim_D = Adam(D.parameters(), lr=5e-5, betas=(0.9, 0.999), capturable=True)
         cfg = dict(steps.DEFAULT_GAN_CFG)
         cfg['target_real'] = torch.ones(BATCH, 1, device=dev)
         cfg['target_fake'] = torch.zeros(BATCH, 1, device=dev)
@@ -218,52 +240,79 @@ def run_b200(args):
     dev_lr = [t.to(dev) for t in host_lr]
     dev_hr = [t.to(dev) for t in host_hr]
 
-    def do_step(lr, hr):
+    def eager_step(lr, hr):
         if args.workload == "gan":
             return steps.gan_step(Gw, Dw, vgg, optim_G, optim_D, lr, hr, cfg, ddp_g=ddp_g, ddp_d=ddp_d)
-        return steps.pretrain_step(Gw, optim_G, lr, hr, ddp=ddp_g)
+        return steps.pretrain_step(Gw, optim_G, lr, hr, ddp=ddp_g).reshape(1)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    host_ms = [0.0]
+    # ---- the step as a CUDA graph (pesr_b200.graph): one cudaGraphLaunch per step instead of ~700 launches from Python
+    warm = max(args.warmup, 3)
+    for i in range(warm):
+        eager_step(dev_lr[i % n_host], dev_hr[i % n_host])
+    barrier()
+    launches_per_step, graph_note, do_step = None, None, eager_step
+    if not args.no_graph and (world == 1 or args.graph_multi):
+        try:
+            L.launch_count(reset=True)
+            mods = [m for m in (G, D, vgg) if m is not None]
+            opts = [o for o in (optim_G, optim_D) if o is not None]
+            gstep = GraphedStep(eager_step, (dev_lr[0], dev_hr[0]), modules=mods, optimizers=opts, warmup=2)
+            launches_per_step = L.launch_count() // 3          # 2 warm-up steps + the captured one went through the launchers
+            do_step = gstep
+        except Exception as e:       # the eager path stays valid; say what happened
+            graph_note = f"CUDA-graph capture failed, eager launches used: {type(e).__name__}: {str(e)[:300]}"
+            print("[bench] " + graph_note, file=sys.stderr, flush=True)
+            torch.cuda.synchronize()
+    graphed = do_step is not eager_step
+    if launches_per_step is None:
+        L.launch_count(reset=True)
+        eager_step(dev_lr[0], dev_hr[0])
+        launches_per_step = L.launch_count()
 
     def timed(fn, k):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(k):
-            fn(i)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
+        ms = _event_timed(fn, k, barrier)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
 
-    # ---- resident-input arm (value)
-    for i in range(max(args.warmup, 3)):
+    # ---- resident-input arm (value): EXACTLY args.steps timed steps after the warm-up
+    for i in range(warm):
         do_step(dev_lr[i % n_host], dev_hr[i % n_host])
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    L.launch_count(reset=True)
     ms_total = timed(lambda i: do_step(dev_lr[i % n_host], dev_hr[i % n_host]), args.steps)
-    launches = L.launch_count()
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     # CPU time to ENQUEUE one step into an empty stream (no launch-queue back-pressure): GPU-bound if < ms_per_step
+    host_enqueue_ms = None
     for i in range(3):
         barrier()
         h0 = time.perf_counter()
         do_step(dev_lr[i % n_host], dev_hr[i % n_host])
-        host_ms[0] = (time.perf_counter() - h0) * 1e3 if i == 0 else min(host_ms[0], (time.perf_counter() - h0) * 1e3)
+        dt = (time.perf_counter() - h0) * 1e3
+        host_enqueue_ms = dt if host_enqueue_ms is None else min(host_enqueue_ms, dt)
     barrier()
-    host_enqueue_ms = host_ms[0]
+
+    # ---- sustained arm: the same step for >= sustain_seconds, so that a comparison with the SUSTAINED cuBLAS rate
+    # (measured over 4 s at whatever clock the 1 kW cap allows) is like for like
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / ms_step) + 1)
+        s2 = ClockSampler(local)
+        if rank == 0:
+            s2.start()
+        ms_sus = timed(lambda i: do_step(dev_lr[i % n_host], dev_hr[i % n_host]), n_sus)
+        c2 = s2.stop() if rank == 0 else None
+        sustained = {"steps": n_sus, "seconds": ms_sus * 1e-3, "ms_per_step": ms_sus / n_sus,
+                     "value": BATCH * world / (ms_sus / n_sus * 1e-3), "clocks": c2}
 
     # ---- end-to-end arm: pinned host batch -> H2D -> step -> D2H loss, every step
     last = {}
@@ -279,11 +328,12 @@ def run_b200(args):
     h2d = host_lr[0].numel() * 4 + host_hr[0].numel() * 4
     d2h = int(last['loss'].numel()) * 4
 
-    # ---- roofline leg: same steps with per-launch CUDA events around the tensor-core kernels
+    # ---- roofline leg: eager steps with per-launch CUDA events around the tensor-core kernels
     L.profile_enable(True)
     L.profile_read(0), L.profile_read(1)
-    for i in range(args.steps):
-        do_step(dev_lr[i % n_host], dev_hr[i % n_host])
+    n_prof = min(args.steps, 10)
+    for i in range(n_prof):
+        eager_step(dev_lr[i % n_host], dev_hr[i % n_host])
     ig_ms, ig_n, ig_fl = L.profile_read(0)
     wg_ms, wg_n, wg_fl = L.profile_read(1)
     L.profile_enable(False)
@@ -298,89 +348,222 @@ def run_b200(args):
     achieved = ig_fl / (ig_ms * 1e-3) / 1e12 if ig_ms > 0 else 0.0
     wg_achieved = wg_fl / (wg_ms * 1e-3) / 1e12 if wg_ms > 0 else 0.0
     step_tflops = step_gflop(args.workload) / ms_step   # GFLOP / ms == TFLOP/s
+    sus_tflops = step_gflop(args.workload) / sustained["ms_per_step"] if sustained else None
     roofline = {
         "bound": "tensor", "kernel": "conv_igemm_kernel (fprop + dgrad of every conv)", "achieved": achieved,
-        "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+        "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "frac_of_burst": achieved / peaks["burst"],
+        "peak_burst": peaks["burst"],
         "traffic": NCU_TRUNK_CONV_DRAM_BYTES,
         "traffic_note": "dram__bytes_read+write of ONE trunk-conv launch (16x48x48, 256->256) from profiles/r01_ncu_conv_igemm.txt; "
                         "algorithmic bytes of that launch: 18.9 MB in + 1.2 MB weights + 18.9 MB out (the output stays in the 126 MB L2)",
-        "peak_source": peaks["source"], "launches_per_step": ig_n / args.steps,
-        "avg_launch_us": ig_ms * 1e3 / max(ig_n, 1), "share_of_step": ig_ms / args.steps / ms_step,
+        "peak_source": peaks["source"], "launches_per_step": ig_n / n_prof,
+        "avg_launch_us": ig_ms * 1e3 / max(ig_n, 1), "share_of_step": ig_ms / n_prof / ms_step,
         "wgrad": {"kernel": "conv_wgrad_kernel", "achieved": wg_achieved, "frac": wg_achieved / peaks["tflops"],
-                  "launches_per_step": wg_n / args.steps, "share_of_step": wg_ms / args.steps / ms_step},
-        "whole_step": {"achieved": step_tflops, "frac": step_tflops / peaks["tflops"],
+                  "frac_of_burst": wg_achieved / peaks["burst"], "launches_per_step": wg_n / n_prof,
+                  "share_of_step": wg_ms / n_prof / ms_step},
+        "whole_step": {"achieved": step_tflops, "frac": step_tflops / peaks["tflops"], "frac_of_burst": step_tflops / peaks["burst"],
+                       "sustained_run_achieved": sus_tflops,
+                       "sustained_run_frac": sus_tflops / peaks["tflops"] if sus_tflops else None,
+                       "sustained_run_frac_of_burst": sus_tflops / peaks["burst"] if sus_tflops else None,
                        "algorithmic_gflop_per_step": step_gflop(args.workload)},
-        "how": "algorithmic FLOPs (2*M*N*K, dense convention) of every launch / CUDA-event time of that launch, "
-               "summed over a repeat of the timed steps with per-launch events enabled",
+        "how": "algorithmic FLOPs (2*M*N*K, dense convention) of every launch / CUDA-event time of that launch, summed over "
+               f"{n_prof} EAGER steps with per-launch events enabled (the events serialise what programmatic dependent "
+               "launch overlaps, so the per-kernel rates are lower bounds); whole_step = algorithmic FLOPs of the step / "
+               "ms_per_step of the timed region (and of the >= 3 s sustained run)",
     }
+    if world == 1 and not args.no_extras:
+        try:
+            roofline["hbm"] = hbm_kernels(dev, peaks["hbm"])
+        except Exception as e:
+            roofline["hbm_error"] = f"{type(e).__name__}: {str(e)[:200]}"
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cb = 2
+        cb = 4
         t = cpu_step_time(args.workload, cb)
         cpu = {"value": cb / t, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"1 step of a {cb}-sample batch (of {BATCH}), fp32, torch CPU oracle, {t:.1f} s"}
     extras = {}
     if world == 1 and not args.no_extras:
         extras = side_measurements(args, dev, G, optim_G, dev_lr, dev_hr)
+    cfg_out = config_dict(args.workload, world)
+    cfg_out["launch"] = "cuda_graph" if graphed else "eager"
     line = {
         "metric": metric_name(args.workload), "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": config_dict(args.workload, world),
+        "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": cfg_out,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e},
-        "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms, "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+        "host_enqueue_ms_per_step": host_enqueue_ms, "sustained": sustained,
+        "roofline": roofline, "cpu_baseline": cpu,
+        "adam_table_builds": [o.table_builds for o in (optim_G, optim_D) if o is not None],
     }
+    if graph_note:
+        line["graph_note"] = graph_note
     line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def hbm_kernels(dev, peak_gbs):
+    """Achieved HBM GB/s of the memory-bound kernels of the step, each timed alone with CUDA events over rotating
+    buffers larger than the 126 MB L2 (Adam, BatchNorm + LeakyReLU, the loss reductions, FC1, the
+    x8 blend).  bytes = algorithmic bytes of ONE launch (read + written once)."""
+    import torch
+    from pesr_b200 import ops
+    from pesr_b200._lib import check, lib
+    f16, f32 = torch.float16, torch.float32
+    out = []
+
+    def run(name, nbytes, fn, rot, iters=12, note=None):
+        for i in range(3):
+            fn(i % rot)
+        ms = _event_timed(lambda i: fn(i % rot), iters) / iters
+        e = {"kernel": name, "bytes": int(nbytes), "us": ms * 1e3, "achieved": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s"}
+        e["frac"] = e["achieved"] / peak_gbs
+        if note:
+            e["note"] = note
+        out.append(e)
+    # multi-tensor Adam over the Generator's 43.09 M parameters: 28 B per parameter
+    n = 43_089_947
+    p, g, m, v = (torch.randn(n, device=dev) * 1e-2 for _ in range(4))
+    v.abs_()
+    rows = [(p.data_ptr() + 4 * o, g.data_ptr() + 4 * o, m.data_ptr() + 4 * o, v.data_ptr() + 4 * o, min(1 << 16, n - o))
+            for o in range(0, n, 1 << 16)]
+    table = torch.tensor(rows, dtype=torch.int64).to(dev)
+    run("adam_multi_kernel (G, 43.09 M params)", 28 * n, lambda i: ops.adam_multi(table, len(rows), 5e-5, 0.9, 0.999, 1e-8, 10), 1)
+    del p, g, m, v, table
+    # BatchNorm + LeakyReLU of the Discriminator's first block: 16 x 192 x 192 x 64 16-bit
+    npix, c = BATCH * 192 * 192, 64
+    ys = [torch.randn(npix, c, device=dev, dtype=f16) for _ in range(3)]
+    a = [torch.empty(npix, c, device=dev, dtype=f16) for _ in range(3)]
+    mean, rstd, gam, bet = (torch.zeros(c, device=dev), torch.ones(c, device=dev), torch.ones(c, device=dev), torch.zeros(c, device=dev))
+    ws = torch.zeros(1024, device=dev, dtype=torch.float64)
+    run("bn_reduce_vec_kernel (statistics), 37.7 M x fp16", 2 * npix * c, lambda i: ops.bn_reduce(ys[i], npix, c, ws), 3)
+    run("bn_lrelu_fwd_kernel (finalise + apply), 37.7 M x fp16", 4 * npix * c,
+        lambda i: ops.bn_lrelu_fwd(ys[i], npix, c, mean, rstd, gam, bet, a[i], sums_ws=ws), 3)
+    dgam, dbet = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+    run("bn_lrelu_bwd (reduce + apply), 37.7 M x fp16", (2 * 2 + 3) * npix * c,
+        lambda i: ops.bn_lrelu_bwd(a[i], ys[i], npix, c, mean, rstd, gam, ws, a[(i + 1) % 3], dgam, dbet), 3,
+        note="two passes: statistics read dz and y, apply reads dz and y and writes dy")
+    del ys, a
+    # loss reductions over sr / hr (16 x 3 x 192 x 192 fp32 = 7.1 MB per tensor: L2-resident, latency-bound)
+    e = BATCH * 3 * 192 * 192
+    xs = [torch.rand(BATCH, 3, 192, 192, device=dev) * 255 for _ in range(24)]
+    gr = torch.empty_like(xs[0])
+    loss = torch.empty((), device=dev)
+    small = "7.1 MB per tensor: at this size the kernel is launch / latency bound, not bandwidth bound"
+    run("diff_loss_kernel L1 (value + gradient)", 12 * e, lambda i: ops.loss_l1(xs[2 * i], xs[2 * i + 1], loss, gr), 12, note=small)
+    run("diff_loss_kernel MSE on VGG features 16x512x12x12", 12 * BATCH * 512 * 144,
+        lambda i: ops.loss_mse(xs[2 * i].view(-1)[:BATCH * 512 * 144], xs[2 * i + 1].view(-1)[:BATCH * 512 * 144], loss,
+                               gr.view(-1)[:BATCH * 512 * 144]), 12, note=small)
+    run("tv_loss_kernel (value + gradient)", 8 * e, lambda i: ops.loss_tv(xs[i], loss, gr), 24, note=small)
+    del xs, gr
+    # FC1 of the Discriminator (75.5 M weights, 16 rows): forward on the split-K igemm, weight gradient on CUDA cores
+    k, o = 73728, 1024
+    w16 = [torch.randn(o, k, device=dev, dtype=f16) * 1e-2 for _ in range(2)]
+    x16 = torch.randn(BATCH, k, device=dev, dtype=f16)
+    ks = 36
+    part = torch.empty(ks * BATCH * o, device=dev)
+    descs = [ops.make_conv_desc(dtype=0, nb=1, h=1, w=BATCH, cin=k, cout=o, block_n=256, taps=[(0, 0)],
+                                srcs=[ops.nhwc_src(x16, 1, 1, BATCH, k)], wpacked=w, out32=part, ld_out32=o, ksplit=ks,
+                                split_stride32=BATCH * o) for w in w16]
+    run("FC1 forward (conv_igemm split-K, 151 MB of fp16 weights)", 2 * k * o, lambda i: ops.conv_igemm(descs[i]), 2)
+    dy = torch.randn(BATCH, o, device=dev)
+    dws = [torch.empty(o, k, device=dev) for _ in range(2)]
+    run("linear_wgrad_kernel FC1 (302 MB fp32 gradient written)", 4 * k * o, lambda i: ops.linear_wgrad(dy, x16, BATCH, k, o, dws[i]), 2)
+    del w16, dws, part
+    # x8 self-ensemble blend + uint8 store at 1356 x 2040 (E6): 9 fp32 reads + 1 byte written per element
+    H, W = 1356, 2040
+    perc = torch.rand(3, H, W, device=dev) * 255
+    ens = torch.rand(8, 3, H * W, device=dev) * 255
+    o8 = torch.empty(H, W, 3, device=dev, dtype=torch.uint8)
+    s = torch.cuda.current_stream().cuda_stream
+    run("blend_x8_to_u8_kernel 1356x2040 (alpha = 0.5)", (9 * 4 + 1) * 3 * H * W,
+        lambda i: check(lib.pesr_blend_x8_to_u8(perc.data_ptr(), ens.data_ptr(), H, W, 0.5, 8, 0, o8.data_ptr(), s)), 1,
+        note="299 MB working set > L2")
+    # 3-channel edges of the Generator at the training shape
+    lr = torch.rand(BATCH, 3, 192, 192, device=dev) * 255
+    cols = [torch.empty(BATCH * 192 * 192, 64, device=dev, dtype=f16) for _ in range(3)]
+    run("im2col3_kernel 16x3x192x192 -> [P][64] fp16", 12 * BATCH * 192 * 192 + 128 * BATCH * 192 * 192,
+        lambda i: ops.im2col3(lr, cols[i]), 3)
+    zs = [torch.randn(BATCH * 192 * 192, 32, device=dev) for _ in range(3)]
+    sr = torch.empty(BATCH, 3, 192, 192, device=dev)
+    run("col2im3_tiled_kernel [P][32] fp32 -> 16x3x192x192", (128 + 12) * BATCH * 192 * 192, lambda i: ops.col2im3(zs[i], 32, BATCH, 192, 192, sr), 3)
+    return out
+
+
 def side_measurements(args, dev, G, optim_G, dev_lr, dev_hr):
     """The other single-GPU configurations of BASELINE.json, measured the same way (CUDA events, warm-up) and
-    reported beside the headline: config 2 (L1 pretrain step) and configs 1 / 5 (x4 inference, alpha = 1)."""
+    reported beside the headline: config 2 (L1 pretrain step), config 1 (128x128 inference) and config 5 (339x510
+    inference: batch sweep 1-32 at alpha = 1, alpha = 0.5 with the x8 self-ensemble, uint8 host image -> uint8 host image)."""
     import torch
     from pesr_b200 import infer, steps
+    from pesr_b200.model import Generator
     out = {}
+    k = min(args.steps, 20)
 
-    def timed(fn, k, warm=3):
+    def timed(fn, n, warm=2):
         for i in range(warm):
             fn(i)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(k):
-            fn(i)
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / k
+        return _event_timed(fn, n) / n
     if args.workload != "pretrain":
-        ms = timed(lambda i: steps.pretrain_step(G, optim_G, dev_lr[i % len(dev_lr)], dev_hr[i % len(dev_hr)]), args.steps)
+        ms = timed(lambda i: steps.pretrain_step(G, optim_G, dev_lr[i % len(dev_lr)], dev_hr[i % len(dev_hr)]), k, warm=3)
         out["pretrain_step"] = {"metric": "L1 pretrain samples/s", "value": BATCH / (ms * 1e-3), "ms_per_step": ms,
-                                "tflops": step_gflop("pretrain") / ms, "config": "BASELINE.json configs[1]"}
+                                "tflops": step_gflop("pretrain") / ms, "launch": "eager", "config": "BASELINE.json configs[1]"}
     G.eval()
+    flop_px = 100505088
     inf = {}
-    for name, (h, w) in (("128x128", (128, 128)), ("339x510", (339, 510))):
-        x = torch.rand(1, 3, h, w, device=dev) * 255
-        ms = timed(lambda i: infer.super_resolve(G, x), 5, warm=2)
-        inf[name] = {"ms_per_image": ms, "hr_mpix_per_s": 16 * h * w / (ms * 1e-3) / 1e6,
-                     "tflops": h * w * 100505088 / (ms * 1e-3) / 1e12}
+    x = torch.rand(1, 3, 128, 128, device=dev) * 255
+    ms = timed(lambda i: infer.super_resolve(G, x), 5)
+    inf["128x128"] = {"ms_per_image": ms, "hr_mpix_per_s": 16 * 128 * 128 / (ms * 1e-3) / 1e6, "tflops": 128 * 128 * flop_px / (ms * 1e-3) / 1e12}
+    h, w = 339, 510
+    sweep = {}
+    for b in (1, 2, 4, 8, 16, 32):
+        xb = torch.rand(b, 3, h, w, device=dev) * 255
+        ms = timed(lambda i: infer.super_resolve(G, xb), 3, warm=1)
+        sweep[str(b)] = {"ms_per_batch": ms, "hr_mpix_per_s": b * 16 * h * w / (ms * 1e-3) / 1e6,
+                         "tflops": b * h * w * flop_px / (ms * 1e-3) / 1e12}
+        del xb
+    inf["339x510_batch_sweep_alpha1"] = sweep
+    # uint8 HWC host image -> uint8 HWC host image (the whole of test.py:103-114 minus PNG decode / encode)
+    host_in = (torch.rand(h, w, 3) * 255).to(torch.uint8).pin_memory()
+    host_out = torch.empty(4 * h, 4 * w, 3, dtype=torch.uint8).pin_memory()
+
+    def e2e(i):
+        o8 = infer.super_resolve_u8(G, host_in.to(dev, non_blocking=True))
+        host_out.copy_(o8, non_blocking=True)
+    ms = timed(e2e, 5)
+    inf["339x510_u8_host_to_host"] = {"ms_per_image": ms, "hr_mpix_per_s": 16 * h * w / (ms * 1e-3) / 1e6,
+                                      "h2d_bytes": host_in.numel(), "d2h_bytes": host_out.numel()}
+    # alpha = 0.5: perceptual model + x8 self-ensemble of the PSNR model (9 forwards) + fused blend
+    torch.manual_seed(1)
+    Gp = Generator(OPT).to(dev).eval()
+    x1 = torch.rand(1, 3, h, w, device=dev) * 255
+    ms = timed(lambda i: infer.super_resolve(G, x1, alpha=0.5, model_psnr=Gp), 3, warm=1)
+    inf["339x510_alpha0.5"] = {"ms_per_image": ms, "hr_mpix_per_s": 16 * h * w / (ms * 1e-3) / 1e6,
+                               "tflops": 9 * h * w * flop_px / (ms * 1e-3) / 1e12, "forwards": 9}
+    del Gp
     G.train()
-    out["inference_alpha1"] = {"metric": "x4 SR inference HR Mpix/s (fp32 image in, uint8 image out, batch 1)", **inf,
-                               "config": "BASELINE.json configs[0] and configs[4] image sizes"}
+    out["inference"] = {"metric": "x4 SR inference HR Mpix/s (fp32 image in, fp32 + uint8 image out unless noted)", **inf,
+                        "config": "BASELINE.json configs[0] and configs[4]"}
     return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("PESR_BENCH_WORKLOAD", "gan"), choices=["pretrain", "gan"])
     ap.add_argument("--no-extras", action="store_true", help="skip the pretrain-step and inference side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
+    ap.add_argument("--graph-multi", action="store_true", help="also capture the step (incl. the NCCL all-reduce) at N > 1")
+    ap.add_argument("--sustain-seconds", type=float, default=3.0, help="length of the extra sustained run (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

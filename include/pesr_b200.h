@@ -116,7 +116,13 @@ typedef struct pesr_conv_desc {
   double* bn_sums;          /* optional, light epilogue only (16-bit NHWC output, no residual / mask): 2*cout doubles that
                                receive += sum and += sum of squares of the ROUNDED 16-bit outputs per channel - the
                                train-mode BatchNorm statistics of model/basic.py:29 without a second pass over y
-                               (close with pesr_bn_stats(y16 = NULL, ...)) */
+                               (consumed by pesr_bn_lrelu_fwd(sums_ws = bn_sums, ...)) */
+  int32_t ncls;             /* > 1: the launch covers ncls sub-problems ("classes") of the same h x w pixel grid and the
+                               same weights / sources / epilogue tensors: class c owns the next cls_ntaps[c] entries of the
+                               tap arrays and writes to output-grid offset (cls_oy[c], cls_ox[c]) instead of (out_oy, out_ox).
+                               The four parity classes of a stride-2 backward-data (1 + 2 + 2 + 4 taps) run as one launch
+                               this way.  Needs ksplit <= 1, K-major weights, NORMAL output addressing. */
+  int8_t cls_ntaps[4], cls_oy[4], cls_ox[4];
 } pesr_conv_desc;
 
 int pesr_conv_igemm(const pesr_conv_desc* d, void* stream);
@@ -315,25 +321,35 @@ int pesr_adam_multi_dev(const int64_t* table_dev, int32_t nchunks, const float* 
 /* ------------------------------------------------------------------------------------------------
  * Discriminator / VGG layer kernels (HBM-bound).
  * ------------------------------------------------------------------------------------------------ */
-/* Train-mode BatchNorm2d statistics (model/basic.py:29): per-channel mean and 1/sqrt(biased var + eps) of the
- * 16-bit NHWC tensor y[npix][c]; updates running_mean / running_var (unbiased) with `momentum` and increments
- * num_batches_tracked when given.  running_mean_shift (optional, per channel) is added to the batch mean in the
- * running_mean update only (y was produced from a constant-shifted input).  sums_ws: 2*c doubles, zero on entry,
- * zero again on exit.  y16 == NULL: the sums were already accumulated by the producing convolution
- * (pesr_conv_desc.bn_sums); only the finalisation runs. */
-int pesr_bn_stats(const void* y16, int64_t npix, int32_t c, float eps, float momentum, double* sums_ws, float* mean,
-                  float* rstd, float* running_mean, float* running_var, int64_t* num_batches_tracked,
-                  const float* running_mean_shift, int32_t dtype, void* stream);
-/* a = LeakyReLU_slope(gamma * (y - mean) * rstd + beta)   (model/basic.py:29-30, model/pesr.py:47) */
-int pesr_bn_lrelu_fwd(const void* y16, int64_t npix, int32_t c, const float* mean, const float* rstd,
-                      const float* gamma, const float* beta, float slope, int32_t dtype, void* a16, void* stream);
-/* BatchNorm backward given dz = dL/d(bn output) (LeakyReLU' already applied by the producer):
- *   dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)), dgamma = sum(dz*xhat), dbeta = sum(dz),
- * the parameter gradients multiplied by grad_mul / (*grad_div_dev); accumulate != 0 adds them to dgamma / dbeta
- * (second backward pass of one optimiser step, train.py:213-216). */
-int pesr_bn_lrelu_bwd(const void* dz16, const void* y16, int64_t npix, int32_t c, const float* mean, const float* rstd,
-                      const float* gamma, double* sums_ws, float grad_mul, const float* grad_div_dev, int32_t dtype,
-                      void* dy16, float* dgamma, float* dbeta, int32_t accumulate, void* stream);
+/* Train-mode BatchNorm2d + LeakyReLU (model/basic.py:29-30, model/pesr.py:47) on 16-bit NHWC tensors.
+ * GROUPS: a tensor may hold `groups` independent batches back to back ([groups][npix][c]); each group is normalised
+ * with its own batch statistics, exactly as `groups` separate module calls would (the Discriminator is called twice
+ * per phase, on hr and on sr: train.py:205-208, 237-238 -- both calls run as one launch per layer).  Per-group
+ * quantities are laid out [groups][...]: sums_ws [groups][2][c] doubles, mean / rstd [groups][c] floats.
+ *
+ * pesr_bn_reduce: sums_ws[g][0][ch] += sum y, sums_ws[g][1][ch] += sum y^2 (fp64 accumulation).  zero_first != 0 clears
+ *   sums_ws first; otherwise the caller provides zeroed sums (one memset for all layers of a pass), or sums already
+ *   accumulated by the producing convolution (pesr_conv_desc.bn_sums, groups == 1).
+ * pesr_bn_lrelu_fwd: a = LeakyReLU_slope(gamma * (y - mean_g) * rstd_g + beta).  sums_ws != NULL (train mode): mean_g and
+ *   rstd_g = 1/sqrt(biased var + eps) are derived from the sums inside the kernel and stored to mean / rstd for backward;
+ *   running_mean / running_var (optional) are updated with `momentum` (unbiased variance) once per group, in group
+ *   order, and num_batches_tracked += groups.  running_mean_shift (optional, per channel) is added to the batch mean in
+ *   the running_mean update only (y was produced from a constant-shifted input).  sums_ws == NULL (eval mode): mean and
+ *   rstd are inputs.
+ * pesr_bn_lrelu_bwd: given dz = dL/d(bn output) (LeakyReLU' already applied by the producer):
+ *   dy = gamma*rstd_g*(dz - mean(dz) - xhat*mean(dz*xhat)) per group; dgamma = sum_groups sum(dz*xhat), dbeta = sum_groups
+ *   sum(dz), multiplied by grad_mul / (*grad_div_dev); accumulate != 0 adds them to dgamma / dbeta (a further backward
+ *   pass of the same optimiser step).  sums_ws as in pesr_bn_reduce (zero_first). */
+int pesr_bn_reduce(const void* y16, int64_t npix_per_group, int32_t c, int32_t groups, double* sums_ws, int32_t zero_first,
+                   int32_t dtype, void* stream);
+int pesr_bn_lrelu_fwd(const void* y16, int64_t npix_per_group, int32_t c, int32_t groups, const double* sums_ws, float eps,
+                      float momentum, float* mean, float* rstd, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                      const float* running_mean_shift, float slope, int32_t dtype, void* a16, void* stream);
+int pesr_bn_lrelu_bwd(const void* dz16, const void* y16, int64_t npix_per_group, int32_t c, int32_t groups,
+                      const float* mean, const float* rstd, const float* gamma, double* sums_ws, int32_t zero_first,
+                      float grad_mul, const float* grad_div_dev, int32_t dtype, void* dy16, float* dgamma, float* dbeta,
+                      int32_t accumulate, void* stream);
 /* 2x2/2 max-pool (vgg19.features) on NHWC 16-bit; backward routes to the first maximum in scan order (PyTorch's
  * tie rule) and, with relu_mask, multiplies by relu'(x). */
 int pesr_maxpool2_fwd(const void* x16, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t dtype, void* y16, void* stream);

@@ -50,6 +50,7 @@ class ConvDesc(C.Structure):
         ("ksplit", C.c_int32), ("b_mn_major", C.c_int32), ("split_stride32", C.c_int64),
         ("tile_n", C.c_int32), ("reserved0", C.c_int32),
         ("bn_sums", C.c_void_p),
+        ("ncls", C.c_int32), ("cls_ntaps", C.c_int8 * 4), ("cls_oy", C.c_int8 * 4), ("cls_ox", C.c_int8 * 4),
     ]
 
 
@@ -115,9 +116,11 @@ SIGNATURES = {
     "pesr_loss_mse": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "pesr_loss_tv": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "pesr_loss_gan": (C.c_int, [_vp, _vp, _i32, _f32, _f32, _f32, _i32, _f32, _vp, _vp, _vp, _vp]),
-    "pesr_bn_stats": (C.c_int, [_vp, _i64, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
-    "pesr_bn_lrelu_fwd": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _i32, _vp, _vp]),
-    "pesr_bn_lrelu_bwd": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _i32, _vp]),
+    "pesr_bn_reduce": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _i32, _vp]),
+    "pesr_bn_lrelu_fwd": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32,
+                                    _i32, _vp, _vp]),
+    "pesr_bn_lrelu_bwd": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _i32, _vp, _vp, _vp,
+                                    _i32, _vp]),
     "pesr_maxpool2_fwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "pesr_maxpool2_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "pesr_linear_workspace_floats": (C.c_int64, [_i32, _i32, _i32]),

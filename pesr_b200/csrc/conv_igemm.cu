@@ -71,6 +71,12 @@ struct ConvK {
   int sub_mode, nsub, a_sub_off, b_sub_off, a_bytes, steps_per_tile;
   unsigned long long* dbg;   // optional timeline of block 0 (bring-up): [64] clock64 stamps + [63] = globaltimer ns
   long long split_stride32;
+  // several sub-problems ("classes") of one pixel grid in ONE launch: class c owns taps [cls_tap0[c], cls_tap0[c+1]) and
+  // the output-grid offset (cls_oy[c], cls_ox[c]); tile index = class * tiles_per_cls + tile-within-class.  The four
+  // parity classes of a stride-2 backward-data run this way (each alone fills half the machine or less).
+  int ncls, tiles_per_cls;
+  int cls_tap0[5];
+  int cls_oy[4], cls_ox[4];
 };
 
 // kPair = false: one CTA per tile (cta_group::1).
@@ -142,7 +148,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int total_kb = p.ntaps * p.kblocks_per_tap;
+  // k-blocks of one tile of class c (ncls == 1: the whole tap list)
+  auto class_kb = [&](int cls) { return (p.cls_tap0[cls + 1] - p.cls_tap0[cls]) * p.kblocks_per_tap; };
   unsigned long long* dbg = (kDebugHooks && p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
   unsigned long long t_begin = 0, g_begin = 0;
   if (dbg && threadIdx.x == 0) {
@@ -157,8 +164,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     p.dbg[64 + 2 * blockIdx.x] = g;
   }
 
-  // tile -> (split, m_tile of THIS CTA, n_tile)
-  auto decode = [&](int tile, int& split, int& m_tile, int& n_tile) {
+  // tile -> (class, split, m_tile of THIS CTA, n_tile)
+  auto decode = [&](int tile, int& split, int& m_tile, int& n_tile, int& cls) {
+    cls = 0;
+    if (p.ncls > 1) { cls = tile / p.tiles_per_cls; tile -= cls * p.tiles_per_cls; }
     split = tile / p.mn_tiles;
     const int mn = tile - split * p.mn_tiles;
     n_tile = mn % p.n_tiles;
@@ -177,9 +186,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       uint32_t phase = 0;
       const int kpt = p.kblocks_per_tap;
       // position inside the K loop: MODE 0/1/3: (t, cb); MODE 2: (cb, dx) with t := dx
-      auto seek = [&](int s, int& t, int& cb) {
+      // t is an index into the tap arrays (absolute: the class's first tap is added)
+      auto seek = [&](int s, int cls, int& t, int& cb) {
         if (MODE == 2) { cb = s / 3; t = s - cb * 3; }
-        else { const int kb = MODE == 1 ? s * p.nsub : s; t = kb / kpt; cb = kb - t * kpt; }
+        else { const int kb = MODE == 1 ? s * p.nsub : s; t = kb / kpt; cb = kb - t * kpt; t += p.cls_tap0[cls]; }
       };
       auto advance = [&](int& t, int& cb) {
         if (MODE == 2) { if (++t == 3) { t = 0; cb++; } }
@@ -203,8 +213,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
           tma_load_2d_w(sa + kABytes, &maps.b, fb, cb * kKBlock, p.tap_widx[t] * p.cout + n0);
         }
       };
-      auto step_range = [&](int split, int& s0, int& s1) {
-        if (MODE == 1 || MODE == 2) { s0 = 0; s1 = p.steps_per_tile; return; }
+      auto step_range = [&](int split, int cls, int& s0, int& s1) {
+        if (MODE == 2) { s0 = 0; s1 = p.steps_per_tile; return; }
+        const int total_kb = class_kb(cls);
+        if (MODE == 1) { s0 = 0; s1 = total_kb / p.nsub; return; }
         s0 = (int)(((long long)split * total_kb) / p.ksplit);
         s1 = (int)(((long long)(split + 1) * total_kb) / p.ksplit);
       };
@@ -212,10 +224,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       // flight while that kernel drains
       int npre = 0;
       if (p.pdl_early_b) {
-        int split, m_tile, n_tile, s0, s1, t, cb;
-        decode(worker, split, m_tile, n_tile);
-        step_range(split, s0, s1);
-        seek(s0, t, cb);
+        int split, m_tile, n_tile, cls, s0, s1, t, cb;
+        decode(worker, split, m_tile, n_tile, cls);
+        step_range(split, cls, s0, s1);
+        seek(s0, cls, t, cb);
         npre = s1 - s0 < p.stages ? s1 - s0 : p.stages;
         const int n0 = n_tile * p.block_n + rank * b_rows;
         for (int i = 0; i < npre; i++) {
@@ -227,10 +239,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       griddep_wait();
       griddep_launch();
       for (int tile = worker; tile < p.num_tiles; tile += nworkers) {
-        int split, m_tile, n_tile, s0, s1, t, cb;
-        decode(tile, split, m_tile, n_tile);
-        step_range(split, s0, s1);
-        seek(s0, t, cb);
+        int split, m_tile, n_tile, cls, s0, s1, t, cb;
+        decode(tile, split, m_tile, n_tile, cls);
+        step_range(split, cls, s0, s1);
+        seek(s0, cls, t, cb);
         const int tw = m_tile % p.tiles_w;
         const int th = (m_tile / p.tiles_w) % p.tiles_h;
         // first image of the tile; >= nb for the padding tile of an odd pair: all OOB -> zeros
@@ -290,15 +302,19 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = worker; tile < p.num_tiles; tile += nworkers) {
-        const int split = tile / p.mn_tiles;
+        int cls = 0, tloc = tile;
+        if (p.ncls > 1) { cls = tile / p.tiles_per_cls; tloc = tile - cls * p.tiles_per_cls; }
+        const int split = tloc / p.mn_tiles;
+        const int total_kb = class_kb(cls);
         const int kb0 = (int)(((long long)split * total_kb) / p.ksplit);
         const int kb1 = (int)(((long long)(split + 1) * total_kb) / p.ksplit);
+        const int steps_per_tile = p.sub_mode == 2 ? p.steps_per_tile : total_kb / p.nsub;
         if (kPair) mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1); else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
         if (dbg && lane == 0) dbg[8 + (tile == worker ? 0 : 4)] = clock64();    // MMA warp: accumulator free
         if (!kPair && p.sub_mode) {
-          for (int st = 0; st < p.steps_per_tile; st++) {
+          for (int st = 0; st < steps_per_tile; st++) {
             mbar_wait_w(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
@@ -312,7 +328,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
               }
             }
             umma_commit_w(&empty_bar[stage]);
-            if (st == p.steps_per_tile - 1) umma_commit_w(&tmem_full[acc]);
+            if (st == steps_per_tile - 1) umma_commit_w(&tmem_full[acc]);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
           acc ^= 1;
@@ -375,8 +391,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       uint32_t acc_phase = 0;
       uint32_t slot = 0;                            // ring slot of the chunk being processed
       for (int tile = worker; tile < p.num_tiles; tile += nworkers) {
-        int split, m_tile, n_tile;
-        decode(tile, split, m_tile, n_tile);
+        int split, m_tile, n_tile, cls;
+        decode(tile, split, m_tile, n_tile, cls);
         const int tw = m_tile % p.tiles_w;
         const int th = (m_tile / p.tiles_w) % p.tiles_h;
         const int img = m_tile / (p.tiles_w * p.tiles_h);
@@ -528,8 +544,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = worker; tile < p.num_tiles; tile += nworkers) {
-      int split, m_tile, n_tile;
-      decode(tile, split, m_tile, n_tile);
+      int split, m_tile, n_tile, cls;
+      decode(tile, split, m_tile, n_tile, cls);
+      const int out_oy = p.cls_oy[cls], out_ox = p.cls_ox[cls];      // output-grid offset of this tile's class
       const int tw = m_tile % p.tiles_w;
       const int th = (m_tile / p.tiles_w) % p.tiles_h;
       const int img = (m_tile / (p.tiles_w * p.tiles_h)) * p.tile_n + tn_l;
@@ -537,7 +554,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       const bool valid = (h < p.h) && (w < p.w) && (img < p.nb);
       // pixel index used by res32 / res16 / mask16 / out32: the GEMM grid, or (aux_mode 1) the strided output grid
       const long long pix = e_aux
-          ? ((long long)img * p.out_h + (h * p.out_sy + p.out_oy)) * p.out_w + (w * p.out_sx + p.out_ox)
+          ? ((long long)img * p.out_h + (h * p.out_sy + out_oy)) * p.out_w + (w * p.out_sx + out_ox)
           : ((long long)img * p.h + h) * p.w + w;
 
       float* bs = bias_s + acc * 256;
@@ -667,7 +684,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
               off = op * p.ld_out16 + p.out_coff + ((h & 1) * 2 + (w & 1)) * p.cout + q0;
             } else {
               const long long op =
-                  ((long long)img * p.out_h + (h * p.out_sy + p.out_oy)) * p.out_w + (w * p.out_sx + p.out_ox);
+                  ((long long)img * p.out_h + (h * p.out_sy + out_oy)) * p.out_w + (w * p.out_sx + out_ox);
               off = op * p.ld_out16 + p.out_coff + q0;
             }
             uint32_t pk[16];
@@ -800,7 +817,7 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
   if (dd.block_n == 256 && dd.tile_h > 0 && dd.tile_w > 0 && g_sub_mode_enabled && dd.ksplit <= 1 && !dd.b_mn_major) {
     const int tn0 = dd.tile_n > 0 ? dd.tile_n : 1;
     const int mt = ((dd.nb + tn0 - 1) / tn0) * ((dd.h + dd.tile_h - 1) / dd.tile_h) * ((dd.w + dd.tile_w - 1) / dd.tile_w);
-    const bool will_pair = g_pair_mode == 2 || (g_pair_mode == 1 && mt >= 256);
+    const bool will_pair = dd.ncls <= 1 && (g_pair_mode == 2 || (g_pair_mode == 1 && mt >= 256));
     if (!will_pair && (dd.ntaps == 9 || (dd.cin / kKBlock) % 2 == 0)) dd.block_n = 128;
   }
   PESR_CHECK_ARG(d->dtype == PESR_DT_F16 || d->dtype == PESR_DT_BF16, "conv_igemm: bad dtype %d", d->dtype);
@@ -831,6 +848,15 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
     PESR_CHECK_ARG(d->b_mn_major || (d->tap_widx[t] + 1) * d->cout <= d->w_rows,
                    "conv_igemm: tap %d weight rows out of range", t);
   }
+  const int ncls = d->ncls > 1 ? d->ncls : 1;
+  if (ncls > 1) {
+    int tsum = 0;
+    for (int c = 0; c < ncls; c++) tsum += d->cls_ntaps[c];
+    PESR_CHECK_ARG(ncls <= 4 && tsum == d->ntaps && d->ksplit <= 1 && !d->b_mn_major && d->out_mode == PESR_OUT_NORMAL &&
+                       !d->bn_sums, "conv_igemm: a multi-class launch needs <= 4 classes whose tap counts sum to ntaps, "
+                                    "whole-K tiles, K-major weights and NORMAL output addressing");
+    for (int c = 0; c < ncls; c++) PESR_CHECK_ARG(d->cls_ntaps[c] >= 1, "conv_igemm: class %d has no taps", c);
+  }
   if (d->out_mode == PESR_OUT_SHUFFLE2)
     PESR_CHECK_ARG(d->ps_c > 0 && d->ps_c % 32 == 0 && d->cout == 4 * d->ps_c, "conv_igemm: bad ps_c %d", d->ps_c);
   if (d->out_mode == PESR_OUT_UNSHUFFLE2)
@@ -845,7 +871,7 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
   const int m_tiles_host = img_groups * ((d->h + d->tile_h - 1) / d->tile_h) * ((d->w + d->tile_w - 1) / d->tile_w);
   // measured on B200 (tools/perf_conv.py pair): the pair kernel wins 4-6% on the 256-wide, many-tile layers (G trunk and
   // upsampler) and loses 8-16% on the small D / VGG layers, so it is used where it wins (mode 2 forces it for tests).
-  const bool pair_legal = d->ksplit <= 1 && !d->b_mn_major && d->block_n >= 64 && m_tiles_host >= 2;
+  const bool pair_legal = d->ksplit <= 1 && !d->b_mn_major && d->block_n >= 64 && m_tiles_host >= 2 && ncls == 1;
   const bool pair = pair_legal && (g_pair_mode == 2 || (g_pair_mode == 1 && d->block_n == 256 && m_tiles_host >= 256));
 
   // staged epilogue (pair kernel): plain NHWC outputs on the GEMM's own pixel grid
@@ -950,9 +976,17 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
   const int m_tiles = img_groups * k.tiles_h * k.tiles_w;
   k.mn_tiles = (pair ? (m_tiles + 1) / 2 : m_tiles) * k.n_tiles;   // pair mode counts tiles of 2 x 128 pixels
   k.ksplit = ksplit;
-  k.num_tiles = k.mn_tiles * ksplit;
+  k.num_tiles = k.mn_tiles * ksplit * ncls;
+  k.ncls = ncls;
+  k.tiles_per_cls = k.mn_tiles * ksplit;
+  k.cls_tap0[0] = 0;
+  for (int c = 0; c < 4; c++) {
+    k.cls_tap0[c + 1] = ncls > 1 ? k.cls_tap0[c] + (c < ncls ? d->cls_ntaps[c] : 0) : d->ntaps;
+    k.cls_oy[c] = ncls > 1 ? d->cls_oy[c] : d->out_oy;
+    k.cls_ox[c] = ncls > 1 ? d->cls_ox[c] : d->out_ox;
+  }
   k.b_mn_major = d->b_mn_major ? 1 : 0;
-  k.pdl_early_b = (pdl_enabled() && weights_settled()) ? 1 : 0;
+  k.pdl_early_b = (weights_settled(stream) && pdl_enabled()) ? 1 : 0;
   k.dbg = g_dbg_buf;
   k.split_stride32 = d->split_stride32;
   k.kblocks_per_tap = d->cin / kKBlock;
@@ -969,7 +1003,7 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
   }
   k.bn_sums = d->bn_sums;
   const int epi_smem = staged ? kEpiBytes : epi == 7 ? kBnEpiBytes : 0;
-  const int smem_budget = 227 * 1024 - 4096 - epi_smem;
+  const int smem_budget = conv_smem_budget() - 4096 - epi_smem;
   k.stages = smem_budget / k.stage_bytes;
   if (k.stages > kMaxStages) k.stages = kMaxStages;
   for (int t = 0; t < PESR_MAX_TAPS; t++) {

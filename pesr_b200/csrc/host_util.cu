@@ -21,16 +21,33 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static int g_since_weight_write = 1 << 20;
 static int g_pdl = -1;
-void count_launch(int n) {
-  g_launches.fetch_add(n, std::memory_order_relaxed);
-  if (g_since_weight_write < (1 << 20)) g_since_weight_write += n;
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+// Packed weights are written by pack_weights / cast16 launches.  A PDL consumer may fetch weights BEFORE its dependency
+// wait only if a kernel that itself waited for the writer lies between them IN THE SAME STREAM (see conv_igemm.cu: the
+// conv kernels trigger their dependents only after their own wait).  Tracked per stream (the training step runs the
+// VGG branch and the Discriminator on two streams): a stream is "dirty" from a weight write on it until the next
+// tensor-core launch on it.
+static cudaStream_t g_dirty_streams[8];
+static int g_ndirty = 0;
+static std::mutex g_dirty_mu;
+void note_weight_write(cudaStream_t stream) {
+  std::lock_guard<std::mutex> g(g_dirty_mu);
+  for (int i = 0; i < g_ndirty; i++)
+    if (g_dirty_streams[i] == stream) return;
+  if (g_ndirty < 8) g_dirty_streams[g_ndirty++] = stream;
+  else g_dirty_streams[7] = stream;      // more than 8 dirty streams: never happens; stays conservative for this one
 }
-// Packed weights are written by pack_weights / cast16 launches.  A PDL consumer may prefetch weights before its
-// dependency wait only if the writer is not its immediate predecessor in the stream (see conv_igemm.cu).
-void note_weight_write() { g_since_weight_write = 0; }
-bool weights_settled() { return g_since_weight_write >= 1; }
+// Called by the tensor-core launchers: true = weights may be prefetched early by THIS launch; marks the stream clean.
+bool weights_settled(cudaStream_t stream) {
+  std::lock_guard<std::mutex> g(g_dirty_mu);
+  for (int i = 0; i < g_ndirty; i++)
+    if (g_dirty_streams[i] == stream) {
+      g_dirty_streams[i] = g_dirty_streams[--g_ndirty];
+      return false;
+    }
+  return true;
+}
 bool pdl_enabled() {
   if (g_pdl < 0) {
     const char* e = getenv("PESR_NO_PDL");
@@ -39,6 +56,21 @@ bool pdl_enabled() {
   return g_pdl != 0;
 }
 void set_pdl(int on) { g_pdl = on; }
+
+// Shared memory (bytes) the tensor-core kernels may claim per CTA.  The full 227 KB maximises pipeline depth; a smaller
+// budget leaves room for the blocks of a concurrently running memory-bound kernel of another stream on the same SM
+// (the training step runs the VGG branch beside the Discriminator).  PESR_CONV_SMEM_KB overrides (120..227).
+int conv_smem_budget() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("PESR_CONV_SMEM_KB");
+    int kb = e ? atoi(e) : 227;
+    if (kb < 120) kb = 120;
+    if (kb > 227) kb = 227;
+    v = kb * 1024;
+  }
+  return v;
+}
 
 int num_sms() {
   static int cached[64] = {0};

@@ -12,11 +12,12 @@ namespace pesr {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
-void note_weight_write();
-bool weights_settled();
+void note_weight_write(cudaStream_t stream);
+bool weights_settled(cudaStream_t stream);
 bool pdl_enabled();
 void set_pdl(int on);
 int num_sms();
+int conv_smem_budget();
 
 // Optional per-launch profiling of the tensor-core kernels (bench.py's roofline leg): when enabled, the
 // launchers bracket each launch with CUDA events on the launch stream and record its algorithmic FLOPs.

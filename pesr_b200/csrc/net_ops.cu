@@ -13,7 +13,10 @@ namespace pesr {
 // ------------------------------------------------------------------------------------------
 // BatchNorm statistics: per-channel sum and sum of squares of x[npix][c] (16-bit), accumulated in
 // double (the pre-BN conv outputs have |mean| >> std on 0..255 images, so E[x^2]-E[x]^2 needs it).
-// block = 256 threads = 32 channel-pairs x 8 pixel rows; grid.y tiles channels by 64.
+// GROUPS: the tensor holds `groups` independent batches back to back ([groups][npix][c]), each normalised with its own
+// statistics -- the Discriminator's two calls of one training phase (D(hr), D(sr): train.py:205-208, 237-238) run as
+// one launch per layer this way.  Group g uses sums + g*2*c and mean / rstd + g*c.
+// block = 256 threads = 32 channel-pairs x 8 pixel rows; grid = (pixel blocks, channel tiles of 64, groups).
 // mode 0: sums[0..c) += sum x,           sums[c..2c) += sum x^2
 // mode 1: sums[0..c) += sum dz,          sums[c..2c) += sum dz * xhat   (xhat = (y - mean) * rstd)
 // ------------------------------------------------------------------------------------------
@@ -22,13 +25,17 @@ __global__ void bn_reduce_kernel(const uint16_t* __restrict__ x, const uint16_t*
                                  double* __restrict__ sums) {
   griddep_wait();   // PDL: see launch_pdl
   __shared__ double red[2][8][64];
+  const int grp = blockIdx.z;
+  x += (long long)grp * npix * c;
+  if (y) y += (long long)grp * npix * c;
+  sums += (long long)grp * 2 * c;
   const int lane = threadIdx.x & 31;
   const int rowi = threadIdx.x >> 5;
   const int c0 = blockIdx.y * 64 + lane * 2;
   double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
   if (c0 < c) {
     float m0 = 0, m1 = 0, r0 = 1, r1 = 1;
-    if (mode == 1) { m0 = mean[c0]; m1 = mean[c0 + 1]; r0 = rstd[c0]; r1 = rstd[c0 + 1]; }
+    if (mode == 1) { m0 = mean[grp * c + c0]; m1 = mean[grp * c + c0 + 1]; r0 = rstd[grp * c + c0]; r1 = rstd[grp * c + c0 + 1]; }
     float fa0 = 0, fa1 = 0, fb0 = 0, fb1 = 0;
     int cnt = 0;
     for (long long p = (long long)blockIdx.x * 8 + rowi; p < npix; p += (long long)gridDim.x * 8) {
@@ -59,22 +66,26 @@ __global__ void bn_reduce_kernel(const uint16_t* __restrict__ x, const uint16_t*
   }
 }
 
-// Vectorised variant for c in {64,128,256,512}: 16-byte loads, c/8 threads per pixel row.
+// Vectorised variant for c in {64,128,256,512}: 16-byte loads, c/8 threads per pixel row; grid = (pixel blocks, groups).
 __global__ void __launch_bounds__(256)
 bn_reduce_vec_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, long long npix, int c,
                      const float* __restrict__ mean, const float* __restrict__ rstd, int mode, int bf,
                      double* __restrict__ sums) {
   griddep_wait();   // PDL: see launch_pdl
   __shared__ double red[2][2048];   // [quantity][row-in-pass * c + channel], rows-per-pass * c == 2048
+  const int grp = blockIdx.y;
   const int tpr = c >> 3;           // threads per pixel row
   const int rpp = 256 / tpr;        // pixel rows per pass
+  x += (long long)grp * npix * tpr;
+  if (y) y += (long long)grp * npix * tpr;
+  sums += (long long)grp * 2 * c;
   const int v = threadIdx.x % tpr, r = threadIdx.x / tpr;
   float m[8], rs[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) { m[j] = 0.f; rs[j] = 1.f; }
   if (mode == 1) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) { m[j] = mean[v * 8 + j]; rs[j] = rstd[v * 8 + j]; }
+    for (int j = 0; j < 8; j++) { m[j] = mean[grp * c + v * 8 + j]; rs[j] = rstd[grp * c + v * 8 + j]; }
   }
   double da[8], db[8];
   float fa[8], fb[8];
@@ -122,40 +133,62 @@ bn_reduce_vec_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, l
   }
 }
 
-// mean / rstd from the sums (+ running statistics update: momentum, unbiased variance), then zero the sums.
-__global__ void bn_finalize_kernel(double* __restrict__ sums, int c, double n, float eps, float momentum,
-                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ run_mean,
-                                   float* __restrict__ run_var, long long* __restrict__ num_batches,
-                                   const float* __restrict__ run_shift) {
-  griddep_wait();   // PDL: see launch_pdl
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < c) {
-    const double m = sums[i] / n;
-    double var = sums[c + i] / n - m * m;
-    if (var < 0) var = 0;
-    mean[i] = (float)m;
-    rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
-    if (run_mean) {
-      run_mean[i] = (1.f - momentum) * run_mean[i] + momentum * ((float)m + (run_shift ? run_shift[i] : 0.f));
-      const double unb = n > 1 ? var * n / (n - 1) : var;
-      run_var[i] = (1.f - momentum) * run_var[i] + momentum * (float)unb;
-    }
-    sums[i] = 0;
-    sums[c + i] = 0;
-  }
-  if (i == 0 && num_batches) *num_batches += 1;
+// mean / rstd of one channel from its sums (the arithmetic every consumer of the sums repeats identically)
+__device__ __forceinline__ void bn_moments(const double* __restrict__ sums, int c, int i, double n, float eps, float& mean,
+                                           float& rstd, double& var_out) {
+  const double m = sums[i] / n;
+  double var = sums[c + i] / n - m * m;
+  if (var < 0) var = 0;
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(var + (double)eps));
+  var_out = var;
 }
 
-// a = lrelu(gamma * (y - mean) * rstd + beta) = lrelu(y * sc + sh), 8 channels (16 bytes) per thread
-__global__ void bn_lrelu_fwd_kernel(const uint4* __restrict__ y, long long nvec, int c, const float* __restrict__ mean,
-                                    const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, float slope, int bf, uint4* __restrict__ a) {
+// a = lrelu(gamma * (y - mean) * rstd + beta) = lrelu(y * sc + sh), 8 channels (16 bytes) per thread; grid = (blocks, groups).
+// sums != NULL (train mode): every block derives mean / rstd of its group from the statistics sums itself (no separate
+// finalisation launch); block 0 of each group stores them for backward, and block (0, 0) updates the running statistics
+// with momentum, group after group in call order (unbiased variance; run_shift is added to the batch mean).
+// sums == NULL (eval mode): mean / rstd are inputs.
+__global__ void bn_lrelu_fwd_kernel(const uint4* __restrict__ y, long long nvec, int c, const double* __restrict__ sums,
+                                    double n, float eps, float momentum, float* __restrict__ mean, float* __restrict__ rstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    float* __restrict__ run_mean, float* __restrict__ run_var,
+                                    long long* __restrict__ num_batches, const float* __restrict__ run_shift, float slope,
+                                    int bf, uint4* __restrict__ a) {
   griddep_wait();   // PDL: see launch_pdl
   __shared__ float sc[512], sh[512];
+  const int grp = blockIdx.y, groups = gridDim.y;
+  y += (long long)grp * nvec;
+  a += (long long)grp * nvec;
   for (int i = threadIdx.x; i < c; i += blockDim.x) {
-    const float k = gamma[i] * rstd[i];
+    float m, r;
+    if (sums) {
+      double var;
+      bn_moments(sums + (long long)grp * 2 * c, c, i, n, eps, m, r, var);
+      if (blockIdx.x == 0) { mean[grp * c + i] = m; rstd[grp * c + i] = r; }
+    } else {
+      m = mean[grp * c + i];
+      r = rstd[grp * c + i];
+    }
+    const float k = gamma[i] * r;
     sc[i] = k;
-    sh[i] = beta[i] - mean[i] * k;
+    sh[i] = beta[i] - m * k;
+  }
+  if (sums && run_mean && blockIdx.x == 0 && grp == 0) {
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+      float rm = run_mean[i], rv = run_var[i];
+      for (int g = 0; g < groups; g++) {
+        float m, r;
+        double var;
+        bn_moments(sums + (long long)g * 2 * c, c, i, n, eps, m, r, var);
+        rm = (1.f - momentum) * rm + momentum * (m + (run_shift ? run_shift[i] : 0.f));
+        const double unb = n > 1 ? var * n / (n - 1) : var;
+        rv = (1.f - momentum) * rv + momentum * (float)unb;
+      }
+      run_mean[i] = rm;
+      run_var[i] = rv;
+    }
+    if (threadIdx.x == 0 && num_batches) *num_batches += groups;
   }
   __syncthreads();
   const int cv = c >> 3;
@@ -178,8 +211,8 @@ __global__ void bn_lrelu_fwd_kernel(const uint4* __restrict__ y, long long nvec,
   }
 }
 
-// dy = gamma * rstd * (dz - s1/n - xhat * s2/n) = ka*dz + kb*y + kc per channel; also emits
-// dgamma = s2*gmul, dbeta = s1*gmul once (block 0).
+// dy = gamma * rstd * (dz - s1/n - xhat * s2/n) = ka*dz + kb*y + kc per channel and group; block (0, 0) also emits
+// dgamma = sum_groups s2 * gmul, dbeta = sum_groups s1 * gmul (the groups are passes of one optimiser step).
 __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ y, long long nvec, int c,
                                     double n, const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ gamma, const double* __restrict__ sums, float gmul,
@@ -187,19 +220,26 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* _
                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
   griddep_wait();   // PDL: see launch_pdl
   __shared__ float ka[512], kb[512], kc[512];
+  const int grp = blockIdx.y, groups = gridDim.y;
+  dz += (long long)grp * nvec;
+  y += (long long)grp * nvec;
+  dy += (long long)grp * nvec;
   const int cv = c >> 3;
-  if (blockIdx.x == 0 && dgamma) {
+  if (blockIdx.x == 0 && grp == 0 && dgamma) {
     float mul = gmul;
     if (gdiv_dev) mul /= __ldg(gdiv_dev);
     for (int i = threadIdx.x; i < c; i += blockDim.x) {
-      const float db = (float)sums[i] * mul, dgm = (float)sums[c + i] * mul;
+      double s1 = 0, s2 = 0;
+      for (int g = 0; g < groups; g++) { s1 += sums[(long long)g * 2 * c + i]; s2 += sums[(long long)g * 2 * c + c + i]; }
+      const float db = (float)s1 * mul, dgm = (float)s2 * mul;
       dbeta[i] = accumulate ? dbeta[i] + db : db;
       dgamma[i] = accumulate ? dgamma[i] + dgm : dgm;
     }
   }
+  const double* sg = sums + (long long)grp * 2 * c;
   for (int i = threadIdx.x; i < c; i += blockDim.x) {
-    const double k1 = sums[i] / n, k2 = sums[c + i] / n;
-    const double g = gamma[i], r = rstd[i], m = mean[i];
+    const double k1 = sg[i] / n, k2 = sg[c + i] / n;
+    const double g = gamma[i], r = rstd[grp * c + i], m = mean[grp * c + i];
     ka[i] = (float)(g * r);
     kb[i] = (float)(-g * r * r * k2);
     kc[i] = (float)(g * r * (m * r * k2 - k1));
@@ -218,12 +258,6 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* _
     }
     dy[i] = make_uint4(out[0], out[1], out[2], out[3]);
   }
-}
-
-__global__ void zero_doubles_kernel(double* p, int n) {
-  griddep_wait();   // PDL: see launch_pdl
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -530,80 +564,84 @@ static int nblocks(long long n, int threads, int cap = 148 * 16) {
   return (int)b;
 }
 
-static void launch_bn_reduce(const void* x16, const void* y16, long long npix, int c, const float* mean, const float* rstd,
-                             int mode, int dtype, double* sums_ws, cudaStream_t stream) {
+static void launch_bn_reduce(const void* x16, const void* y16, long long npix, int c, int groups, const float* mean,
+                             const float* rstd, int mode, int dtype, double* sums_ws, cudaStream_t stream) {
   if (c == 64 || c == 128 || c == 256 || c == 512) {
     const int rpp = 256 / (c / 8);
     long long bx = (npix + (long long)rpp * 8 - 1) / ((long long)rpp * 8);
-    // two blocks per SM: measured (tools/perf_helpers.py, PESR_BN_BLOCKS) 2-4 us faster per call than 4 or 8 - every
-    // block ends with 2*c double atomics onto the same addresses
+    // two blocks per SM over all groups: measured (tools/perf_helpers.py, PESR_BN_BLOCKS) 2-4 us faster per call than 4 or
+    // 8 - every block ends with 2*c double atomics onto the same addresses
     static int cap = -1;
     if (cap < 0) {
       const char* e = getenv("PESR_BN_BLOCKS");
       cap = e ? atoi(e) : 148 * 2;
     }
-    if (bx > cap) bx = cap;
+    const long long cap_g = cap / groups > 0 ? cap / groups : 1;
+    if (bx > cap_g) bx = cap_g;
     if (bx < 1) bx = 1;
-    launch_pdl(bn_reduce_vec_kernel, (unsigned)bx, 256, 0, stream, reinterpret_cast<const uint4*>(x16),
-                                                          reinterpret_cast<const uint4*>(y16), npix, c, mean, rstd,
-                                                          mode, dtype, sums_ws);
+    launch_pdl(bn_reduce_vec_kernel, dim3((unsigned)bx, (unsigned)groups), 256, 0, stream, reinterpret_cast<const uint4*>(x16),
+               reinterpret_cast<const uint4*>(y16), npix, c, mean, rstd, mode, dtype, sums_ws);
   } else {
     long long bx = (npix + 8 * 64 - 1) / (8 * 64);
     if (bx > 1184) bx = 1184;
-    dim3 grid((unsigned)bx, (unsigned)((c + 63) / 64));
+    dim3 grid((unsigned)bx, (unsigned)((c + 63) / 64), (unsigned)groups);
     launch_pdl(bn_reduce_kernel, grid, 256, 0, stream, reinterpret_cast<const uint16_t*>(x16),
                                               reinterpret_cast<const uint16_t*>(y16), npix, c, mean, rstd, mode, dtype,
                                               sums_ws);
   }
 }
 
-extern "C" int pesr_bn_stats(const void* y16, int64_t npix, int32_t c, float eps, float momentum, double* sums_ws,
-                             float* mean, float* rstd, float* running_mean, float* running_var,
-                             int64_t* num_batches_tracked, const float* running_mean_shift, int32_t dtype,
-                             void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  PESR_CHECK_ARG(sums_ws && mean && rstd && npix > 0 && c > 0 && c % 8 == 0, "bn_stats: bad arguments");
-  PESR_CHECK_ARG(c <= 512, "bn_stats: at most 512 channels");
-  if (y16) launch_bn_reduce(y16, nullptr, npix, c, nullptr, nullptr, 0, dtype, sums_ws, stream);
-  launch_pdl(bn_finalize_kernel, (c + 127) / 128, 128, 0, stream, sums_ws, c, (double)npix, eps, momentum, mean, rstd,
-                                                         running_mean, running_var,
-                                                         reinterpret_cast<long long*>(num_batches_tracked),
-                                                         running_mean_shift);
-  count_launch(2);
-  PESR_CHECK_LAUNCH("bn_stats");
+static int bn_zero(double* sums_ws, int groups, int c, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(sums_ws, 0, sizeof(double) * 2 * (size_t)c * groups, stream);
+  if (e != cudaSuccess) { set_error("bn: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
   return 0;
 }
 
-extern "C" int pesr_bn_lrelu_fwd(const void* y16, int64_t npix, int32_t c, const float* mean, const float* rstd,
-                                 const float* gamma, const float* beta, float slope, int32_t dtype, void* a16,
-                                 void* stream_) {
+extern "C" int pesr_bn_reduce(const void* y16, int64_t npix, int32_t c, int32_t groups, double* sums_ws, int32_t zero_first,
+                              int32_t dtype, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  PESR_CHECK_ARG(y16 && a16 && mean && rstd && gamma && beta && npix > 0 && c % 8 == 0 && c <= 512,
-                 "bn_lrelu_fwd: bad arguments");
+  PESR_CHECK_ARG(y16 && sums_ws && npix > 0 && c > 0 && c % 8 == 0 && c <= 512 && groups >= 1 && groups <= 8,
+                 "bn_reduce: bad arguments");
+  if (zero_first) { int r = bn_zero(sums_ws, groups, c, stream); if (r) return r; }
+  launch_bn_reduce(y16, nullptr, npix, c, groups, nullptr, nullptr, 0, dtype, sums_ws, stream);
+  count_launch();
+  PESR_CHECK_LAUNCH("bn_reduce");
+  return 0;
+}
+
+extern "C" int pesr_bn_lrelu_fwd(const void* y16, int64_t npix, int32_t c, int32_t groups, const double* sums_ws, float eps,
+                                 float momentum, float* mean, float* rstd, const float* gamma, const float* beta,
+                                 float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                                 const float* running_mean_shift, float slope, int32_t dtype, void* a16, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(y16 && a16 && mean && rstd && gamma && beta && npix > 0 && c % 8 == 0 && c <= 512 && groups >= 1 &&
+                     groups <= 8, "bn_lrelu_fwd: bad arguments");
   const long long nvec = npix * (c / 8);
-  launch_pdl(bn_lrelu_fwd_kernel, nblocks(nvec, 256, 148 * 16), 256, 0, stream, reinterpret_cast<const uint4*>(y16), nvec, c, mean,
-                                                                       rstd, gamma, beta, slope, dtype,
-                                                                       reinterpret_cast<uint4*>(a16));
+  int bx = nblocks(nvec, 256, 148 * 16 / groups);
+  launch_pdl(bn_lrelu_fwd_kernel, dim3((unsigned)bx, (unsigned)groups), 256, 0, stream, reinterpret_cast<const uint4*>(y16), nvec, c,
+             sums_ws, (double)npix, eps, momentum, mean, rstd, gamma, beta, running_mean, running_var,
+             reinterpret_cast<long long*>(num_batches_tracked), running_mean_shift, slope, dtype,
+             reinterpret_cast<uint4*>(a16));
   count_launch();
   PESR_CHECK_LAUNCH("bn_lrelu_fwd");
   return 0;
 }
 
-extern "C" int pesr_bn_lrelu_bwd(const void* dz16, const void* y16, int64_t npix, int32_t c, const float* mean,
-                                 const float* rstd, const float* gamma, double* sums_ws, float grad_mul,
-                                 const float* grad_div_dev, int32_t dtype, void* dy16, float* dgamma, float* dbeta,
-                                 int32_t accumulate, void* stream_) {
+extern "C" int pesr_bn_lrelu_bwd(const void* dz16, const void* y16, int64_t npix, int32_t c, int32_t groups,
+                                 const float* mean, const float* rstd, const float* gamma, double* sums_ws,
+                                 int32_t zero_first, float grad_mul, const float* grad_div_dev, int32_t dtype, void* dy16,
+                                 float* dgamma, float* dbeta, int32_t accumulate, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  PESR_CHECK_ARG(dz16 && y16 && dy16 && mean && rstd && gamma && sums_ws && npix > 0 && c % 8 == 0,
-                 "bn_lrelu_bwd: bad arguments");
-  PESR_CHECK_ARG(c <= 512, "bn_lrelu_bwd: at most 512 channels");
-  launch_bn_reduce(dz16, y16, npix, c, mean, rstd, 1, dtype, sums_ws, stream);
+  PESR_CHECK_ARG(dz16 && y16 && dy16 && mean && rstd && gamma && sums_ws && npix > 0 && c % 8 == 0 && c <= 512 &&
+                     groups >= 1 && groups <= 8, "bn_lrelu_bwd: bad arguments");
+  if (zero_first) { int r = bn_zero(sums_ws, groups, c, stream); if (r) return r; }
+  launch_bn_reduce(dz16, y16, npix, c, groups, mean, rstd, 1, dtype, sums_ws, stream);
   const long long nvec = npix * (c / 8);
-  launch_pdl(bn_bwd_apply_kernel, nblocks(nvec, 256, 148 * 16), 256, 0, stream, 
+  int bx = nblocks(nvec, 256, 148 * 16 / groups);
+  launch_pdl(bn_bwd_apply_kernel, dim3((unsigned)bx, (unsigned)groups), 256, 0, stream,
       reinterpret_cast<const uint4*>(dz16), reinterpret_cast<const uint4*>(y16), nvec, c, (double)npix, mean, rstd, gamma,
       sums_ws, grad_mul, grad_div_dev, dtype, reinterpret_cast<uint4*>(dy16), dgamma, dbeta, accumulate);
-  launch_pdl(zero_doubles_kernel, (2 * c + 255) / 256, 256, 0, stream, sums_ws, 2 * c);
-  count_launch(3);
+  count_launch(2);
   PESR_CHECK_LAUNCH("bn_lrelu_bwd");
   return 0;
 }
@@ -699,10 +737,16 @@ extern "C" int pesr_linear_skinny_wgrad(const float* dy, const void* x16, int32_
                                         const float* div_dev, int32_t accumulate, int32_t dtype, float* dw,
                                         void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  PESR_CHECK_ARG(dy && x16 && dw && nb > 0 && nb <= 16 && k % 4 == 0 && o > 0, "linear_wgrad: bad arguments");
+  PESR_CHECK_ARG(dy && x16 && dw && nb > 0 && nb <= 32 && k % 4 == 0 && o > 0, "linear_wgrad: bad arguments");
   dim3 grid((unsigned)((k / 4 + 255) / 256), (unsigned)((o + 7) / 8));
-  linear_wgrad_kernel<16><<<grid, 256, 0, stream>>>(dy, reinterpret_cast<const uint16_t*>(x16), nb, k, o, mul, div_dev,
-                                                    accumulate, dtype, dw);
+  // up to 32 rows per pass: the 302 MB gradient of the Discriminator's first Linear is written once for the two
+  // batched calls of a phase (a second 16-row pass re-reads and re-writes all of it)
+  if (nb <= 16)
+    linear_wgrad_kernel<16><<<grid, 256, 0, stream>>>(dy, reinterpret_cast<const uint16_t*>(x16), nb, k, o, mul, div_dev,
+                                                      accumulate, dtype, dw);
+  else
+    linear_wgrad_kernel<32><<<grid, 256, 0, stream>>>(dy, reinterpret_cast<const uint16_t*>(x16), nb, k, o, mul, div_dev,
+                                                      accumulate, dtype, dw);
   count_launch();
   PESR_CHECK_LAUNCH("linear_wgrad");
   return 0;
@@ -713,7 +757,7 @@ extern "C" int pesr_cast16(const float* src, int64_t n, int32_t dtype, void* dst
   PESR_CHECK_ARG(src && dst && n > 0, "cast16: bad arguments");
   cast16_kernel<<<nblocks((n + 1) / 2, 256), 256, 0, stream>>>(src, n, dtype, reinterpret_cast<uint16_t*>(dst));
   count_launch();
-  note_weight_write();   // cast16 produces the 16-bit Linear weights the FC igemm reads as its B operand
+  note_weight_write(stream);   // cast16 produces the 16-bit Linear weights the FC igemm reads as its B operand
   PESR_CHECK_LAUNCH("cast16");
   return 0;
 }

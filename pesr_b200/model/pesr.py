@@ -70,14 +70,18 @@ class Generator(nn.Module):
     def forward(self, x):
         _require_cuda(x, "Generator")
         eng = self.engine()
+        if not torch.is_grad_enabled():
+            # inference (test.py:106, the validation loop of train.py:281-295): no activations are kept.  (Inside an
+            # autograd.Function ctx.needs_input_grad is True for the parameters even under no_grad, so the decision is
+            # taken here.)
+            return eng.forward(x, train=False)[0]
         return _GeneratorFn.apply(eng, x, *eng.param_list)
 
 
 class _DiscriminatorFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, x, *params):
-        need = any(ctx.needs_input_grad)
-        logits, state = engine.forward(x, save=need)
+        logits, state = engine.forward(x, save=any(ctx.needs_input_grad))
         ctx.engine, ctx.state = engine, state
         return logits
 
@@ -85,42 +89,42 @@ class _DiscriminatorFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, dlogits):
         eng = ctx.engine
+        if ctx.state is None:
+            raise RuntimeError("pesr_b200.Discriminator: backward called twice through one forward")
         need_params = any(ctx.needs_input_grad[2:])
-        grads, dx = eng.backward(ctx.state, dlogits, need_param_grads=need_params,
-                                 need_input_grad=ctx.needs_input_grad[1])
+        grads, dxs = eng.backward(ctx.state, dlogits, need_param_grads=need_params,
+                                  need_input_grad=ctx.needs_input_grad[1])
         ctx.state = None
-        out = [None, dx]
+        out = [None, dxs[0]]
         for i, p in enumerate(eng.param_list):
             out.append(grads.get(p) if ctx.needs_input_grad[2 + i] else None)
         return tuple(out)
 
 
 class _DiscriminatorPairFn(torch.autograd.Function):
-    """D(a), D(b) as two separate train-mode calls (separate BatchNorm statistics, exactly as two module calls) whose
-    parameter gradients are produced by ONE backward: the second pass accumulates into the first pass's flat buffer,
-    so autograd has nothing to add and data-parallel training all-reduces the Discriminator's 80 M gradients once
-    per optimiser step instead of twice (train.py:205-216 back-propagates both logits before optim_D.step())."""
+    """D(a), D(b) as two separate train-mode calls (separate BatchNorm statistics, running statistics updated in call
+    order, exactly as two module calls) executed as ONE batch of 2N images: every layer is one launch instead of two
+    (the Discriminator's launches are latency-bound at batch 16), the parameter gradients of both calls come out of one
+    backward pass already summed, and data-parallel training all-reduces the Discriminator's 80 M gradients once per
+    optimiser step (train.py:205-216 back-propagates both logits before optim_D.step())."""
 
     @staticmethod
     def forward(ctx, engine, a, b, *params):
-        need = any(ctx.needs_input_grad)
-        la, sa = engine.forward(a, save=need)
-        lb, sb = engine.forward(b, save=need)
-        ctx.engine, ctx.states = engine, (sa, sb)
+        (la, lb), state = engine.forward([a, b], save=any(ctx.needs_input_grad))
+        ctx.engine, ctx.state = engine, state
         return la, lb
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dla, dlb):
         eng = ctx.engine
-        sa, sb = ctx.states
+        if ctx.state is None:
+            raise RuntimeError("pesr_b200.Discriminator: backward called twice through one forward")
         need_params = any(ctx.needs_input_grad[3:])
-        _, dxa = eng.backward(sa, dla, need_param_grads=need_params, need_input_grad=ctx.needs_input_grad[1],
-                              fire_hooks=False)
-        grads, dxb = eng.backward(sb, dlb, need_param_grads=need_params, need_input_grad=ctx.needs_input_grad[2],
-                                  acc_flat=eng.last_flat if need_params else None)
-        ctx.states = None
-        out = [None, dxa, dxb]
+        grads, dxs = eng.backward(ctx.state, [dla, dlb], need_param_grads=need_params,
+                                  need_input_grad=[ctx.needs_input_grad[1], ctx.needs_input_grad[2]])
+        ctx.state = None
+        out = [None, dxs[0], dxs[1]]
         for i, p in enumerate(eng.param_list):
             out.append(grads.get(p) if ctx.needs_input_grad[3 + i] else None)
         return tuple(out)
@@ -162,6 +166,8 @@ class Discriminator(nn.Module):
     def forward(self, x):
         _require_cuda(x, "Discriminator")
         eng = self.engine()
+        if not torch.is_grad_enabled():
+            return eng.forward(x, save=False)[0]
         return _DiscriminatorFn.apply(eng, x, *eng.param_list)
 
     def forward_pair(self, a, b):
@@ -169,4 +175,7 @@ class Discriminator(nn.Module):
         _require_cuda(a, "Discriminator")
         _require_cuda(b, "Discriminator")
         eng = self.engine()
+        if not torch.is_grad_enabled():
+            la, lb = eng.forward([a, b], save=False)[0]
+            return la, lb
         return _DiscriminatorPairFn.apply(eng, a, b, *eng.param_list)

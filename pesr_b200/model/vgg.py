@@ -78,4 +78,7 @@ class VGG(nn.Module):
     def forward(self, sr, hr):
         if not sr.is_cuda:
             raise RuntimeError(f"pesr_b200.VGG: input is on {sr.device}; the B200 path has no CPU fallback")
+        if not torch.is_grad_enabled():
+            f_sr, f_hr, _ = self.engine().forward(sr, hr, save=False)
+            return f_sr, f_hr
         return _VGGFn.apply(self.engine(), sr, hr)

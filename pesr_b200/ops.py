@@ -76,8 +76,11 @@ def make_conv_desc(*, dtype, nb, h, w, cin, cout, block_n=None, taps=TAPS_3X3, t
                    ld_res16=0, act=ACT_NONE, mask16=None, ld_mask16=0, mask_mode=0, out32=None, ld_out32=0,
                    out16=None, ld_out16=0, out_mode=OUT_NORMAL, out_h=0, out_w=0, out_sy=1, out_sx=1, out_oy=0,
                    out_ox=0, out_coff=0, ps_c=0, tile=None, aux_mode=0, ksplit=0, b_mn_major=0, split_stride32=0,
-                   bn_sums=None):
+                   bn_sums=None, classes=None):
     """Build a ``pesr_conv_desc``.
+
+    ``classes``: optional list of (ntaps, out_oy, out_ox) sub-problems sharing this launch (``taps`` / ``tap_widx`` list
+    their taps class by class), see pesr_conv_desc.ncls.
 
     ``srcs`` is a list of (tensor_or_ptr, src_h, src_w, stride_n, stride_h, stride_w) NHWC views (element
     strides); the descriptor keeps raw pointers, the caller keeps the tensors alive.
@@ -115,6 +118,12 @@ def make_conv_desc(*, dtype, nb, h, w, cin, cout, block_n=None, taps=TAPS_3X3, t
     d.aux_mode = aux_mode
     d.ksplit, d.b_mn_major, d.split_stride32 = ksplit, b_mn_major, split_stride32
     d.bn_sums = _ptr(bn_sums)
+    if classes:
+        if len(classes) > 4 or sum(c[0] for c in classes) != len(taps):
+            raise ValueError("make_conv_desc: at most 4 classes whose tap counts sum to len(taps)")
+        d.ncls = len(classes)
+        for i, (nt, oy, ox) in enumerate(classes):
+            d.cls_ntaps[i], d.cls_oy[i], d.cls_ox[i] = nt, oy, ox
     return d
 
 
@@ -326,24 +335,48 @@ def adam_multi_dev(table, nchunks, lr_dev, beta1, beta2, eps, step_dev, grad_mul
                                   _stream()), "pesr_adam_multi_dev")
 
 
+def bn_reduce(y16, npix, c, sums_ws, groups=1, zero_first=True):
+    """sums_ws[g] += (sum y, sum y^2) per channel of group g (npix pixels per group)."""
+    check(lib.pesr_bn_reduce(_ptr(y16), npix, c, groups, _ptr(sums_ws), 1 if zero_first else 0, dt_code(y16.dtype),
+                             _stream()), "pesr_bn_reduce")
+
+
+def bn_lrelu_fwd(y16, npix, c, mean, rstd, gamma, beta, a16, slope=0.2, groups=1, sums_ws=None, eps=1e-5, momentum=0.1,
+                 running_mean=None, running_var=None, num_batches=None, running_mean_shift=None):
+    """sums_ws given (train mode): mean / rstd are derived from the sums in the kernel, stored, and the running statistics
+    updated; sums_ws None (eval mode): mean / rstd are inputs."""
+    check(lib.pesr_bn_lrelu_fwd(_ptr(y16), npix, c, groups, _ptr(sums_ws), eps, momentum, _ptr(mean), _ptr(rstd),
+                                _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), _ptr(num_batches),
+                                _ptr(running_mean_shift), slope, dt_code(y16.dtype), _ptr(a16), _stream()),
+          "pesr_bn_lrelu_fwd")
+
+
 def bn_stats(y16, npix, c, sums_ws, mean, rstd, running_mean=None, running_var=None, num_batches=None, eps=1e-5,
              momentum=0.1, running_mean_shift=None):
-    # y16 = None: the sums come from the producing conv (make_conv_desc(bn_sums=...)); only the finalisation runs
-    check(lib.pesr_bn_stats(_ptr(y16), npix, c, eps, momentum, _ptr(sums_ws), _ptr(mean), _ptr(rstd),
-                            _ptr(running_mean), _ptr(running_var), _ptr(num_batches), _ptr(running_mean_shift),
-                            dt_code(y16.dtype) if y16 is not None else 0, _stream()), "pesr_bn_stats")
-
-
-def bn_lrelu_fwd(y16, npix, c, mean, rstd, gamma, beta, a16, slope=0.2):
-    check(lib.pesr_bn_lrelu_fwd(_ptr(y16), npix, c, _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), slope,
-                                dt_code(y16.dtype), _ptr(a16), _stream()), "pesr_bn_lrelu_fwd")
+    """Statistics only (tests / stand-alone use): mean, rstd and the running-statistics update of one train-mode call.
+    y16 = None: the sums were accumulated by the producing conv (make_conv_desc(bn_sums=...)).  The engines never call
+    this: their apply kernel derives mean / rstd from the sums itself."""
+    if y16 is not None:
+        bn_reduce(y16, npix, c, sums_ws)
+    mean64 = sums_ws[:c] / npix
+    var = (sums_ws[c:2 * c] / npix - mean64 * mean64).clamp_min(0)
+    mean.copy_(mean64)
+    rstd.copy_(torch.rsqrt(var + eps))
+    if running_mean is not None:
+        shift = running_mean_shift if running_mean_shift is not None else 0
+        running_mean.mul_(1 - momentum).add_(momentum * (mean64.float() + shift))
+        running_var.mul_(1 - momentum).add_(momentum * (var * (npix / max(npix - 1, 1))).float())
+    if num_batches is not None:
+        num_batches += 1
+    sums_ws[:2 * c].zero_()
 
 
 def bn_lrelu_bwd(dz16, y16, npix, c, mean, rstd, gamma, sums_ws, dy16, dgamma, dbeta, grad_mul=1.0, grad_div_dev=None,
-                 accumulate=False):
-    check(lib.pesr_bn_lrelu_bwd(_ptr(dz16), _ptr(y16), npix, c, _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(sums_ws),
-                                grad_mul, _ptr(grad_div_dev), dt_code(y16.dtype), _ptr(dy16), _ptr(dgamma),
-                                _ptr(dbeta), 1 if accumulate else 0, _stream()), "pesr_bn_lrelu_bwd")
+                 accumulate=False, groups=1, zero_first=True):
+    check(lib.pesr_bn_lrelu_bwd(_ptr(dz16), _ptr(y16), npix, c, groups, _ptr(mean), _ptr(rstd), _ptr(gamma),
+                                _ptr(sums_ws), 1 if zero_first else 0, grad_mul, _ptr(grad_div_dev), dt_code(y16.dtype),
+                                _ptr(dy16), _ptr(dgamma), _ptr(dbeta), 1 if accumulate else 0, _stream()),
+          "pesr_bn_lrelu_bwd")
 
 
 def maxpool2_fwd(x16, nb, h, w, c, y16):
@@ -388,8 +421,8 @@ def linear_dgrad(dy32, w16, nb, k, o, dx32):
 
 def linear_wgrad(dy32, x16, nb, k, o, dw, mul=1.0, div_dev=None, accumulate=False):
     dy32, x16 = dy32.view(nb, o), x16.view(nb, k)
-    for r in range(0, nb, _LINEAR_ROWS):
-        n = min(_LINEAR_ROWS, nb - r)
+    for r in range(0, nb, 2 * _LINEAR_ROWS):          # the weight-gradient kernel takes up to 32 rows per pass
+        n = min(2 * _LINEAR_ROWS, nb - r)
         check(lib.pesr_linear_skinny_wgrad(_ptr(dy32[r:]), _ptr(x16[r:]), n, k, o, mul, _ptr(div_dev),
                                            1 if (accumulate or r > 0) else 0, dt_code(x16.dtype), _ptr(dw), _stream()),
               "pesr_linear_skinny_wgrad")

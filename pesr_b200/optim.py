@@ -15,7 +15,11 @@ class Adam(torch.optim.Optimizer):
     CUDA graph of the whole training step (pesr_b200.graph.GraphedStep) replays correctly."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, capturable=False):
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, capturable=capturable))
+        # the keys torch.optim.Adam keeps in its param_groups, at the values this kernel implements, so that
+        # state_dict() loads into torch.optim.Adam and back
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False,
+                                      foreach=None, capturable=capturable, differentiable=False, fused=None,
+                                      decoupled_weight_decay=False))
         self._tables = {}
         self._dev = {}          # group index -> (step int32[1], lr float32[1], last lr uploaded)
         self.table_builds = 0   # how often the pointer table had to be rebuilt (0 or 1 per group in steady state)
@@ -68,6 +72,9 @@ class Adam(torch.optim.Optimizer):
             plist = [p for p in group['params'] if p.grad is not None]
             if not plist:
                 continue
+            if group.get('weight_decay', 0) or group.get('amsgrad', False) or group.get('maximize', False):
+                raise NotImplementedError("pesr_b200.optim.Adam: weight_decay / amsgrad / maximize are not on the PESR "
+                                          "path (train.py:124-126)")
             for p in plist:
                 if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
                     raise RuntimeError("pesr_b200.optim.Adam: parameters must be contiguous fp32 CUDA tensors")

@@ -10,6 +10,15 @@ import torch
 from . import losses
 
 _D_PAIR = os.environ.get("PESR_NO_D_PAIR") != "1"    # A/B knob (tools/ab_env.sh)
+_TWO_STREAMS = os.environ.get("PESR_NO_TWO_STREAMS") != "1"    # A/B knob: VGG branch on a second stream
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    s = _SIDE_STREAMS.get(device)
+    if s is None:
+        s = _SIDE_STREAMS[device] = torch.cuda.Stream(device=device)
+    return s
 
 
 def pretrain_step(G, optim_G, lr, hr, ddp=None):
@@ -34,9 +43,21 @@ def gan_step(G, D, vgg, optim_G, optim_D, lr, hr, cfg, ddp_g=None, ddp_d=None):
         p.requires_grad = True
     optim_D.zero_grad(set_to_none=True)
     sr = G(lr)
+    # The perceptual branch (VGG forward of sr / hr and, through autograd, its backward) depends on sr and hr only.  It is
+    # issued on a second stream: its tensor-core-bound convolutions then overlap the Discriminator's BatchNorm /
+    # element-wise / small-layer kernels, which are HBM- and latency-bound and leave the tensor cores idle (a conv CTA and
+    # the blocks of those kernels are co-resident on an SM).  Autograd runs each backward node on the stream of its forward
+    # and orders the streams where gradients meet, so the VGG backward overlaps the Discriminator's in the same way.
+    two = _TWO_STREAMS and sr.is_cuda
+    if two:
+        main, side = torch.cuda.current_stream(), _side_stream(sr.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            f_sr, f_hr = vgg(sr, hr)
+            vgg_loss = losses.mse_loss(f_sr, f_hr) * cfg['alpha_vgg']
     if _D_PAIR and hasattr(D, "forward_pair"):
         # D(hr) then D(sr.detach()) as in train.py:205-207 (same order of the BatchNorm running-statistics updates),
-        # with one gradient pass / one all-reduce for the parameters
+        # executed as one batch of 2N images with one gradient pass / one all-reduce for the parameters
         pred_real, pred_fake = D.forward_pair(hr, sr.detach())
     else:
         pred_real = D(hr)
@@ -54,8 +75,9 @@ def gan_step(G, D, vgg, optim_G, optim_D, lr, hr, cfg, ddp_g=None, ddp_d=None):
     # optimiser).
     optim_G.zero_grad(set_to_none=True)
     l1_loss = losses.l1_loss(sr, hr) * cfg['alpha_l1']
-    f_sr, f_hr = vgg(sr, hr)
-    vgg_loss = losses.mse_loss(f_sr, f_hr) * cfg['alpha_vgg']
+    if not two:
+        f_sr, f_hr = vgg(sr, hr)
+        vgg_loss = losses.mse_loss(f_sr, f_hr) * cfg['alpha_vgg']
     tv_scale = cfg['alpha_tv'] * (ddp_g.world_size if ddp_g is not None else 1)  # TV is a batch SUM (train.py:137-140)
     tv_loss = losses.tv_loss(sr) * tv_scale
     if ddp_d is not None:
@@ -64,8 +86,11 @@ def gan_step(G, D, vgg, optim_G, optim_D, lr, hr, cfg, ddp_g=None, ddp_d=None):
     # ---- Generator phase (train.py:234-259)
     for p in D.parameters():
         p.requires_grad = False
-    pred_fake = D(sr)
-    pred_real = D(hr)
+    if _D_PAIR and hasattr(D, "forward_pair"):
+        pred_fake, pred_real = D.forward_pair(sr, hr)       # D(sr) then D(hr), train.py:237-238, as one batch of 2N
+    else:
+        pred_fake = D(sr)
+        pred_real = D(hr)
     if cfg['gan_type'] == 'SGAN':
         if cfg['focal_loss']:
             G_loss = losses._GanLoss.apply(pred_fake, None, 1.0, 0.0, losses._uniform_target(t_real), 1,
@@ -78,6 +103,8 @@ def gan_step(G, D, vgg, optim_G, optim_D, lr, hr, cfg, ddp_g=None, ddp_d=None):
         else:
             G_loss = losses.rsgan_bce(pred_fake, pred_real, t_real)
     G_loss = G_loss * cfg['alpha_gan']
+    if two:
+        main.wait_stream(side)
     total_G_loss = l1_loss + vgg_loss + G_loss + tv_loss
     total_G_loss.backward()
     if ddp_g is not None:

@@ -17,14 +17,16 @@ def _latest(pool):
     return max(pool, key=lambda q: q.stamp) if isinstance(pool, (list, tuple)) else pool
 
 
-def d_plan_pins(pl):
+def d_plan_pins(pl, group=0):
+    """Pins of call `group` of a (possibly batched, see DiscriminatorEngine.forward) Discriminator forward."""
     nb = pl.nb
     pins = {}
     for i, (hh, ww) in enumerate(pl.dims):
         co = pl.Y[i].shape[1]
-        pins[f'y{i}'] = _nchw(pl.Y[i], nb, hh, ww, co)
-        pins[f'a{i}'] = _nchw(pl.A[i], nb, hh, ww, co)
-    pins['h1'] = pl.h1_32.double().cpu()
+        lo, hi = group * nb * hh * ww, (group + 1) * nb * hh * ww
+        pins[f'y{i}'] = _nchw(pl.Y[i][lo:hi], nb, hh, ww, co)
+        pins[f'a{i}'] = _nchw(pl.A[i][lo:hi], nb, hh, ww, co)
+    pins['h1'] = pl.h1_32[group * nb:(group + 1) * nb].double().cpu()
     return pins
 
 
@@ -57,7 +59,7 @@ def g_plan_pins(pl, c):
 
 def discriminator_pins(D, nb, h, w, which=0):
     """Saved tensors of plan `which` (order of acquisition) of the (nb, h, w) pool of D's engine."""
-    return d_plan_pins(D.engine().pools[(nb, h, w)][which])
+    return d_plan_pins(D.engine().pools[(nb, h, w, 1)][which])
 
 
 def vgg_pins(V, nb, h, w):
@@ -79,7 +81,7 @@ class StepTracer:
         G.engine().trace_hook = lambda pl: self.g.append(g_plan_pins(pl, G.n_feats)) if pl.train else None
         self.engines.append(G.engine())
         if D is not None:
-            D.engine().trace_hook = lambda pl: self.d.append(d_plan_pins(pl))
+            D.engine().trace_hook = lambda pl: self.d.extend(d_plan_pins(pl, g) for g in range(pl.groups))
             self.engines.append(D.engine())
         if V is not None:
             V.engine().trace_hook = lambda pl: self.v.append(v_plan_pins(pl))

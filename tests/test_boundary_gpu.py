@@ -86,7 +86,7 @@ def test_discriminator_batch_larger_than_16():
     assert y.shape == (nb, 1) and rel_l2(y.detach().cpu(), yo) < 6e-3
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in D.parameters())
     # the classifier gradients are exact functions of the saved activations: check the chunked Linear kernels directly
-    pl = D.engine().pools[(nb, 32, 32)][0]
+    pl = D.engine().pools[(nb, 32, 32, 1)][0]
     h1, flat7 = pl.h1_32.double(), pl.flat7.double()
     dlog = R.cuda().double()
     w2 = D.classifier[2].weight.detach().half().double()
@@ -215,9 +215,9 @@ def test_adam_state_dict_interchange_and_capturable_mode():
     p_e, o_e = make(Adam, capturable=True)   # device-side step count
     run(p_e, o_e, grads)
     for ref, b, d, e in zip(p_ref, p_b, p_d, p_e):
-        assert torch.allclose(b, ref, rtol=0, atol=2e-7)
-        assert torch.allclose(d, ref, rtol=0, atol=2e-7)
-        assert torch.allclose(e, ref, rtol=0, atol=2e-7)
+        assert torch.allclose(b, ref, rtol=0, atol=1e-6)      # a few fp32 ulps of |p| ~ 2 over five steps (operation order)
+        assert torch.allclose(d, ref, rtol=0, atol=1e-6)
+        assert torch.allclose(e, ref, rtol=0, atol=1e-6)
     assert int(o_e.state[p_e[0]]['step']) == 5
 
 

@@ -86,42 +86,60 @@ def test_stride2_fprop_dgrad_wgrad(nb, cin, cout, h, w):
     assert rel_l2(dw, ref_dw) < 2e-5
 
 
-@pytest.mark.parametrize("nb,c,h,w", [(4, 64, 24, 24), (2, 512, 3, 3), (16, 128, 12, 12)])
-def test_batchnorm_lrelu_forward_backward(nb, c, h, w):
-    """model/basic.py:29-30 in train mode, incl. running statistics, against torch's batch_norm in fp64."""
+@pytest.mark.parametrize("groups", [1, 2])
+@pytest.mark.parametrize("nb,c,h,w", [(4, 64, 24, 24), (2, 512, 3, 3), (16, 128, 12, 12), (3, 24, 5, 7)])
+def test_batchnorm_lrelu_forward_backward(nb, c, h, w, groups):
+    """model/basic.py:29-30 in train mode against torch's batch_norm in fp64, as the engines run it: statistics sums,
+    then ONE apply kernel that derives mean / rstd from the sums and updates the running statistics; `groups` independent
+    batches (= separate module calls, each with its own statistics, running statistics updated call after call) in one
+    launch; backward with the parameter gradients summed over the groups."""
     from pesr_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(1)
-    y = torch.randn(nb, c, h, w, device="cuda", generator=g) * 3 + 5 * torch.randn(1, c, 1, 1, device="cuda", generator=g)
+    nt = groups * nb
+    y = torch.randn(nt, c, h, w, device="cuda", generator=g) * 3 + 5 * torch.randn(1, c, 1, 1, device="cuda", generator=g)
+    y[nb:] += 2.0                                   # the groups have different statistics
     gamma = torch.rand(c, device="cuda", generator=g) + 0.5
     beta = torch.randn(c, device="cuda", generator=g)
+    shift = torch.randn(c, device="cuda", generator=g)
     y16 = _nhwc16(y)
-    yr = _nchw32(y16, nb, c, h, w).double().requires_grad_(True)
+    yr = _nchw32(y16, nt, c, h, w).double().requires_grad_(True)
     rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
     rm64, rv64 = rm.double(), rv.double()
     gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
-    ref = F.leaky_relu(F.batch_norm(yr, rm64, rv64, gd, bd, training=True, momentum=0.1, eps=1e-5), 0.2)
+    ref = torch.cat([F.leaky_relu(F.batch_norm(yr[k * nb:(k + 1) * nb] + shift.double().view(1, c, 1, 1), rm64, rv64, gd, bd,
+                                               training=True, momentum=0.1, eps=1e-5), 0.2) for k in range(groups)])
     npix = nb * h * w
-    ws = torch.zeros(2 * c, device="cuda", dtype=torch.float64)
-    mean, rstd = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    ws = torch.zeros(groups, 2, c, device="cuda", dtype=torch.float64)
+    mean, rstd = torch.empty(groups, c, device="cuda"), torch.empty(groups, c, device="cuda")
     nbt = torch.zeros((), device="cuda", dtype=torch.long)
-    ops.bn_stats(y16, npix, c, ws, mean, rstd, rm, rv, nbt)
+    ops.bn_reduce(y16, npix, c, ws, groups=groups, zero_first=True)
     a16 = torch.empty_like(y16)
-    ops.bn_lrelu_fwd(y16, npix, c, mean, rstd, gamma, beta, a16)
-    assert rel_l2(_nchw32(a16, nb, c, h, w), ref) < 4e-4
-    assert rel_l2(rm, rm64) < 1e-5 and rel_l2(rv, rv64) < 1e-5 and int(nbt) == 1
-    assert float(ws.abs().max()) == 0.0
+    ops.bn_lrelu_fwd(y16, npix, c, mean, rstd, gamma, beta, a16, groups=groups, sums_ws=ws, running_mean=rm, running_var=rv,
+                     num_batches=nbt, running_mean_shift=shift)
+    assert rel_l2(_nchw32(a16, nt, c, h, w), ref) < 4e-4     # BatchNorm output is invariant to the constant shift
+    assert rel_l2(rm, rm64) < 1e-5 and rel_l2(rv, rv64) < 1e-5 and int(nbt) == groups
+    for k in range(groups):
+        yk = yr[k * nb:(k + 1) * nb].detach()
+        assert rel_l2(mean[k], yk.mean(dim=(0, 2, 3))) < 1e-5
+        assert rel_l2(rstd[k], 1.0 / torch.sqrt(yk.var(dim=(0, 2, 3), unbiased=False) + 1e-5)) < 1e-5
+    # eval-mode form: mean / rstd are inputs, same result
+    a16b = torch.empty_like(y16)
+    ops.bn_lrelu_fwd(y16, npix, c, mean, rstd, gamma, beta, a16b, groups=groups)
+    assert torch.equal(a16b, a16)
     # backward: dz = dL/d(bn out) with lrelu' applied by the producer
-    da = torch.randn(nb, c, h, w, device="cuda", generator=g)
-    dz = da * torch.where(_nchw32(a16, nb, c, h, w) > 0, 1.0, 0.2)
+    da = torch.randn(nt, c, h, w, device="cuda", generator=g)
+    dz = da * torch.where(_nchw32(a16, nt, c, h, w) > 0, 1.0, 0.2)
     dz16 = _nhwc16(dz)
-    dzr = _nchw32(dz16, nb, c, h, w).double()
-    bn_out = F.batch_norm(yr, None, None, gd, bd, training=True, eps=1e-5)
+    dzr = _nchw32(dz16, nt, c, h, w).double()
+    bn_out = torch.cat([F.batch_norm(yr[k * nb:(k + 1) * nb], None, None, gd, bd, training=True, eps=1e-5) for k in range(groups)])
     gy, gg, gb = torch.autograd.grad(bn_out, [yr, gd, bd], dzr)
     dy16 = torch.empty_like(y16)
     dgam, dbet = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
-    ops.bn_lrelu_bwd(dz16, y16, npix, c, mean, rstd, gamma, ws, dy16, dgam, dbet)
-    assert rel_l2(_nchw32(dy16, nb, c, h, w), gy) < 5e-4
+    ops.bn_lrelu_bwd(dz16, y16, npix, c, mean, rstd, gamma, ws, dy16, dgam, dbet, groups=groups, zero_first=True)
+    assert rel_l2(_nchw32(dy16, nt, c, h, w), gy) < 5e-4
     assert rel_l2(dgam, gg) < 1e-5 and rel_l2(dbet, gb) < 1e-5
+    ops.bn_lrelu_bwd(dz16, y16, npix, c, mean, rstd, gamma, ws, dy16, dgam, dbet, groups=groups, zero_first=True, accumulate=True)
+    assert rel_l2(dgam, 2 * gg) < 1e-5 and rel_l2(dbet, 2 * gb) < 1e-5
 
 
 @pytest.mark.parametrize("nb,c,h,w", [(2, 64, 16, 24), (1, 128, 7, 9)])

@@ -17,7 +17,7 @@ import torch
 
 from . import ops
 from ._lib import check, lib
-from .engine_g import FlatGrads, PackedWeight, _Plan, _Release, _run_conv
+from .engine_g import _WGRAD_STREAM, FlatGrads, PackedWeight, SideLane, _Plan, _Release, _run_conv
 from .ops import ACT_LRELU
 
 D_LAYERS = [(3, 64, 1), (64, 64, 2), (64, 128, 1), (128, 128, 2), (128, 256, 1), (256, 256, 2), (256, 512, 1),
@@ -69,6 +69,7 @@ class DiscriminatorEngine:
         self.param_list = None
         self.defer_finish = False  # True: the data-parallel wrapper waits for the all-reduce itself (DataParallel.finish)
         self.last_flat = None
+        self.lane = None           # SideLane for the weight-gradient kernels (see engine_g.SideLane)
         self.trace_hook = None     # callable(plan), called at the end of every forward (parity tests read the saved activations)
 
     # ------------------------------------------------------------------ parameters
@@ -408,17 +409,42 @@ class DiscriminatorEngine:
             mark_hi[0] = lo
 
         h1_32, h1_16, flat7 = pl.h1_32[:nbb], pl.h1_16[:nbb], pl.flat7[:nbb]
+        # parameter gradients are leaves of the backward-data chain: they run on a second stream (engine_g.SideLane)
+        lane = None
+        if need_param_grads and _WGRAD_STREAM:
+            if self.lane is None:
+                self.lane = SideLane(dev)
+            lane = self.lane
+            lane.begin(torch.cuda.current_stream())
+
+        def on_lane(fn):
+            if lane is None:
+                fn(stream)
+            else:
+                lane.enter_lane()
+                with torch.cuda.stream(lane.stream):
+                    fn(lane.stream.cuda_stream)
+
+        def chained():
+            if lane is not None:
+                lane.after_chain()
+
         # ---- classifier (fp32 gradients, 16-bit operands)
         if need_param_grads:
-            ops.linear_wgrad(dlogits, h1_16, nbb, 1024, 1, grads[fc2.weight])
-            torch.sum(dlogits, dim=0, out=grads[fc2.bias])
-            mark(fc2.weight)
+            def fc2_grads(_st):
+                ops.linear_wgrad(dlogits, h1_16, nbb, 1024, 1, grads[fc2.weight])
+                torch.sum(dlogits, dim=0, out=grads[fc2.bias])
+                mark(fc2.weight)
+            on_lane(fc2_grads)
         ops.linear_dgrad(dlogits, self.w2_16, nbb, 1024, 1, sc.dh1)
         dz1 = sc.dh1 * torch.where(h1_32 > 0, 1.0, 0.2)      # LeakyReLU'(h1), an nbb x 1024 tensor
+        chained()
         if need_param_grads:
-            ops.linear_wgrad(dz1, flat7, nbb, pl.kfc, 1024, grads[fc1.weight])
-            torch.sum(dz1, dim=0, out=grads[fc1.bias])
-            mark(fc1.weight)
+            def fc1_grads(_st):
+                ops.linear_wgrad(dz1, flat7, nbb, pl.kfc, 1024, grads[fc1.weight])
+                torch.sum(dz1, dim=0, out=grads[fc1.bias])
+                mark(fc1.weight)
+            on_lane(fc1_grads)
         if sc.fc1_dgrad is not None:
             ops.amax_scale(dz1, sc.scale1, target=16.0)
             sc.dz1_16.copy_(dz1 * sc.scale1[1:2])
@@ -447,20 +473,25 @@ class DiscriminatorEngine:
                 dgam, dbet = dummy[:co], dummy[512:512 + co]
             ops.bn_lrelu_bwd(sc.dZ[i], pl.Y[i], npix, co, pl.mean[i], pl.rstd[i], bn.weight.detach(), sc.bn_sums[i],
                              sc.dY[i], dgam, dbet, grad_div_dev=scale, groups=gsel, zero_first=False)
+            chained()
             if need_param_grads:
-                check(lib.pesr_conv_wgrad(C.byref(wg[i]), C.byref(splits), stream), "pesr_conv_wgrad")
-                if i == 0:
-                    check(lib.pesr_wgrad_reduce(sc.wg.data_ptr(), splits.value, 1, 64, 64, ops.WMAP_COL_IN, 64, 3, 1.0,
-                                                scale.data_ptr(), 0, grads[conv.weight].data_ptr(), stream),
-                          "pesr_wgrad_reduce")
-                else:
-                    check(lib.pesr_wgrad_reduce(sc.wg.data_ptr(), splits.value, 9, co, ci, ops.WMAP_OIHW, co, ci, 1.0,
-                                                scale.data_ptr(), 0, grads[conv.weight].data_ptr(), stream),
-                          "pesr_wgrad_reduce")
-                mark(conv.weight)
+                def conv_grads(st, i=i, ci=ci, co=co, conv=conv):
+                    check(lib.pesr_conv_wgrad(C.byref(wg[i]), C.byref(splits), st), "pesr_conv_wgrad")
+                    if i == 0:
+                        check(lib.pesr_wgrad_reduce(sc.wg.data_ptr(), splits.value, 1, 64, 64, ops.WMAP_COL_IN, 64, 3, 1.0,
+                                                    scale.data_ptr(), 0, grads[conv.weight].data_ptr(), st),
+                              "pesr_wgrad_reduce")
+                    else:
+                        check(lib.pesr_wgrad_reduce(sc.wg.data_ptr(), splits.value, 9, co, ci, ops.WMAP_OIHW, co, ci, 1.0,
+                                                    scale.data_ptr(), 0, grads[conv.weight].data_ptr(), st),
+                              "pesr_wgrad_reduce")
+                    mark(conv.weight)
+                on_lane(conv_grads)
             if i > 0 or any(need_in[:gsel]):
                 for dsc in dg[i]:
                     _run_conv(dsc, stream)
+        if lane is not None:
+            lane.join()
         dxs = [None] * G
         if any(need_in[:gsel]):
             dx = torch.empty(nbb, 3, h, w, device=dev, dtype=torch.float32)

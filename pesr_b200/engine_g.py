@@ -158,6 +158,68 @@ class FlatGrads:
         return self.buf
 
 
+# Weight gradients on a second stream (SideLane): OFF by default.  Measured on the B200 (tools/gpu_r2_h.sh, CUDA-graph
+# replay, 50 steps): GAN step 16.90 ms with the lane vs 16.94 ms without, L1 pretrain step 11.17 vs 11.17 ms -- the SM
+# clock under the 1 kW power cap drops by as much as the overlap gains (1657 vs 1732 MHz median): the step is power-
+# bound, not tail-bound.  PESR_WGRAD_STREAM=1 enables it.
+_WGRAD_STREAM = os.environ.get("PESR_WGRAD_STREAM") == "1"
+
+
+class SideLane:
+    """A second CUDA stream for the weight-gradient kernels of a backward pass.
+
+    Backward-data is a serial chain (each dgrad feeds the next); the weight / bias gradients hang off it as leaves that
+    nothing in the chain waits for.  On one stream every one of those ~130 launches sits BETWEEN two links of the chain,
+    so every kernel boundary exposes the tail of one persistent kernel and the pipeline fill of the next (about 5 us of
+    a 33 us trunk convolution).  With the leaves on their own stream the block scheduler fills the SMs one kernel's
+    last wave leaves idle with the other stream's CTAs.  Ordering is by events (in a captured CUDA graph they become
+    plain edges): the lane waits for the newest chain event before each leaf group, and the chain waits, before
+    overwriting a ping-pong buffer, for the leaf work that read it (issued two chain launches earlier)."""
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.pool, self.used = [], 0
+
+    def _event(self):
+        if self.used == len(self.pool):
+            self.pool.append(torch.cuda.Event())
+        ev = self.pool[self.used]
+        self.used += 1
+        return ev
+
+    def begin(self, main):
+        self.main = main
+        self.used = 0
+        self.stream.wait_stream(main)
+        self.chain_ev, self.chain_dirty = None, False
+        self.lane_ev, self.snaps = None, []
+
+    def before_chain(self, lag=2):
+        """Call before a chain (backward-data) launch that may overwrite a buffer the lane read `lag` launches ago."""
+        if len(self.snaps) >= lag and self.snaps[-lag] is not None:
+            self.main.wait_event(self.snaps[-lag])
+        self.snaps.append(self.lane_ev)
+
+    def after_chain(self):
+        ev = self._event()
+        ev.record(self.main)
+        self.chain_ev, self.chain_dirty = ev, True
+
+    def enter_lane(self):
+        """Make the lane wait for everything the chain has produced so far (no-op if it already did)."""
+        if self.chain_dirty:
+            self.stream.wait_event(self.chain_ev)
+            self.chain_dirty = False
+
+    def after_lane(self):
+        ev = self._event()
+        ev.record(self.stream)
+        self.lane_ev = ev
+
+    def join(self):
+        self.main.wait_stream(self.stream)
+
+
 def _run_conv(desc, stream):
     check(lib.pesr_conv_igemm(C.byref(desc), stream), "pesr_conv_igemm")
 
@@ -179,6 +241,7 @@ class GeneratorEngine:
         self.param_list = None
         self.last_flat = None
         self.defer_finish = False  # True: the data-parallel wrapper waits for the all-reduce itself (DataParallel.finish)
+        self.lane = None           # SideLane for the weight-gradient kernels (created on first backward)
         self.trace_hook = None     # callable(plan), called at the end of every forward (parity tests read the saved activations)
 
     # ------------------------------------------------------------------ parameters
@@ -304,8 +367,9 @@ class GeneratorEngine:
         pl.dZ1 = e16(P, 4 * Cn)
         pl.dR16 = e16(P, Cn)
         pl.gS32 = e32(P, Cn)
-        pl.gS16 = e16(P, Cn)
-        pl.dT16 = e16(P, Cn)
+        # ping-pong (block parity): the weight-gradient stream may still read a buffer while backward-data runs ahead
+        pl.gS16 = [e16(P, Cn), e16(P, Cn)]
+        pl.dT16 = [e16(P, Cn), e16(P, Cn)]
         pl.dF0 = e16(P, Cn)
         pl.Zd = e32(P, 32)
         pl.dx_sm = e32(nb, 3, h, w)
@@ -349,20 +413,21 @@ class GeneratorEngine:
         wgrad(pl.dR16, Cn, Cn, pl.X[depth], Cn, Cn, h, w, tail.weight, ops.WMAP_OIHW, Cn, Cn)
         b.append(("mark", tail.weight))
         conv(h=h, w=w, cin=Cn, cout=Cn, srcs=src(pl.dR16, h, w, Cn), wpacked=pk["tail_d"].buf, out32=pl.gS32,
-             ld_out32=Cn, out16=pl.gS16, ld_out16=Cn)
+             ld_out32=Cn, out16=pl.gS16[depth % 2], ld_out16=Cn)
         for i in range(depth - 1, -1, -1):
             c1, c2 = trunk[i]
-            bgrad(pl.gS16, P, Cn, Cn, c2.bias, mul=rs)
-            wgrad(pl.gS16, Cn, Cn, pl.T[i], Cn, Cn, h, w, c2.weight, ops.WMAP_OIHW, Cn, Cn, mul=rs)
-            conv(h=h, w=w, cin=Cn, cout=Cn, srcs=src(pl.gS16, h, w, Cn), wpacked=pk[f"b{i}c2_d"].buf, alpha=rs,
-                 mask16=pl.T[i], ld_mask16=Cn, mask_mode=1, out16=pl.dT16, ld_out16=Cn)
-            bgrad(pl.dT16, P, Cn, Cn, c1.bias)
-            wgrad(pl.dT16, Cn, Cn, pl.X[i], Cn, Cn, h, w, c1.weight, ops.WMAP_OIHW, Cn, Cn)
+            gs_in, gs_out, dT = pl.gS16[(i + 1) % 2], pl.gS16[i % 2], pl.dT16[i % 2]
+            bgrad(gs_in, P, Cn, Cn, c2.bias, mul=rs)
+            wgrad(gs_in, Cn, Cn, pl.T[i], Cn, Cn, h, w, c2.weight, ops.WMAP_OIHW, Cn, Cn, mul=rs)
+            conv(h=h, w=w, cin=Cn, cout=Cn, srcs=src(gs_in, h, w, Cn), wpacked=pk[f"b{i}c2_d"].buf, alpha=rs,
+                 mask16=pl.T[i], ld_mask16=Cn, mask_mode=1, out16=dT, ld_out16=Cn)
+            bgrad(dT, P, Cn, Cn, c1.bias)
+            wgrad(dT, Cn, Cn, pl.X[i], Cn, Cn, h, w, c1.weight, ops.WMAP_OIHW, Cn, Cn)
             b.append(("mark", c1.weight))
             last = i == 0
-            conv(h=h, w=w, cin=Cn, cout=Cn, srcs=src(pl.dT16, h, w, Cn), wpacked=pk[f"b{i}c1_d"].buf,
+            conv(h=h, w=w, cin=Cn, cout=Cn, srcs=src(dT, h, w, Cn), wpacked=pk[f"b{i}c1_d"].buf,
                  res32=pl.gS32, ld_res32=Cn, res16=pl.dR16 if last else None, ld_res16=Cn,
-                 out32=None if last else pl.gS32, ld_out32=Cn, out16=pl.dF0 if last else pl.gS16, ld_out16=Cn)
+                 out32=None if last else pl.gS32, ld_out32=Cn, out16=pl.dF0 if last else gs_out, ld_out16=Cn)
         # embed (Cin = 3): wgrad against the saved im2col matrix; dgrad as a col2im GEMM (for sub_mean's gradients)
         bgrad(pl.dF0, P, Cn, Cn, g.embed.bias)
         wgrad(pl.dF0, Cn, Cn, pl.col_in, 64, 64, h, w, g.embed.weight, ops.WMAP_COL_IN, Cn, 3, taps=[(0, 0)])
@@ -483,25 +548,31 @@ class GeneratorEngine:
         splits_out = C.c_int32(0)
         if pl.first_fused_bias is not None:
             grads[pl.first_fused_bias].zero_()
-        for op in pl.bwd:
+        lane = None
+        if _WGRAD_STREAM:
+            if self.lane is None:
+                self.lane = SideLane(dev)
+            lane = self.lane
+            lane.begin(torch.cuda.current_stream())
+            wstream = lane.stream.cuda_stream
+
+        def leaf(op, st):
             kind = op[0]
-            if kind == "conv":
-                _run_conv(op[1], stream)
-            elif kind == "wgrad":
+            if kind == "wgrad":
                 _, d, (ntaps, m_total, n_total, map_mode, co, ci, mul), param = op
-                check(lib.pesr_conv_wgrad(C.byref(d), C.byref(splits_out), stream), "pesr_conv_wgrad")
+                check(lib.pesr_conv_wgrad(C.byref(d), C.byref(splits_out), st), "pesr_conv_wgrad")
                 check(lib.pesr_wgrad_reduce(pl.wg.data_ptr(), splits_out.value, ntaps, m_total, n_total, map_mode, co,
-                                            ci, mul, scale.data_ptr(), 0, grads[param].data_ptr(), stream),
+                                            ci, mul, scale.data_ptr(), 0, grads[param].data_ptr(), st),
                       "pesr_wgrad_reduce")
             elif kind == "wgrad_bias":
                 _, d, (ntaps, m_total, n_total, map_mode, co, ci, mul), param, (x16, npix, c, ldc, bmul, _p), bparam, znext = op
-                check(lib.pesr_conv_wgrad(C.byref(d), C.byref(splits_out), stream), "pesr_conv_wgrad")
+                check(lib.pesr_conv_wgrad(C.byref(d), C.byref(splits_out), st), "pesr_conv_wgrad")
                 zn = grads[znext] if znext is not None else None
                 check(lib.pesr_wgrad_reduce_bias(pl.wg.data_ptr(), splits_out.value, ntaps, m_total, n_total, map_mode, co,
                                                  ci, mul, scale.data_ptr(), 0, grads[param].data_ptr(), x16.data_ptr(),
                                                  npix, c, ldc, bmul, self.dt, grads[bparam].data_ptr(),
                                                  zn.data_ptr() if zn is not None else 0, zn.numel() if zn is not None else 0,
-                                                 stream), "pesr_wgrad_reduce_bias")
+                                                 st), "pesr_wgrad_reduce_bias")
             elif kind == "bias":
                 _, (x16, npix, c, ldc, mul, perm_c), param = op
                 if perm_c:
@@ -511,6 +582,26 @@ class GeneratorEngine:
                     ops.colsum16(x16, npix, c, ldc, grads[param], mul=mul, div_dev=scale)
             else:
                 mark(op[1])
+
+        if lane is None:
+            for op in pl.bwd:
+                if op[0] == "conv":
+                    _run_conv(op[1], stream)
+                else:
+                    leaf(op, stream)
+        else:
+            for op in pl.bwd:
+                if op[0] == "conv":                     # the backward-data chain stays on the caller's stream
+                    lane.before_chain()
+                    _run_conv(op[1], stream)
+                    lane.after_chain()
+                else:                                   # weight / bias gradients and the data-parallel hooks: side lane
+                    lane.enter_lane()
+                    with torch.cuda.stream(lane.stream):
+                        leaf(op, wstream)
+                    if op[0] != "mark":
+                        lane.after_lane()
+            lane.join()
         ops.col2im3(pl.Zd, 32, nb, h, w, pl.dx_sm, mul=1.0, div_dev=scale, sgn=-1)
         ops.moments3(pl.dx_sm, lr, pl.sums[12:])
         grads[g.sub_mean.weight].view(-1).copy_(s[12:21])

@@ -10,7 +10,11 @@ import torch
 from . import losses
 
 _D_PAIR = os.environ.get("PESR_NO_D_PAIR") != "1"    # A/B knob (tools/ab_env.sh)
-_TWO_STREAMS = os.environ.get("PESR_NO_TWO_STREAMS") != "1"    # A/B knob: VGG branch on a second stream
+# VGG branch on a second stream: OFF by default.  Measured (tools/gpu_r2_d.sh / gpu_r2_e.sh): 17.10 vs 17.19 ms per GAN
+# step; the tensor-core kernels claim all 227 KB of an SM's shared memory, so the Discriminator's memory-bound kernels
+# cannot be co-resident with them, and with a 176 KB budget the convolutions lose 0.45 ms while the overlap returns 0.19
+# (and the SM clock drops under the 1 kW power cap).  PESR_TWO_STREAMS=1 enables it.
+_TWO_STREAMS = os.environ.get("PESR_TWO_STREAMS") == "1"
 _SIDE_STREAMS = {}
 
 

@@ -256,7 +256,8 @@ def run_b200(args):
         eager_step(dev_lr[i % n_host], dev_hr[i % n_host])
     barrier()
     launches_per_step, graph_note, do_step = None, None, eager_step
-    if not args.no_graph and (world == 1 or args.graph_multi):
+    # N > 1 stays eager: capturing the step with ProcessGroupNCCL's all-reduce inside hung on the 2-GPU box (round 2)
+    if not args.no_graph and world == 1:
         try:
             L.launch_count(reset=True)
             mods = [m for m in (G, D, vgg) if m is not None]
@@ -562,7 +563,6 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the pretrain-step and inference side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
-    ap.add_argument("--graph-multi", action="store_true", help="also capture the step (incl. the NCCL all-reduce) at N > 1")
     ap.add_argument("--sustain-seconds", type=float, default=3.0, help="length of the extra sustained run (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -201,8 +201,8 @@ def _gan_step_against_pinned_oracle(opt, nb, gan_type, focal):
     print(f"{tag}: G grads rel-L2 median {ge[len(ge) // 2][0]:.2e} worst {ge[-1][0]:.2e} ({ge[-1][1]}); "
           f"D grads median {de[len(de) // 2][0]:.2e} worst {de[-1][0]:.2e} ({de[-1][1]}); "
           f"[free-running G median {gf[len(gf) // 2]:.2e}, information only]")
-    assert ge[len(ge) // 2][0] < 2e-3 and ge[-1][0] < 1e-2
-    assert de[len(de) // 2][0] < 2e-3 and de[-1][0] < 1e-2
+    assert ge[len(ge) // 2][0] < 2e-3 and ge[-1][0] < 3e-3      # measured 1.0e-3 .. 1.6e-3 / 1.3e-3 .. 1.8e-3
+    assert de[len(de) // 2][0] < 2e-3 and de[-1][0] < 3e-3      # measured 6.5e-4 / 1.1e-3
     # optim_D.step() (train.py:229): first Adam step = -lr * g / (|g| + eps), i.e. +-lr per element; compare the UPDATE
     bad, total = 0, 0
     for k, p in D.named_parameters():
@@ -212,7 +212,7 @@ def _gan_step_against_pinned_oracle(opt, nb, gan_type, focal):
         total += u_got.numel()
         assert float(u_got.abs().max()) <= 1.001 * lrate + 1e-7 * float(d_sd[k].abs().max()), k
     print(f"{tag}: D Adam update differs (by > 5% of lr) on {bad} of {total} elements ({bad / total:.2e})")
-    assert bad / total < 5e-3             # sign of near-zero gradient elements
+    assert bad / total < 1e-3             # sign of near-zero gradient elements (measured 2e-4)
     moved = [float((p.detach().cpu() - g_sd[k]).abs().max()) for k, p in G.named_parameters()]
     assert max(moved) < 6.2e-5 and min(moved) > 0   # optim_G.step(): lr = 5e-5 plus fp32 rounding of |p| ~ 114 (MeanShift bias)
     return G, D, V, optG, optD, cfg, lr, hr

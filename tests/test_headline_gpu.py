@@ -103,8 +103,9 @@ def test_gan_step_at_headline_config(gen):
     assert float(got[0]) == 0.0 and float(ref[0]) == 0.0          # alpha_l1 = 0 (train.py:76)
     for i in (1, 3):
         assert rels[i] < 1e-3, names[i]
-    # the adversarial terms go through 8 train-mode BatchNorm layers on 16-bit activations (logits 2-3e-3, see
-    # test_oracle.py::test_rounding_noise_floor): gated at 3e-3, measured values printed above
-    for i in (2, 4):
-        assert rels[i] < 3e-3, names[i]
+    # the adversarial terms go through 8 train-mode BatchNorm layers on 16-bit activations, twice (the G loss after D's
+    # Adam step): measured 6.4e-4 (g) and 1.2e-5 (d); the G loss is gated at 2e-3 because two free-running evaluations of a
+    # 16-bit BatchNorm stack agree on the logits only to ~2e-3 (test_oracle.py::test_rounding_noise_floor)
+    assert rels[4] < 1e-3, names[4]
+    assert rels[2] < 2e-3, names[2]
     G.load_state_dict(g_sd)      # leave the module-scoped fixture as it was

@@ -7,9 +7,11 @@ BatchNorm network (tests/test_oracle.py::test_rounding_noise_floor measures that
 Forward values are gated separately, against the free-running fp64 oracle (test_gan_gpu.py, test_generator_gpu.py,
 test_headline_gpu.py).
 
-Gates: every parameter / input gradient within 2e-3 relative L2 (median) and 1e-2 (worst tensor).  What remains is the
-16-bit storage of the gradient tensors between layers (one rounding of 2^-11/sqrt(3) = 2.8e-4 per stored tensor,
-accumulating like sqrt(#layers)); measured values are printed.
+Gates: every parameter / input gradient within 2e-3 relative L2 (median over the tensors) and 3e-3 (worst tensor).  What
+remains is the 16-bit storage of the gradient tensors between layers (one rounding of 2^-11/sqrt(3) = 2.8e-4 per stored
+tensor, accumulating like sqrt(#layers)).  Measured on the B200 (round 2): Discriminator median 6.5e-4 / worst 1.25e-3,
+VGG d(loss)/d(sr) 7.5e-4, Generator median 3.8e-4 .. 5.1e-4 / worst 6.1e-4, at the headline sizes as well as the small
+ones; the numbers are printed.
 """
 import pytest
 import torch
@@ -19,7 +21,7 @@ from conftest import rel_l2
 
 pytestmark = pytest.mark.gpu
 
-MED, WORST = 2e-3, 1e-2
+MED, WORST = 2e-3, 3e-3
 
 
 def _report(name, errs, extra=""):
@@ -86,7 +88,7 @@ def test_vgg_input_gradient_pinned(nb, side):
     e_g = rel_l2(src.grad.cpu(), og)
     print(f"VGG {side}px nb {nb}: pinned features {e_f:.2e}, loss {e_l:.2e}, d(loss)/d(sr) rel-L2 {e_g:.2e}")
     assert e_f < 1e-6 and e_l < 1e-5        # pinned: identical by construction
-    assert e_g < 5e-3                        # 16 stored 16-bit gradient tensors between the loss and the image
+    assert e_g < 2e-3                        # 16 stored 16-bit gradient tensors between the loss and the image
 
 
 @pytest.mark.parametrize("opt,shape", [({'depth': 2, 'num_channels': 64, 'res_scale': 0.1}, (2, 3, 10, 12)),

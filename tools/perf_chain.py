@@ -74,9 +74,9 @@ for npix, cc in ((16 * 192 * 192, 64), (16 * 96 * 96, 64), (16 * 96 * 96, 128), 
     mean, rstd = torch.zeros(cc, device="cuda"), torch.ones(cc, device="cuda")
     gam, bet = torch.ones(cc, device="cuda"), torch.zeros(cc, device="cuda")
     dg, db = torch.zeros(cc, device="cuda"), torch.zeros(cc, device="cuda")
-    t1 = chain_time(lambda: ops.bn_stats(y, npix, cc, ws, mean, rstd))
-    t2 = chain_time(lambda: ops.bn_lrelu_fwd(y, npix, cc, mean, rstd, gam, bet, a))
-    t3 = chain_time(lambda: ops.bn_lrelu_bwd(dz, y, npix, cc, mean, rstd, gam, ws, a, dg, db))
+    t1 = chain_time(lambda: ops.bn_reduce(y, npix, cc, ws, zero_first=False))
+    t2 = chain_time(lambda: ops.bn_lrelu_fwd(y, npix, cc, mean, rstd, gam, bet, a, sums_ws=ws))
+    t3 = chain_time(lambda: ops.bn_lrelu_bwd(dz, y, npix, cc, mean, rstd, gam, ws, a, dg, db, zero_first=False))
     mb = npix * cc * 2 / 1e6
     print(f"  {npix}x{cc} ({mb:.0f} MB): stats {t1:.1f} us, apply {t2:.1f} us, backward {t3:.1f} us")
 

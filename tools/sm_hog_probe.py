@@ -11,6 +11,9 @@ from pesr_b200 import steps  # noqa: E402
 from pesr_b200._lib import check, lib  # noqa: E402
 from pesr_b200.model import Generator  # noqa: E402
 from pesr_b200.optim import Adam  # noqa: E402
+# bring-up hooks live in the debug build only: run with PESR_B200_LIB=pesr_b200/libpesr_b200_debug.so (tools/build_debug.sh)
+from pesr_b200 import _debug as _dbg  # noqa: E402
+_dbg.bind()
 
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
@@ -32,19 +35,4 @@ for n in (0, 1, 4, 8, 16):
     e1.record()
     torch.cuda.synchronize()
     print(f"{n:2d} SMs pinned: pretrain step {e0.elapsed_time(e1) / 10:.2f} ms", flush=True)
-
-# bring-up hooks live in the debug build only: run with PESR_B200_LIB=pesr_b200/libpesr_b200_debug.so (tools/build_debug.sh)
-from pesr_b200 import _debug as _dbg, _lib as _L   # noqa: E402
-_dbg.bind()
-
-
-def _set_pair_mode_compat(mode):
-    """round-1 encoding of the option hook: 0/1/2 pair mode, 20x sub stages, 30x PDL, 40x staged epilogue, 50x specialised epilogue"""
-    if mode >= 500: _L.set_option(_L.OPT_SPECIALISED_EPILOGUE, mode - 500)
-    elif mode >= 400: _L.set_option(_L.OPT_STAGED_EPILOGUE, mode - 400)
-    elif mode >= 300: _L.set_option(_L.OPT_PDL, mode - 300)
-    elif mode >= 200: _L.set_option(_L.OPT_SUB_STAGES, mode - 200)
-    elif mode >= 100: pass
-    else: _L.set_option(_L.OPT_PAIR_MODE, mode)
-
 

@@ -514,6 +514,20 @@ def side_measurements(args, dev, G, optim_G, dev_lr, dev_hr):
         ms = timed(lambda i: steps.pretrain_step(G, optim_G, dev_lr[i % len(dev_lr)], dev_hr[i % len(dev_hr)]), k, warm=3)
         out["pretrain_step"] = {"metric": "L1 pretrain samples/s", "value": BATCH / (ms * 1e-3), "ms_per_step": ms,
                                 "tflops": step_gflop("pretrain") / ms, "launch": "eager", "config": "BASELINE.json configs[1]"}
+    # split-precision Generator (fp16 hi+lo operands, three tensor-core passes per conv: fp32-grade gradients), same step
+    try:
+        from pesr_b200.optim import Adam
+        torch.manual_seed(2)
+        Gs = Generator(OPT, split_precision=True).to(dev)
+        oS = Adam(Gs.parameters(), lr=5e-5)
+        ms = timed(lambda i: steps.pretrain_step(Gs, oS, dev_lr[i % len(dev_lr)], dev_hr[i % len(dev_hr)]), 5, warm=2)
+        out["split_precision_pretrain_step"] = {"metric": "L1 pretrain samples/s, split-precision Generator", "value": BATCH / (ms * 1e-3),
+                                                "ms_per_step": ms, "tflops_algorithmic": step_gflop("pretrain") / ms,
+                                                "tensor_passes_per_conv": 3, "launch": "eager",
+                                                "note": "pesr_b200/engine_g_split.py; tests/test_split_precision_gpu.py"}
+        del Gs, oS
+    except Exception as e:
+        out["split_precision_pretrain_step"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     G.eval()
     flop_px = 100505088
     inf = {}

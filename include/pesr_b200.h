@@ -241,6 +241,14 @@ int pesr_col2im3_tiled(const float* z, int32_t ldz, int32_t nb, int32_t h, int32
                        const float* affine_a, const float* affine_b, float mul_host, const float* div_dev, int32_t sgn,
                        float* pre_nchw, float* out_nchw, uint8_t* out_u8, void* stream);
 
+/* Split-precision operands (pesr_b200/engine_g_split.py): v = act(src * mul * [*mul_dev]) * act'(mask_hi + mask_lo)
+ * (mask_mode 1: relu', 2: lrelu'(0.2); masks optional); hi = round16(v), lo = round16(v - hi).  hi + lo carries 22 (fp16)
+ * significant bits, and hi*hi + lo*hi + hi*lo over three passes of pesr_conv_igemm (fp32 accumulation into out32 via
+ * res32) reproduces an fp32-grade product.  n must be a multiple of 4; either output may be NULL.
+ * pesr_im2col3 with pad_affine bit 3 (value 8) emits the low part of the im2col matrix in the same way. */
+int pesr_split16(const float* src, int64_t n, int32_t act, const void* mask_hi, const void* mask_lo, int32_t mask_mode,
+                 float mul, const float* mul_dev, int32_t dtype, void* hi, void* lo, void* stream);
+
 /* MeanShift as a stand-alone op (model/basic.py:9-17): out[n][o][p] = sum_i w9[o*3+i] * x[n][i][p] + b3[o] on
  * [nb][3][hw] fp32 tensors (b3 may be NULL). */
 int pesr_mean_shift(const float* x, int32_t nb, int64_t hw, const float* w9, const float* b3, float* out, void* stream);

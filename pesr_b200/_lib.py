@@ -110,6 +110,7 @@ SIGNATURES = {
     "pesr_u8hwc_to_f32nchw_batch": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "pesr_col2im3_tiled": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "pesr_mean_shift": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "pesr_split16": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _f32, _vp, _i32, _vp, _vp, _vp]),
     "pesr_psnr_y_sse": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp]),
     "pesr_gather_patches": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "pesr_loss_l1": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),

@@ -184,6 +184,45 @@ __global__ void gather_patches_kernel(const long long* __restrict__ table, int n
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Split-precision operands: v = act(src * mul) [* act'(mask_hi + mask_lo)]; hi = round16(v); lo = round16(v - hi).
+// hi + lo carries 22 (fp16) / 16 (bf16) significant bits; three tensor-core passes (hi*hi + lo*hi + hi*lo) then
+// reproduce an fp32-grade product (pesr_b200/engine_g_split.py).
+// ------------------------------------------------------------------------------------------
+__global__ void split16_kernel(const float4* __restrict__ src, long long n4, int act, const uint2* __restrict__ mask_hi,
+                               const uint2* __restrict__ mask_lo, int mask_mode, float mul,
+                               const float* __restrict__ mul_dev, int bf, uint2* __restrict__ hi, uint2* __restrict__ lo) {
+  griddep_wait();
+  if (mul_dev) mul *= __ldg(mul_dev);
+  const float neg = mask_mode == 2 ? 0.2f : 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 s = src[i];
+    float v[4] = {s.x * mul, s.y * mul, s.z * mul, s.w * mul};
+    if (act == PESR_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = fmaxf(v[j], 0.f);
+    } else if (act == PESR_ACT_LRELU) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+    }
+    if (mask_hi) {
+      const uint2 mh = mask_hi[i];
+      uint2 ml = make_uint2(0, 0);
+      if (mask_lo) ml = mask_lo[i];
+      const float2 a0 = unpack2(mh.x, bf), a1 = unpack2(mh.y, bf), b0 = unpack2(ml.x, bf), b1 = unpack2(ml.y, bf);
+      const float m[4] = {a0.x + b0.x, a0.y + b0.y, a1.x + b1.x, a1.y + b1.y};
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] *= m[j] > 0.f ? 1.f : neg;
+    }
+    const uint32_t h0 = pack2(v[0], v[1], bf), h1 = pack2(v[2], v[3], bf);
+    if (hi) hi[i] = make_uint2(h0, h1);
+    if (lo) {
+      const float2 r0 = unpack2(h0, bf), r1 = unpack2(h1, bf);
+      lo[i] = make_uint2(pack2(v[0] - r0.x, v[1] - r0.y, bf), pack2(v[2] - r1.x, v[3] - r1.y, bf));
+    }
+  }
+}
+
 // uint8 HWC [nb][h][w][3] -> fp32 NCHW [nb][3][h][w]
 __global__ void u8hwc_to_f32nchw_batch_kernel(const uint8_t* __restrict__ src, int nb, long long hw,
                                               float* __restrict__ dst) {
@@ -248,6 +287,19 @@ extern "C" int pesr_gather_patches(const int64_t* table_dev, int32_t nb, int32_t
              hr);
   count_launch();
   PESR_CHECK_LAUNCH("gather_patches");
+  return 0;
+}
+
+extern "C" int pesr_split16(const float* src, int64_t n, int32_t act, const void* mask_hi, const void* mask_lo,
+                            int32_t mask_mode, float mul, const float* mul_dev, int32_t dtype, void* hi, void* lo,
+                            void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(src && (hi || lo) && n > 0 && n % 4 == 0 && ((uintptr_t)src % 16) == 0, "split16: bad arguments (n %% 4, 16-byte alignment)");
+  launch_pdl(split16_kernel, io_blocks(n / 4, 256), 256, 0, stream, reinterpret_cast<const float4*>(src), (long long)(n / 4), act,
+             reinterpret_cast<const uint2*>(mask_hi), reinterpret_cast<const uint2*>(mask_lo), mask_mode, mul, mul_dev, dtype,
+             reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo));
+  count_launch();
+  PESR_CHECK_LAUNCH("split16");
   return 0;
 }
 

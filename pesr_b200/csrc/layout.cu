@@ -289,6 +289,10 @@ im2col3_tile_kernel(const float* __restrict__ src, int nb, int h, int w, const f
       }
       v[tap * 3] = v0; v[tap * 3 + 1] = v1; v[tap * 3 + 2] = v2;
     }
+    if (flags & 8) {        // split precision: emit the LOW part, v - float(round16(v)), of every column
+#pragma unroll
+      for (int j = 0; j < 27; j++) v[j] -= to_f32(from_f32(v[j], bf), bf);
+    }
     const int row = threadIdx.x, sw = row & 7;
 #pragma unroll
     for (int c = 0; c < 4; c++)

@@ -39,7 +39,7 @@ class Generator(nn.Module):
     """EDSR-style x4 SR network (model/pesr.py:3-38): sub_mean, embed, `depth` ResBlocks + conv with a
     global skip, Upsampler, add_mean.  ``opt`` keys: depth, num_channels, res_scale."""
 
-    def __init__(self, opt, dtype=torch.float16):
+    def __init__(self, opt, dtype=torch.float16, split_precision=False):
         nn.Module.__init__(self)
         self.n_resblock = opt['depth']
         self.n_feats = opt['num_channels']
@@ -58,12 +58,19 @@ class Generator(nn.Module):
         self.upsample = Upsampler(self.n_feats)
         self.add_mean = MeanShift(255, rgb_mean, rgb_std, 1)
         self._compute_dtype = dtype
+        # split_precision: fp16 hi+lo operands, three tensor-core passes per convolution (pesr_b200/engine_g_split.py):
+        # fp32-grade forward AND gradients at ~3.5x the cost; the headline path is the 16-bit schedule
+        self._split = bool(split_precision)
         self._engine = None
 
     def engine(self):
         if self._engine is None:
-            from ..engine_g import GeneratorEngine
-            self._engine = GeneratorEngine(self, self._compute_dtype)
+            if self._split:
+                from ..engine_g_split import SplitGeneratorEngine
+                self._engine = SplitGeneratorEngine(self)
+            else:
+                from ..engine_g import GeneratorEngine
+                self._engine = GeneratorEngine(self, self._compute_dtype)
             self._engine.param_list = list(self.parameters())
         return self._engine
 

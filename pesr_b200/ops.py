@@ -208,7 +208,7 @@ def im2col3_u8(src_u8, col, affine_a=None, affine_b=None):
     return col
 
 
-def im2col3(src, col, affine_a=None, affine_b=None, mul_dev=None, sgn=1, pad_affine=False, upper_zeroed=False):
+def im2col3(src, col, affine_a=None, affine_b=None, mul_dev=None, sgn=1, pad_affine=False, upper_zeroed=False, low_part=False):
     """upper_zeroed: columns 32..63 of ``col`` already hold zeros (buffer created with torch.zeros and only ever written
     by this function) - they are not stored again.  Not used by the engines: measured on the GAN step it is 0.4 ms
     SLOWER (18.18 -> 18.57 ms) - the conv that follows then fetches the zero halves from HBM instead of finding the
@@ -217,8 +217,8 @@ def im2col3(src, col, affine_a=None, affine_b=None, mul_dev=None, sgn=1, pad_aff
     nb, c, h, w = src.shape
     assert c == 3 and src.dtype == torch.float32 and src.is_contiguous()
     check(lib.pesr_im2col3(_ptr(src), nb, h, w, _ptr(affine_a), _ptr(affine_b), _ptr(mul_dev), sgn,
-                           (1 if pad_affine else 0) | (2 if upper_zeroed else 0), dt_code(col.dtype), _ptr(col),
-                           _stream()), "pesr_im2col3")
+                           (1 if pad_affine else 0) | (2 if upper_zeroed else 0) | (8 if low_part else 0), dt_code(col.dtype),
+                           _ptr(col), _stream()), "pesr_im2col3")
     return col
 
 
@@ -237,6 +237,13 @@ def col2im3(z, ldz, nb, h, w, out, bias=None, affine_a=None, affine_b=None, mul=
         check(lib.pesr_col2im3(_ptr(z), ldz, nb, h, w, _ptr(bias), _ptr(affine_a), _ptr(affine_b), mul, _ptr(div_dev),
                                sgn, _ptr(pre), _ptr(out), _stream()), "pesr_col2im3")
     return out if out is not None else out_u8
+
+
+def split16(src32, hi, lo, act=ACT_NONE, mask_hi=None, mask_lo=None, mask_mode=0, mul=1.0, mul_dev=None):
+    """hi = round16(v), lo = round16(v - hi) with v = act(src32 * mul) * act'(mask) (see pesr_split16)."""
+    ref = hi if hi is not None else lo
+    check(lib.pesr_split16(_ptr(src32), src32.numel(), act, _ptr(mask_hi), _ptr(mask_lo), mask_mode, mul, _ptr(mul_dev),
+                           dt_code(ref.dtype), _ptr(hi), _ptr(lo), _stream()), "pesr_split16")
 
 
 def mean_shift(x, w9, b3, out):

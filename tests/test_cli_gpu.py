@@ -21,12 +21,36 @@ def test_train_py_pretrain_then_gan(tmp_path):
               "--num_epochs", "1", "--max_iters", "2", "--check_point", str(tmp_path / "ck")]
     out = _run([os.path.join(ROOT, "train.py"), "--phase", "pretrain"] + common, ROOT)
     assert "Finish train [1/1]" in out and "Saved snapshot model." in out
+    assert "Finish valid [1/1]. Best PSNR:" in out and "Saved new best model." in out
     ckpt = tmp_path / "ck" / "pretrain" / "model_1.pt"
-    assert ckpt.exists()
+    assert ckpt.exists() and (tmp_path / "ck" / "pretrain" / "best_model.pt").exists()
     out = _run([os.path.join(ROOT, "train.py"), "--phase", "train", "--vgg_random", "--pretrained_model", str(ckpt)] + common,
                ROOT)
-    assert "Finish train [1/1]" in out and "Total G" in out
+    assert "Finish train [1/1]" in out and "Total G" in out and "Finish valid [1/1]. PSNR:" in out
     assert (tmp_path / "ck" / "train" / "model_1.pt").exists()
+    # full-state checkpoint (G, D incl. BatchNorm running statistics, both Adam states, epoch, RNG) and --resume
+    import torch
+    state = tmp_path / "ck" / "train" / "state_1.pt"
+    st = torch.load(state, map_location="cpu", weights_only=False)
+    assert st["epoch"] == 1 and {"G", "D", "optim_G", "optim_D", "rng", "best_psnr"} <= set(st)
+    assert any("running_mean" in k for k in st["D"]) and len(st["optim_D"]["state"]) == len(list(st["D"])) - 3 * 8
+    common2 = [a if a != "1" or common[i - 1] != "--num_epochs" else "2" for i, a in enumerate(common)]
+    out = _run([os.path.join(ROOT, "train.py"), "--phase", "train", "--vgg_random", "--resume", str(state)] + common2, ROOT)
+    assert "Resumed from" in out and "Epoch [2/2]" in out and "Epoch [1/2]" not in out
+    assert (tmp_path / "ck" / "train" / "state_2.pt").exists()
+    assert torch.load(tmp_path / "ck" / "train" / "state_2.pt", map_location="cpu", weights_only=False)["epoch"] == 2
+
+
+def test_train_py_with_cuda_graph(tmp_path):
+    """--cuda_graph true: the GAN step captured once and replayed (pesr_b200/graph.py); validation in between runs eagerly on
+    the replayed parameters."""
+    common = ["--synthetic", "--vgg_random", "--num_channels", "64", "--num_blocks", "2", "--batch_size", "4", "--patch_size", "16",
+              "--num_epochs", "2", "--max_iters", "3", "--cuda_graph", "true", "--check_point", str(tmp_path / "ck")]
+    out = _run([os.path.join(ROOT, "train.py"), "--phase", "train"] + common, ROOT)
+    assert "Finish train [2/2]" in out and "Finish valid [2/2]. PSNR:" in out
+    import re
+    psnr = [float(x) for x in re.findall(r"PSNR: ([0-9.]+)dB", out)]
+    assert len(psnr) == 2 and all(0 < p < 100 for p in psnr)
 
 
 def test_test_py_writes_x4_images(tmp_path):

@@ -64,6 +64,8 @@ parser.add_argument('--max_iters', type=int, default=0, help='stop an epoch afte
 parser.add_argument('--vgg_random', action='store_true', help='random-init VGG19 instead of torchvision\'s ImageNet '
                     'checkpoint (machines without network access)')
 parser.add_argument('--log_every', type=int, default=50)
+parser.add_argument('--cuda_graph', type=_bool, default=False, help='replay the training step as one CUDA graph (single GPU): '
+                    'host cost 0.04 ms instead of ~8 ms per step')
 parser.add_argument('--resume', type=str, default='', help='full training state written by this script '
                     '(<check_point>/<phase>/state_<epoch>.pt): networks, both Adam states, epoch, RNG')
 
@@ -140,13 +142,15 @@ def main():
         print('Fetching pretrained model', args.pretrained_model)
         G.load_state_dict(torch.load(args.pretrained_model, map_location='cpu'))
     G = DataParallel(G.to(device))
-    optim_G = Adam([p for p in G.parameters() if p.requires_grad], betas=(0.9, 0.999), lr=args.learning_rate)
+    graphed = args.cuda_graph and world == 1
+    optim_G = Adam([p for p in G.parameters() if p.requires_grad], betas=(0.9, 0.999), lr=args.learning_rate,
+                   capturable=graphed)
     gan = args.phase != 'pretrain'
     D = optim_D = None
     if gan:
         D = DataParallel(Discriminator(opt).to(device))
         vgg = VGG(pretrained=not args.vgg_random).to(device)
-        optim_D = Adam(D.parameters(), betas=(0.9, 0.999), lr=args.learning_rate)
+        optim_D = Adam(D.parameters(), betas=(0.9, 0.999), lr=args.learning_rate, capturable=graphed)
         cfg = dict(alpha_l1=args.alpha_l1, alpha_vgg=args.alpha_vgg, alpha_gan=args.alpha_gan, alpha_tv=args.alpha_tv,
                    fl_gamma=args.fl_gamma, gan_type=args.gan_type, focal_loss=args.focal_loss,
                    target_real=torch.ones(args.batch_size, 1, device=device),
@@ -180,6 +184,14 @@ def main():
         set_rng_state(st['rng'])
         if rank == 0:
             print('Resumed from %s at epoch %d' % (args.resume, start_epoch))
+    if gan:
+        def step_fn(lr, hr):
+            return steps.gan_step(G, D, vgg, optim_G, optim_D, lr, hr, cfg, ddp_g=G if world > 1 else None,
+                                  ddp_d=D if world > 1 else None)
+    else:
+        def step_fn(lr, hr):
+            return steps.pretrain_step(G, optim_G, lr, hr, ddp=G if world > 1 else None).detach().reshape(1)
+    gstep = None
     for epoch in range(start_epoch, args.num_epochs + 1):
         # train.py:156,185-186 call StepLR.step() at the START of every epoch.  Under the pinned torch 0.4 (README.md:22)
         # the scheduler's counter starts at -1, so epoch e (1-based) runs at lr * 0.5 ** ((e - 1) // lr_step): the first
@@ -195,11 +207,14 @@ def main():
         running = torch.zeros(5 if gan else 1, device=device)
         for it in range(iters):
             lr, hr = data.batch()
-            if gan:
-                running += steps.gan_step(G, D, vgg, optim_G, optim_D, lr, hr, cfg, ddp_g=G if world > 1 else None,
-                                          ddp_d=D if world > 1 else None)
+            if graphed:
+                if gstep is None:       # captured once (after the learning rate of this epoch is set); replayed afterwards
+                    from pesr_b200.graph import GraphedStep
+                    gstep = GraphedStep(step_fn, (lr, hr), modules=[m.module for m in (G, D) if m is not None] + ([vgg] if gan else []),
+                                        optimizers=[o for o in (optim_G, optim_D) if o is not None], warmup=2)
+                running += gstep(lr, hr)
             else:
-                running += steps.pretrain_step(G, optim_G, lr, hr, ddp=G if world > 1 else None).detach()
+                running += step_fn(lr, hr)
             if rank == 0 and args.log_every and (it + 1) % args.log_every == 0:
                 print('  iter %d/%d  %s' % (it + 1, iters, (running / (it + 1)).tolist()))   # one sync per log line
         avr = (running / max(iters, 1)).tolist()

@@ -135,6 +135,10 @@ int pesr_conv_igemm(const pesr_conv_desc* d, void* stream);
 #define PESR_OPT_PDL 2              /* programmatic dependent launch: 0 off, 1 on (default; PESR_NO_PDL=1 in the environment disables) */
 #define PESR_OPT_STAGED_EPILOGUE 3  /* residual epilogue through shared memory (pair kernel): 0 off, 1 on (default) */
 #define PESR_OPT_SPECIALISED_EPILOGUE 4 /* compile-time specialised epilogues: 0 generic kernel only, 1 on (default) */
+#define PESR_OPT_RESERVE_SMS 5      /* SMs the persistent tensor-core kernels leave free (their grids are sized to #SM - value;
+                                       default 0, PESR_RESERVE_SMS in the environment).  Data-parallel training reserves the SMs
+                                       NCCL's all-reduce CTAs occupy: with a full-machine static tile schedule ONE SM taken by a
+                                       concurrent kernel sends a CTA to a second wave (profiles/r02_sm_hog_probe.txt). */
 int pesr_set_option(int option, int value);
 
 /* ------------------------------------------------------------------------------------------------
@@ -160,6 +164,8 @@ typedef struct pesr_wgrad_desc {
   int32_t splits;           /* split-K factor (0 = choose) */
   float* partials;          /* [splits][ntaps][m_total][n_total] fp32 workspace */
   int64_t partials_elems;   /* capacity of `partials` in floats */
+  float out_mul;            /* the sums are stored multiplied by out_mul / (*out_div_dev): with splits == 1 `partials` can be */
+  const float* out_div_dev; /* the gradient itself (0 / NULL = 1; the Linear(73728 -> 1024) weight gradient is written this way) */
 } pesr_wgrad_desc;
 
 /* Returns the number of splits actually used in *splits_out (may be NULL). */
@@ -248,6 +254,22 @@ int pesr_col2im3_tiled(const float* z, int32_t ldz, int32_t nb, int32_t h, int32
  * pesr_im2col3 with pad_affine bit 3 (value 8) emits the low part of the im2col matrix in the same way. */
 int pesr_split16(const float* src, int64_t n, int32_t act, const void* mask_hi, const void* mask_lo, int32_t mask_mode,
                  float mul, const float* mul_dev, int32_t dtype, void* hi, void* lo, void* stream);
+
+/* fp32 NHWC helpers of the split-precision Discriminator / VGG schedules (activations between the three-pass
+ * convolutions are fp32; BatchNorm, LeakyReLU / ReLU and max-pool act on fp32 and only conv operands are split):
+ *  pesr_colmoments32: sums[0][ch] += sum_p a[p][ch]; sums[1][ch] += sum_p a[p][ch] * (b ? b : a)[p][ch]   (fp64, [2][c])
+ *  pesr_affine_split: v = ka[ch]*a + kb[ch]*b + kc[ch] (per-channel vectors; ka, kb/b, kc optional), v = act(v),
+ *    v *= act'(mask) (mask = 16-bit hi + lo pair or an fp32 tensor; mask_mode 1 relu', 2 lrelu'(0.2)); outputs (each
+ *    optional): out32 = v, hi = round16(v), lo = round16(v - hi).  BatchNorm forward / backward are this with the
+ *    coefficients derived from the moments.
+ *  pesr_maxpool2_f32_fwd / _bwd: as pesr_maxpool2_* on fp32. */
+int pesr_colmoments32(const float* a, const float* b, int64_t npix, int32_t c, double* sums, void* stream);
+int pesr_affine_split(const float* a, const float* b, int64_t npix, int32_t c, const float* ka, const float* kb,
+                      const float* kc, int32_t act, const void* mask_hi, const void* mask_lo, const float* mask32,
+                      int32_t mask_mode, int32_t dtype, float* out32, void* hi, void* lo, void* stream);
+int pesr_maxpool2_f32_fwd(const float* x, int32_t nb, int32_t h, int32_t w, int32_t c, float* y, void* stream);
+int pesr_maxpool2_f32_bwd(const float* x, const float* dy, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t relu_mask,
+                          float* dx, void* stream);
 
 /* MeanShift as a stand-alone op (model/basic.py:9-17): out[n][o][p] = sum_i w9[o*3+i] * x[n][i][p] + b3[o] on
  * [nb][3][hw] fp32 tensors (b3 may be NULL). */

@@ -67,6 +67,7 @@ class WgradDesc(C.Structure):
         ("b_sn", C.c_int64 * MAX_SRC), ("b_sh", C.c_int64 * MAX_SRC), ("b_sw", C.c_int64 * MAX_SRC),
         ("nsrc", C.c_int32), ("splits", C.c_int32),
         ("partials", C.c_void_p), ("partials_elems", C.c_int64),
+        ("out_mul", C.c_float), ("out_div_dev", C.c_void_p),
     ]
 
 
@@ -111,6 +112,10 @@ SIGNATURES = {
     "pesr_col2im3_tiled": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "pesr_mean_shift": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "pesr_split16": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _f32, _vp, _i32, _vp, _vp, _vp]),
+    "pesr_colmoments32": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "pesr_affine_split": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "pesr_maxpool2_f32_fwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "pesr_maxpool2_f32_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "pesr_psnr_y_sse": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp]),
     "pesr_gather_patches": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "pesr_loss_l1": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),

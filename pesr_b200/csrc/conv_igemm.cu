@@ -793,6 +793,7 @@ extern "C" int pesr_set_option(int option, int value) {
     case PESR_OPT_PDL: set_pdl(value); return 0;
     case PESR_OPT_STAGED_EPILOGUE: g_staged_enabled = value; return 0;
     case PESR_OPT_SPECIALISED_EPILOGUE: g_light_enabled = value; return 0;
+    case PESR_OPT_RESERVE_SMS: set_reserved_sms(value); return 0;
   }
   set_error("pesr_set_option: unknown option %d", option);
   return PESR_E_ARG;

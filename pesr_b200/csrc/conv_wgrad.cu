@@ -41,6 +41,8 @@ struct WgK {
   int lbo, sbo;  // MN-major descriptor strides (bytes)
   int8_t tap_dh[PESR_MAX_TAPS], tap_dw[PESR_MAX_TAPS], tap_src[PESR_MAX_TAPS];
   float* partials;
+  float out_mul;               // stored value = sum * out_mul / (*out_div_dev)
+  const float* out_div_dev;
   unsigned long long* dbg;
 };
 
@@ -229,6 +231,9 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
       float* dst_w = p.partials + (((long long)split * p.ntaps + tap) * p.m_total + mt * 128 + quarter * 32) * p.n_total +
                      nt * p.block_n + c16 * 4;
       const int rows_left = p.m_total - (mt * 128 + quarter * 32);      // rows of this warp inside the matrix
+      float osc = p.out_mul;
+      if (p.out_div_dev) osc /= __ldg(p.out_div_dev);
+      const bool scaled = osc != 1.f;
       uint32_t v[32], vn[32];
       tmem_ld32(taddr + ch_lo * 32, v);
       tmem_ld_wait();
@@ -245,7 +250,11 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
 #pragma unroll
           for (int i = 0; i < 4; i++) {
             const uint32_t rr = (uint32_t)(i * 8 + r16);
-            const uint4 o = lds128(tb + rr * 64u + (((uint32_t)c16 ^ ((rr >> 1) & 3u)) << 4));
+            uint4 o = lds128(tb + rr * 64u + (((uint32_t)c16 ^ ((rr >> 1) & 3u)) << 4));
+            if (scaled) {
+              o.x = __float_as_uint(__uint_as_float(o.x) * osc); o.y = __float_as_uint(__uint_as_float(o.y) * osc);
+              o.z = __float_as_uint(__uint_as_float(o.z) * osc); o.w = __float_as_uint(__uint_as_float(o.w) * osc);
+            }
             if ((int)rr < rows_left) stg128(dst_w + (long long)rr * p.n_total + ch * 32 + half * 16, o);
           }
           __syncwarp();      // the tile is rewritten by the next pass
@@ -560,6 +569,8 @@ extern "C" int pesr_conv_wgrad(const pesr_wgrad_desc* d, int32_t* splits_out, vo
   for (int t = 0; t < d->ntaps; t++)
     PESR_CHECK_ARG(d->tap_src[t] >= 0 && d->tap_src[t] < d->nsrc, "conv_wgrad: tap %d reads source %d", t, d->tap_src[t]);
   k.partials = d->partials;
+  k.out_mul = d->out_mul != 0.f ? d->out_mul : 1.f;
+  k.out_div_dev = d->out_div_dev;
   k.dbg = g_wg_dbg;
 
   WgMaps maps;

@@ -72,7 +72,24 @@ int conv_smem_budget() {
   return v;
 }
 
+static int g_reserve_sms = -1;     // -1: from the environment (PESR_RESERVE_SMS)
+
+void set_reserved_sms(int n) { g_reserve_sms = n < 0 ? 0 : n; }
+
+// SMs the persistent tensor-core kernels size their grids to: the device's count minus the reserved ones
+// (PESR_OPT_RESERVE_SMS), kept even so that CTA pairs fit.
 int num_sms() {
+  if (g_reserve_sms < 0) {
+    const char* e = getenv("PESR_RESERVE_SMS");
+    g_reserve_sms = e ? atoi(e) : 0;
+    if (g_reserve_sms < 0) g_reserve_sms = 0;
+  }
+  int n = device_sms() - g_reserve_sms;
+  n &= ~1;
+  return n < 2 ? 2 : n;
+}
+
+int device_sms() {
   static int cached[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);

@@ -16,7 +16,9 @@ void note_weight_write(cudaStream_t stream);
 bool weights_settled(cudaStream_t stream);
 bool pdl_enabled();
 void set_pdl(int on);
-int num_sms();
+int num_sms();        // SMs available to the persistent tensor-core kernels (device count - reserved)
+int device_sms();     // SMs of the current device
+void set_reserved_sms(int n);
 int conv_smem_budget();
 
 // Optional per-launch profiling of the tensor-core kernels (bench.py's roofline leg): when enabled, the

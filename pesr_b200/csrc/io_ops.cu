@@ -223,6 +223,142 @@ __global__ void split16_kernel(const float4* __restrict__ src, long long n4, int
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// fp32 NHWC helpers of the split-precision schedules (engine_d_split.py / engine_v_split.py): activations between the
+// three-pass convolutions are fp32, so BatchNorm / LeakyReLU / ReLU / max-pool act on fp32 and only the conv OPERANDS are
+// split into hi + lo.
+//   colmoments32:  sums[0][ch] += sum_p a[p][ch],  sums[1][ch] += sum_p a[p][ch] * (b ? b[p][ch] : a[p][ch])   (fp64)
+//   affine_split:  v = ka[ch]*a + kb[ch]*b + kc[ch]  (kb / b optional; ka / kc optional = 1 / 0), v = act(v),
+//                  v *= act'(mask_hi + mask_lo or mask32), outputs: out32 = v, hi = round16(v), lo = round16(v - hi)
+//   maxpool2_f32:  2x2 / 2 max-pool and its backward (first maximum in scan order, optional relu' mask), NHWC fp32
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colmoments32_kernel(const float* __restrict__ a, const float* __restrict__ b, long long npix, int c, double* __restrict__ sums) {
+  griddep_wait();
+  __shared__ double red[2][8][32];
+  const int lane = threadIdx.x & 31, rowi = threadIdx.x >> 5;
+  const int ch = blockIdx.y * 32 + lane;
+  double s0 = 0, s1 = 0;
+  if (ch < c) {
+    for (long long p = (long long)blockIdx.x * 8 + rowi; p < npix; p += (long long)gridDim.x * 8) {
+      const float x = a[p * c + ch];
+      const float y = b ? b[p * c + ch] : x;
+      s0 += (double)x;
+      s1 += (double)x * (double)y;
+    }
+  }
+  red[0][rowi][lane] = s0;
+  red[1][rowi][lane] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int which = threadIdx.x >> 5, l = threadIdx.x & 31;
+    double t = 0;
+    for (int i = 0; i < 8; i++) t += red[which][i][l];
+    const int cc = blockIdx.y * 32 + l;
+    if (cc < c) atomicAdd(sums + (long long)which * c + cc, t);
+  }
+}
+
+__global__ void affine_split_kernel(const float4* __restrict__ a, const float4* __restrict__ b, long long n4, int c4,
+                                    const float4* __restrict__ ka, const float4* __restrict__ kb, const float4* __restrict__ kc,
+                                    int act, const uint2* __restrict__ mask_hi, const uint2* __restrict__ mask_lo,
+                                    const float4* __restrict__ mask32, int mask_mode, int bf, float4* __restrict__ out32,
+                                    uint2* __restrict__ hi, uint2* __restrict__ lo) {
+  griddep_wait();
+  const float neg = mask_mode == 2 ? 0.2f : 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % c4);
+    const float4 s = a[i];
+    float v[4] = {s.x, s.y, s.z, s.w};
+    if (ka) { const float4 k = __ldg(ka + cc); v[0] *= k.x; v[1] *= k.y; v[2] *= k.z; v[3] *= k.w; }
+    if (b && kb) {
+      const float4 t = b[i], k = __ldg(kb + cc);
+      v[0] += k.x * t.x; v[1] += k.y * t.y; v[2] += k.z * t.z; v[3] += k.w * t.w;
+    }
+    if (kc) { const float4 k = __ldg(kc + cc); v[0] += k.x; v[1] += k.y; v[2] += k.z; v[3] += k.w; }
+    if (act == PESR_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = fmaxf(v[j], 0.f);
+    } else if (act == PESR_ACT_LRELU) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+    }
+    if (mask_hi) {
+      const uint2 mh = mask_hi[i];
+      uint2 ml = make_uint2(0, 0);
+      if (mask_lo) ml = mask_lo[i];
+      const float2 a0 = unpack2(mh.x, bf), a1 = unpack2(mh.y, bf), b0 = unpack2(ml.x, bf), b1 = unpack2(ml.y, bf);
+      const float m[4] = {a0.x + b0.x, a0.y + b0.y, a1.x + b1.x, a1.y + b1.y};
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] *= m[j] > 0.f ? 1.f : neg;
+    } else if (mask32) {
+      const float4 m = mask32[i];
+      v[0] *= m.x > 0.f ? 1.f : neg; v[1] *= m.y > 0.f ? 1.f : neg; v[2] *= m.z > 0.f ? 1.f : neg; v[3] *= m.w > 0.f ? 1.f : neg;
+    }
+    if (out32) out32[i] = make_float4(v[0], v[1], v[2], v[3]);
+    if (hi || lo) {
+      const uint32_t h0 = pack2(v[0], v[1], bf), h1 = pack2(v[2], v[3], bf);
+      if (hi) hi[i] = make_uint2(h0, h1);
+      if (lo) {
+        const float2 r0 = unpack2(h0, bf), r1 = unpack2(h1, bf);
+        lo[i] = make_uint2(pack2(v[0] - r0.x, v[1] - r0.y, bf), pack2(v[2] - r1.x, v[3] - r1.y, bf));
+      }
+    }
+  }
+}
+
+__global__ void maxpool2_f32_fwd_kernel(const float4* __restrict__ x, int nb, int h, int w, int c4, float4* __restrict__ y) {
+  griddep_wait();
+  const int ho = h >> 1, wo = w >> 1;
+  const long long total = (long long)nb * ho * wo * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % c4);
+    long long r = i / c4;
+    const int ox = (int)(r % wo); r /= wo;
+    const int oy = (int)(r % ho);
+    const int n = (int)(r / ho);
+    const long long base = (((long long)n * h + 2 * oy) * w + 2 * ox) * c4 + v;
+    const float4 q0 = x[base], q1 = x[base + c4], q2 = x[base + (long long)w * c4], q3 = x[base + (long long)w * c4 + c4];
+    y[i] = make_float4(fmaxf(fmaxf(q0.x, q1.x), fmaxf(q2.x, q3.x)), fmaxf(fmaxf(q0.y, q1.y), fmaxf(q2.y, q3.y)),
+                       fmaxf(fmaxf(q0.z, q1.z), fmaxf(q2.z, q3.z)), fmaxf(fmaxf(q0.w, q1.w), fmaxf(q2.w, q3.w)));
+  }
+}
+
+__global__ void maxpool2_f32_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, int nb, int h, int w, int c4,
+                                        int relu_mask, float4* __restrict__ dx) {
+  griddep_wait();
+  const int ho = h >> 1, wo = w >> 1;
+  const long long total = (long long)nb * ho * wo * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % c4);
+    long long r = i / c4;
+    const int ox = (int)(r % wo); r /= wo;
+    const int oy = (int)(r % ho);
+    const int n = (int)(r / ho);
+    const long long base = (((long long)n * h + 2 * oy) * w + 2 * ox) * c4 + v;
+    const long long offs[4] = {base, base + c4, base + (long long)w * c4, base + (long long)w * c4 + c4};
+    float q[4][4], g[4], o[4][4];
+    for (int k = 0; k < 4; k++) { const float4 t = x[offs[k]]; q[k][0] = t.x; q[k][1] = t.y; q[k][2] = t.z; q[k][3] = t.w; }
+    { const float4 t = dy[i]; g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w; }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int am = 0;
+#pragma unroll
+      for (int k = 1; k < 4; k++) if (q[k][j] > q[am][j]) am = k;
+#pragma unroll
+      for (int k = 0; k < 4; k++) o[k][j] = (k == am && (!relu_mask || q[k][j] > 0.f)) ? g[j] : 0.f;
+    }
+    for (int k = 0; k < 4; k++) dx[offs[k]] = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
+  }
+  if (((h & 1) || (w & 1)) && blockIdx.x == 0) {       // odd trailing row / column (floor pooling drops them)
+    for (long long i = threadIdx.x; i < (long long)nb * h * w * c4; i += blockDim.x) {
+      const long long pix = i / c4;
+      const int xx = (int)(pix % w), yy = (int)((pix / w) % h);
+      if (yy >= 2 * ho || xx >= 2 * wo) dx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
 // uint8 HWC [nb][h][w][3] -> fp32 NCHW [nb][3][h][w]
 __global__ void u8hwc_to_f32nchw_batch_kernel(const uint8_t* __restrict__ src, int nb, long long hw,
                                               float* __restrict__ dst) {
@@ -300,6 +436,58 @@ extern "C" int pesr_split16(const float* src, int64_t n, int32_t act, const void
              reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo));
   count_launch();
   PESR_CHECK_LAUNCH("split16");
+  return 0;
+}
+
+extern "C" int pesr_colmoments32(const float* a, const float* b, int64_t npix, int32_t c, double* sums, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(a && sums && npix > 0 && c > 0, "colmoments32: bad arguments");
+  long long bx = (npix + 8 * 32 - 1) / (8 * 32);
+  if (bx > 148 * 8) bx = 148 * 8;
+  dim3 grid((unsigned)bx, (unsigned)((c + 31) / 32));
+  launch_pdl(colmoments32_kernel, grid, 256, 0, stream, a, b, (long long)npix, c, sums);
+  count_launch();
+  PESR_CHECK_LAUNCH("colmoments32");
+  return 0;
+}
+
+extern "C" int pesr_affine_split(const float* a, const float* b, int64_t npix, int32_t c, const float* ka, const float* kb,
+                                 const float* kc, int32_t act, const void* mask_hi, const void* mask_lo, const float* mask32,
+                                 int32_t mask_mode, int32_t dtype, float* out32, void* hi, void* lo, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(a && (out32 || hi || lo) && npix > 0 && c > 0 && c % 4 == 0 && ((uintptr_t)a % 16) == 0,
+                 "affine_split: bad arguments (c %% 4 == 0, 16-byte alignment)");
+  const long long n4 = (long long)npix * (c / 4);
+  launch_pdl(affine_split_kernel, io_blocks(n4, 256), 256, 0, stream, reinterpret_cast<const float4*>(a),
+             reinterpret_cast<const float4*>(b), n4, c / 4, reinterpret_cast<const float4*>(ka), reinterpret_cast<const float4*>(kb),
+             reinterpret_cast<const float4*>(kc), act, reinterpret_cast<const uint2*>(mask_hi),
+             reinterpret_cast<const uint2*>(mask_lo), reinterpret_cast<const float4*>(mask32), mask_mode, dtype,
+             reinterpret_cast<float4*>(out32), reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo));
+  count_launch();
+  PESR_CHECK_LAUNCH("affine_split");
+  return 0;
+}
+
+extern "C" int pesr_maxpool2_f32_fwd(const float* x, int32_t nb, int32_t h, int32_t w, int32_t c, float* y, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(x && y && nb > 0 && h >= 2 && w >= 2 && c % 4 == 0, "maxpool2_f32_fwd: bad arguments");
+  const long long total = (long long)nb * (h / 2) * (w / 2) * (c / 4);
+  launch_pdl(maxpool2_f32_fwd_kernel, io_blocks(total, 256), 256, 0, stream, reinterpret_cast<const float4*>(x), nb, h, w, c / 4,
+             reinterpret_cast<float4*>(y));
+  count_launch();
+  PESR_CHECK_LAUNCH("maxpool2_f32_fwd");
+  return 0;
+}
+
+extern "C" int pesr_maxpool2_f32_bwd(const float* x, const float* dy, int32_t nb, int32_t h, int32_t w, int32_t c,
+                                     int32_t relu_mask, float* dx, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  PESR_CHECK_ARG(x && dy && dx && nb > 0 && h >= 2 && w >= 2 && c % 4 == 0, "maxpool2_f32_bwd: bad arguments");
+  const long long total = (long long)nb * (h / 2) * (w / 2) * (c / 4);
+  launch_pdl(maxpool2_f32_bwd_kernel, io_blocks(total, 256), 256, 0, stream, reinterpret_cast<const float4*>(x),
+             reinterpret_cast<const float4*>(dy), nb, h, w, c / 4, relu_mask, reinterpret_cast<float4*>(dx));
+  count_launch();
+  PESR_CHECK_LAUNCH("maxpool2_f32_bwd");
   return 0;
 }
 

@@ -54,6 +54,7 @@ def _parity_planes(t, nb, h, w, c):
 # depend on the warp scheduling order, so the deterministic separate pass stays the default.
 _FUSE_BN_STATS = os.environ.get("PESR_FUSED_BN", "0")
 _MERGE_S2_DGRAD = os.environ.get("PESR_NO_MERGED_S2_DGRAD") != "1"    # A/B knob: four parity classes in one launch
+_FC1_WGRAD_SKINNY = os.environ.get("PESR_FC1_WGRAD_SKINNY") == "1"     # A/B knob: CUDA-core Linear weight gradient (round 1)
 
 
 class DiscriminatorEngine:
@@ -71,6 +72,13 @@ class DiscriminatorEngine:
         self.last_flat = None
         self.lane = None           # SideLane for the weight-gradient kernels (see engine_g.SideLane)
         self.trace_hook = None     # callable(plan), called at the end of every forward (parity tests read the saved activations)
+        # data-parallel training (parallel.DataParallel): the Linear(73728 -> 1024) weight gradient is dz1^T x flat7, a
+        # rank-(rows) product.  Instead of all-reducing its 302 MB the ranks all-gather the two factors (19 MB at 8 GPUs)
+        # and every rank forms the averaged gradient itself.  fc1_gather(dz1, flat7) -> (dz1_all, flat7_all, event, world);
+        # grad_hook_skip(lo, hi) tells the wrapper that this range of the flat buffer is not to be reduced.
+        self.fc1_gather = None
+        self.grad_hook_skip = None
+        self.fc1_scratch = {}
 
     # ------------------------------------------------------------------ parameters
     def _ensure_packed(self, device):
@@ -366,6 +374,40 @@ class DiscriminatorEngine:
             return outs, (pl, _Release(pl), xs)
         return outs, None
 
+    # ------------------------------------------------------------------ Linear(kfc -> 1024) weight gradient
+    def _fc1_wgrad(self, dz1, flat7, kfc, grad, world=1, stream=None):
+        """grad[1024][kfc] = dz1^T x flat7 / world (dz1 fp32 [rows][1024], flat7 16-bit [rows][kfc]) on the tensor cores:
+        the split-K weight-gradient kernel with the rows as its "pixels" (64-row patches), dz1 as a 16-bit hi + lo pair
+        stacked along K (22 significant bits; flat7 is already 16-bit), written straight into `grad` with the range scale
+        and 1/world folded into the store.  302 MB are written once; nothing is read back."""
+        rows = dz1.shape[0]
+        if _FC1_WGRAD_SKINNY or kfc % 64 != 0 or grad.data_ptr() % 32 != 0 or self.dtype != torch.float16:
+            ops.linear_wgrad(dz1, flat7, rows, kfc, 1024, grad, mul=1.0 / world)
+            return
+        rp = (rows + 63) // 64 * 64
+        key = (rows, kfc)
+        sc = self.fc1_scratch.get(key)
+        if sc is None:
+            dev = dz1.device
+            sc = _Plan()
+            sc.a16 = torch.zeros(2 * rp, 1024, device=dev, dtype=self.dtype)       # [hi rows; lo rows], padding rows stay 0
+            sc.b16 = torch.zeros(2 * rp, kfc, device=dev, dtype=self.dtype)        # [flat7; flat7]
+            sc.scale = torch.zeros(4, device=dev, dtype=torch.float32)
+            self.fc1_scratch[key] = sc
+        ops.amax_scale(dz1, sc.scale, target=64.0)
+        ops.split16(dz1, sc.a16[:rows], sc.a16[rp:rp + rows], mul_dev=sc.scale[1:2])
+        sc.b16[:rows].copy_(flat7)
+        sc.b16[rp:rp + rows].copy_(flat7)
+        nimg = 2 * rp // 64
+        d = ops.make_wgrad_desc(dtype=self.dt, nb=nimg, h=4, w=16, a=sc.a16, a_c=1024, m_total=1024,
+                                b_srcs=[ops.nhwc_src(sc.b16, nimg, 4, 16, kfc)], n_total=kfc, taps=[(0, 0)], partials=grad,
+                                splits=1, out_mul=1.0 / world, out_div_dev=sc.scale[1:2])
+        splits = C.c_int32(0)
+        check(lib.pesr_conv_wgrad(C.byref(d), C.byref(splits), stream if stream is not None else
+                                  torch.cuda.current_stream().cuda_stream), "pesr_conv_wgrad")
+        if splits.value != 1:
+            raise RuntimeError("fc1 weight gradient: the kernel did not take the single-split path")
+
     # ------------------------------------------------------------------ backward
     def backward(self, state, dlogits, need_param_grads, need_input_grad):
         """dlogits: one tensor or a list with one [nb,1] gradient (or None) per call of the batched forward;
@@ -439,12 +481,21 @@ class DiscriminatorEngine:
         ops.linear_dgrad(dlogits, self.w2_16, nbb, 1024, 1, sc.dh1)
         dz1 = sc.dh1 * torch.where(h1_32 > 0, 1.0, 0.2)      # LeakyReLU'(h1), an nbb x 1024 tensor
         chained()
+        fc1_deferred = None
         if need_param_grads:
-            def fc1_grads(_st):
-                ops.linear_wgrad(dz1, flat7, nbb, pl.kfc, 1024, grads[fc1.weight])
+            if hook is not None and self.fc1_gather is not None and self.grad_hook_skip is not None:
+                # data parallel: gather the factors now (side stream), form the averaged gradient at the end of backward
                 torch.sum(dz1, dim=0, out=grads[fc1.bias])
-                mark(fc1.weight)
-            on_lane(fc1_grads)
+                mark(fc1.bias)
+                fc1_deferred = self.fc1_gather(dz1, flat7)
+                self.grad_hook_skip(off[fc1.weight], mark_hi[0])
+                mark_hi[0] = off[fc1.weight]
+            else:
+                def fc1_grads(st):
+                    self._fc1_wgrad(dz1, flat7, pl.kfc, grads[fc1.weight], stream=st)
+                    torch.sum(dz1, dim=0, out=grads[fc1.bias])
+                    mark(fc1.weight)
+                on_lane(fc1_grads)
         if sc.fc1_dgrad is not None:
             ops.amax_scale(dz1, sc.scale1, target=16.0)
             sc.dz1_16.copy_(dz1 * sc.scale1[1:2])
@@ -492,6 +543,10 @@ class DiscriminatorEngine:
                     _run_conv(dsc, stream)
         if lane is not None:
             lane.join()
+        if fc1_deferred is not None:
+            dz_all, f_all, ev, world = fc1_deferred
+            torch.cuda.current_stream().wait_event(ev)
+            self._fc1_wgrad(dz_all, f_all, pl.kfc, grads[fc1.weight], world=world)
         dxs = [None] * G
         if any(need_in[:gsel]):
             dx = torch.empty(nbb, 3, h, w, device=dev, dtype=torch.float32)

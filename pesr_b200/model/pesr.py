@@ -142,7 +142,7 @@ class Discriminator(nn.Module):
     flatten, Linear(512*(patch/4)^2 -> 1024), LeakyReLU, Linear(1024 -> 1).  ``opt`` keys: patch_size,
     spectral_norm (True raises NameError exactly as the reference does, model/basic.py:25)."""
 
-    def __init__(self, opt, dtype=torch.float16):
+    def __init__(self, opt, dtype=torch.float16, split_precision=False):
         nn.Module.__init__(self)
         act = nn.LeakyReLU(negative_slope=0.2, inplace=True)
         self.patch_size = opt['patch_size']
@@ -161,12 +161,18 @@ class Discriminator(nn.Module):
         side = self.patch_size * 4 // (2 ** ((depth + 1) // 2))
         self.classifier = nn.Sequential(nn.Linear(out_channels * side ** 2, 1024), act, nn.Linear(1024, 1))
         self._compute_dtype = dtype
+        # split_precision: fp16 hi+lo operands, three tensor-core passes per layer, fp32 activations (engine_d_split.py)
+        self._split = bool(split_precision)
         self._engine = None
 
     def engine(self):
         if self._engine is None:
-            from ..engine_d import DiscriminatorEngine
-            self._engine = DiscriminatorEngine(self, self._compute_dtype)
+            if self._split:
+                from ..engine_d_split import SplitDiscriminatorEngine
+                self._engine = SplitDiscriminatorEngine(self)
+            else:
+                from ..engine_d import DiscriminatorEngine
+                self._engine = DiscriminatorEngine(self, self._compute_dtype)
             self._engine.param_list = list(self.parameters())
         return self._engine
 

@@ -45,7 +45,7 @@ class _VGGFn(torch.autograd.Function):
 
 
 class VGG(nn.Module):
-    def __init__(self, pretrained=True, dtype=torch.float16):
+    def __init__(self, pretrained=True, dtype=torch.float16, split_precision=False):
         nn.Module.__init__(self)
         self.vgg = nn.Sequential(*_vgg19_features_35())   # conv5_4, before its ReLU (model/vgg.py:10)
         if pretrained:
@@ -67,12 +67,18 @@ class VGG(nn.Module):
         for p in self.parameters():
             p.requires_grad_(False)
         self._compute_dtype = dtype
+        # split_precision: fp16 hi+lo operands, three tensor-core passes per conv, fp32 activations (engine_v_split.py)
+        self._split = bool(split_precision)
         self._engine = None
 
     def engine(self):
         if self._engine is None:
-            from ..engine_v import VGGEngine
-            self._engine = VGGEngine(self, self._compute_dtype)
+            if self._split:
+                from ..engine_v_split import SplitVGGEngine
+                self._engine = SplitVGGEngine(self)
+            else:
+                from ..engine_v import VGGEngine
+                self._engine = VGGEngine(self, self._compute_dtype)
         return self._engine
 
     def forward(self, sr, hr):

@@ -137,7 +137,7 @@ def conv_igemm(desc):
 
 
 def make_wgrad_desc(*, dtype, nb, h, w, a, a_c, m_total, b_srcs, n_total, block_n=None, taps=TAPS_3X3, tap_src=None,
-                    partials, splits=0):
+                    partials, splits=0, out_mul=0.0, out_div_dev=None):
     d = WgradDesc()
     d.dtype = dtype
     d.nb, d.h, d.w = nb, h, w
@@ -157,6 +157,7 @@ def make_wgrad_desc(*, dtype, nb, h, w, a, a_c, m_total, b_srcs, n_total, block_
     d.splits = splits
     d.partials = _ptr(partials)
     d.partials_elems = partials.numel()
+    d.out_mul, d.out_div_dev = out_mul, _ptr(out_div_dev)
     return d
 
 
@@ -244,6 +245,28 @@ def split16(src32, hi, lo, act=ACT_NONE, mask_hi=None, mask_lo=None, mask_mode=0
     ref = hi if hi is not None else lo
     check(lib.pesr_split16(_ptr(src32), src32.numel(), act, _ptr(mask_hi), _ptr(mask_lo), mask_mode, mul, _ptr(mul_dev),
                            dt_code(ref.dtype), _ptr(hi), _ptr(lo), _stream()), "pesr_split16")
+
+
+def colmoments32(a32, npix, c, sums64, b32=None):
+    """sums64[0] += column sums of a32 [npix][c]; sums64[1] += column sums of a32 * (b32 or a32)   (fp64)."""
+    check(lib.pesr_colmoments32(_ptr(a32), _ptr(b32), npix, c, _ptr(sums64), _stream()), "pesr_colmoments32")
+
+
+def affine_split(a32, npix, c, out32=None, hi=None, lo=None, ka=None, kb=None, kc=None, b32=None, act=ACT_NONE,
+                 mask_hi=None, mask_lo=None, mask32=None, mask_mode=0):
+    """v = act(ka*a + kb*b + kc) * act'(mask), per-channel fp32 coefficient vectors; out32 = v, hi / lo = split of v."""
+    check(lib.pesr_affine_split(_ptr(a32), _ptr(b32), npix, c, _ptr(ka), _ptr(kb), _ptr(kc), act, _ptr(mask_hi),
+                                _ptr(mask_lo), _ptr(mask32), mask_mode, DT_F16, _ptr(out32), _ptr(hi), _ptr(lo), _stream()),
+          "pesr_affine_split")
+
+
+def maxpool2_f32_fwd(x32, nb, h, w, c, y32):
+    check(lib.pesr_maxpool2_f32_fwd(_ptr(x32), nb, h, w, c, _ptr(y32), _stream()), "pesr_maxpool2_f32_fwd")
+
+
+def maxpool2_f32_bwd(x32, dy32, nb, h, w, c, dx32, relu_mask=True):
+    check(lib.pesr_maxpool2_f32_bwd(_ptr(x32), _ptr(dy32), nb, h, w, c, 1 if relu_mask else 0, _ptr(dx32), _stream()),
+          "pesr_maxpool2_f32_bwd")
 
 
 def mean_shift(x, w9, b3, out):

@@ -11,8 +11,32 @@ buffer that completes from its end towards its start; each completed range is ha
 ``_on_range``, which launches ncclAllReduce(AVG) for every full bucket on a side stream while the
 remaining backward kernels keep the SMs busy.  The last (smallest) bucket is the only exposed one.
 """
+import os
+
 import torch
 import torch.distributed as dist
+
+
+_FC1_GATHER = os.environ.get("PESR_NO_FC1_GATHER") != "1"    # A/B knob: all-reduce the Linear weight gradient instead
+
+
+def _reserve_sms_for_nccl():
+    """The persistent tensor-core kernels size their grids to the whole machine with a static tile schedule: one SM taken
+    by a concurrently running NCCL CTA sends the CTA that wanted it to a second wave (tools/sm_hog_probe.py: +20 % per
+    step for ONE pinned SM).  So the kernels leave PESR_RESERVE_SMS SMs (default 4) to NCCL, and NCCL is told to use at
+    most that many CTAs (NCCL_MAX_CTAS, read when the communicator is created: set it before init_process_group, see
+    `nccl_env_defaults`)."""
+    if not torch.cuda.is_available():
+        return
+    from ._lib import lib
+    lib.pesr_set_option(5, int(os.environ.get("PESR_RESERVE_SMS", "4")))
+
+
+def nccl_env_defaults():
+    """Environment defaults for data-parallel training; call before torch.distributed.init_process_group."""
+    n = os.environ.get("PESR_RESERVE_SMS", "4")
+    os.environ.setdefault("NCCL_MAX_CTAS", n if int(n) > 0 else "32")
+    os.environ.setdefault("NCCL_MIN_CTAS", "1")
 
 
 class DataParallel(torch.nn.Module):
@@ -40,6 +64,10 @@ class DataParallel(torch.nn.Module):
                 # overlap the all-reduce instead of waiting for it inside backward
                 e.defer_finish = defer_finish
                 self._engine = e
+                if hasattr(e, "fc1_gather") and _FC1_GATHER:
+                    e.fc1_gather = self._gather_rows
+                    e.grad_hook_skip = self._skip_range
+            _reserve_sms_for_nccl()
 
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)
@@ -60,6 +88,32 @@ class DataParallel(torch.nn.Module):
             self._pending[0] = lo
         if self._pending[1] - self._pending[0] >= self.bucket_elems:
             self._flush()
+
+    def _skip_range(self, lo, hi):
+        """[lo, hi) of the flat buffer is filled by the engine with an already averaged gradient: reduce what is pending
+        above it and leave the range alone."""
+        self._flush()
+
+    def _gather_rows(self, dz1, flat7):
+        """all-gather the two factors of the Linear weight gradient on the communication stream.  Returns
+        (dz1 of all ranks [world*rows][1024], flat7 of all ranks, event, world)."""
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream()
+        w = self.world_size
+        dz1, flat7 = dz1.contiguous(), flat7.contiguous()
+        dz_all = torch.empty(w * dz1.shape[0], dz1.shape[1], device=dz1.device, dtype=dz1.dtype)
+        f_all = torch.empty(w * flat7.shape[0], flat7.shape[1], device=flat7.device, dtype=flat7.dtype)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._comm_stream.wait_event(ev)
+        with torch.cuda.stream(self._comm_stream):
+            dist.all_gather_into_tensor(dz_all, dz1, group=self.pg)
+            dist.all_gather_into_tensor(f_all, flat7, group=self.pg)
+            done = torch.cuda.Event()
+            done.record()
+        for t in (dz1, flat7, dz_all, f_all):
+            t.record_stream(self._comm_stream)
+        return dz_all, f_all, done, w
 
     def _flush(self):
         if self._pending is None:

@@ -281,3 +281,21 @@ def test_linear_on_the_implicit_gemm_kernel(nb, k, o):
                                       srcs=[ops.nhwc_src(dy16, 1, 1, nb, o)], wpacked=w16, out32=dx, ld_out32=k,
                                       b_mn_major=1))
     assert rel_l2(dx, dy16.double() @ w16.double()) < 1e-5
+
+
+@pytest.mark.parametrize("rows,kfc,world", [(32, 512 * 9, 1), (8, 512 * 16, 1), (96, 512 * 9, 3), (32, 73728, 1)])
+def test_linear_weight_gradient_on_the_tensor_cores(rows, kfc, world):
+    """DiscriminatorEngine._fc1_wgrad: dW = dz1^T x flat7 / world through the split-K weight-gradient kernel (rows as
+    pixels, dz1 as a 16-bit hi + lo pair stacked along K, scale folded into the store) against fp64; `world` > 1 is the
+    data-parallel form (the gathered factors of all ranks)."""
+    from pesr_b200.engine_d import DiscriminatorEngine
+    g = torch.Generator(device="cuda").manual_seed(11)
+    eng = DiscriminatorEngine(None)
+    dz1 = torch.randn(rows, 1024, device="cuda", generator=g) * 3e-6          # gradients far below the fp16 normal range
+    flat7 = torch.randn(rows, kfc, device="cuda", generator=g).half()
+    grad = torch.full((1024, kfc), float("nan"), device="cuda")
+    eng._fc1_wgrad(dz1, flat7, kfc, grad, world=world)
+    ref = dz1.double().t() @ flat7.double() / world
+    e = rel_l2(grad, ref)
+    print(f"fc1 wgrad on tensor cores rows={rows} kfc={kfc}: rel-L2 {e:.2e}")
+    assert e < 2e-6

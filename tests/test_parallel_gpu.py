@@ -95,6 +95,8 @@ def _worker(rank, port, out_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
+    from pesr_b200.parallel import nccl_env_defaults
+    nccl_env_defaults()
     dist.init_process_group("nccl", device_id=dev)
     try:
         G, D, V = _build(dev)

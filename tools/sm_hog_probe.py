@@ -25,14 +25,17 @@ for _ in range(5):
     steps.pretrain_step(G, opt, lr, hr)
 torch.cuda.synchronize()
 side = torch.cuda.Stream()
-for n in (0, 1, 4, 8, 16):
-    if n:
-        check(lib.pesr_debug_sm_hog(n, 400000, side.cuda_stream), "hog")      # 0.4 s
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10):
-        steps.pretrain_step(G, opt, lr, hr)
-    e1.record()
-    torch.cuda.synchronize()
-    print(f"{n:2d} SMs pinned: pretrain step {e0.elapsed_time(e1) / 10:.2f} ms", flush=True)
+# second column: the persistent kernels leave `reserve` SMs free (PESR_OPT_RESERVE_SMS, what parallel.DataParallel sets)
+for reserve in (0, 2, 4, 8):
+    lib.pesr_set_option(5, reserve)
+    for n in (0, 1, 2, 4, 8, 16):
+        if n:
+            check(lib.pesr_debug_sm_hog(n, 400000, side.cuda_stream), "hog")      # 0.4 s
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            steps.pretrain_step(G, opt, lr, hr)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"reserve {reserve}: {n:2d} SMs pinned: pretrain step {e0.elapsed_time(e1) / 10:.2f} ms", flush=True)
 

@@ -132,6 +132,8 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
     if world > 1:
+        from pesr_b200.parallel import nccl_env_defaults
+        nccl_env_defaults()
         dist.init_process_group('nccl', device_id=device)
     if rank == 0:
         print('Loading model using %d GPU(s)' % world)

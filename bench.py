@@ -215,6 +215,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         from pesr_b200.parallel import nccl_env_defaults
         nccl_env_defaults()       # NCCL_MAX_CTAS = the SMs the persistent kernels leave free (pesr_b200/parallel.py)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -297,9 +298,17 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    from pesr_b200 import parallel as _par
+    _par.TRACE_EVENTS.clear()
     ms_total = timed(lambda i: do_step(dev_lr[i % n_host], dev_hr[i % n_host]), args.steps)
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
+    ddp_exposed = None
+    if _par.TRACE_EVENTS:        # PESR_DDP_TRACE=1: time the compute stream spent waiting for NCCL, per step (rank 0)
+        ddp_exposed = {}
+        for lab, e0, e1 in _par.TRACE_EVENTS:
+            ddp_exposed[lab] = ddp_exposed.get(lab, 0.0) + e0.elapsed_time(e1) / args.steps
+        _par.TRACE_EVENTS.clear()
     # CPU time to ENQUEUE one step into an empty stream (no launch-queue back-pressure): GPU-bound if < ms_per_step
     host_enqueue_ms = None
     for i in range(3):
@@ -410,6 +419,11 @@ def run_b200(args):
     }
     if graph_note:
         line["graph_note"] = graph_note
+    if world > 1:
+        line["ddp"] = {"nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"), "reserved_sms": os.environ.get("PESR_RESERVE_SMS", "4"),
+                       "bucket_mb": os.environ.get("PESR_DDP_BUCKET_MB", "16"),
+                       "fc1_factor_gather": os.environ.get("PESR_NO_FC1_GATHER") != "1",
+                       "exposed_wait_ms_per_step": ddp_exposed}
     line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:

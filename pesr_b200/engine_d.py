@@ -67,6 +67,7 @@ class DiscriminatorEngine:
         self.device = None
         self.grad_hook = None
         self.grad_hook_finish = None
+        self.grad_hook_flush = None    # launches the all-reduce of the gradient ranges handed over so far (tail bucket)
         self.param_list = None
         self.defer_finish = False  # True: the data-parallel wrapper waits for the all-reduce itself (DataParallel.finish)
         self.last_flat = None
@@ -74,7 +75,7 @@ class DiscriminatorEngine:
         self.trace_hook = None     # callable(plan), called at the end of every forward (parity tests read the saved activations)
         # data-parallel training (parallel.DataParallel): the Linear(73728 -> 1024) weight gradient is dz1^T x flat7, a
         # rank-(rows) product.  Instead of all-reducing its 302 MB the ranks all-gather the two factors (19 MB at 8 GPUs)
-        # and every rank forms the averaged gradient itself.  fc1_gather(dz1, flat7) -> (dz1_all, flat7_all, event, world);
+        # and every rank forms the averaged gradient itself.  fc1_gather(dz1, flat7) -> (dz1_all, flat7_all, wait(), world);
         # grad_hook_skip(lo, hi) tells the wrapper that this range of the flat buffer is not to be reduced.
         self.fc1_gather = None
         self.grad_hook_skip = None
@@ -543,9 +544,11 @@ class DiscriminatorEngine:
                     _run_conv(dsc, stream)
         if lane is not None:
             lane.join()
+        if need_param_grads and hook is not None and self.grad_hook_flush is not None:
+            self.grad_hook_flush()          # the tail bucket goes on the wire now; DataParallel.finish() waits for it
         if fc1_deferred is not None:
-            dz_all, f_all, ev, world = fc1_deferred
-            torch.cuda.current_stream().wait_event(ev)
+            dz_all, f_all, wait, world = fc1_deferred
+            wait()
             self._fc1_wgrad(dz_all, f_all, pl.kfc, grads[fc1.weight], world=world)
         dxs = [None] * G
         if any(need_in[:gsel]):

@@ -238,6 +238,7 @@ class GeneratorEngine:
         self.device = None
         self.grad_hook = None      # callable(lo, hi, flat) -> None
         self.grad_hook_finish = None
+        self.grad_hook_flush = None    # launches the all-reduce of the gradient ranges handed over so far (tail bucket)
         self.param_list = None
         self.last_flat = None
         self.defer_finish = False  # True: the data-parallel wrapper waits for the all-reduce itself (DataParallel.finish)
@@ -609,6 +610,8 @@ class GeneratorEngine:
         mark(self.param_list[0])
         if mark_hi[0] != 0:
             raise AssertionError("generator backward: gradient ranges did not cover the flat buffer")
+        if hook is not None and self.grad_hook_flush is not None:
+            self.grad_hook_flush()
         if hook is not None and self.grad_hook_finish is not None and not self.defer_finish:
             # autograd may copy the gradient views when it accumulates them: the reduced values must be in place
             self.grad_hook_finish()

@@ -18,6 +18,22 @@ import torch.distributed as dist
 
 
 _FC1_GATHER = os.environ.get("PESR_NO_FC1_GATHER") != "1"    # A/B knob: all-reduce the Linear weight gradient instead
+_TRACE = os.environ.get("PESR_DDP_TRACE") == "1"             # event pairs around every wait of the compute stream
+TRACE_EVENTS = []                                            # (label, e0, e1): bench.py reports their sum per step
+
+
+def _traced_wait(label, events):
+    """Make the current stream wait for `events`; with PESR_DDP_TRACE=1 the exposed wait is measured on the device."""
+    cur = torch.cuda.current_stream()
+    if _TRACE:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+    for ev in events:
+        cur.wait_event(ev)
+    if _TRACE:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        TRACE_EVENTS.append((label, e0, e1))
 
 
 def _reserve_sms_for_nccl():
@@ -42,12 +58,15 @@ def nccl_env_defaults():
 class DataParallel(torch.nn.Module):
     """Wraps a pesr_b200 network; exposes ``.module`` like nn.DataParallel (train.py:303,309)."""
 
-    def __init__(self, module, process_group=None, bucket_mb=32, defer_finish=True):
+    def __init__(self, module, process_group=None, bucket_mb=None, defer_finish=True):
         super().__init__()
         self.module = module
         self.pg = process_group
         self.world_size = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        if bucket_mb is None:
+            bucket_mb = float(os.environ.get("PESR_DDP_BUCKET_MB", "16"))
         self.bucket_elems = int(bucket_mb * (1 << 20) // 4)
+        self.label = type(module).__name__
         self._pending = None      # (lo, hi, flat) accumulated, not yet reduced
         self._works = []
         self._comm_stream = None
@@ -59,6 +78,7 @@ class DataParallel(torch.nn.Module):
                 e = module.engine()
                 e.grad_hook = self._on_range
                 e.grad_hook_finish = self.finish
+                e.grad_hook_flush = self._flush     # end of backward: launch the tail bucket now, wait for it in finish()
                 # the step bodies (pesr_b200.steps) call finish() right before optimizer.step(): the kernels issued
                 # between backward and that call (e.g. the Generator-phase VGG forward while D's 321 MB are on the wire)
                 # overlap the all-reduce instead of waiting for it inside backward
@@ -113,7 +133,7 @@ class DataParallel(torch.nn.Module):
             done.record()
         for t in (dz1, flat7, dz_all, f_all):
             t.record_stream(self._comm_stream)
-        return dz_all, f_all, done, w
+        return dz_all, f_all, (lambda: _traced_wait(self.label + " factor gather", [done])), w
 
     def _flush(self):
         if self._pending is None:
@@ -140,13 +160,16 @@ class DataParallel(torch.nn.Module):
     def finish(self):
         """Make the current stream wait for every outstanding bucket (call before optimizer.step())."""
         self._flush()
+        evs = []
         for w in self._works:
             if isinstance(w, tuple):
                 work, flat, lo, hi = w
                 work.wait()
                 flat[lo:hi].div_(self.world_size)
             else:
-                torch.cuda.current_stream().wait_event(w)
+                evs.append(w)
+        if evs:
+            _traced_wait(self.label + " all-reduce", evs)
         had_work = bool(self._works)
         self._works = []
         if had_work:

@@ -53,3 +53,132 @@ def test_split_precision_generator_matches_free_running_fp64_oracle(opt, shape):
     assert med < 1e-3 and dx < 1e-3        # the north_star's gradient tolerance, free-running
     assert worst < 5e-3                    # the reference's own fp32 vs fp64: 8.7e-4 max
     assert med < 0.2 * res["fp16"][1]      # and it is the storage format that made the difference
+
+
+@pytest.mark.parametrize("patch,nb", [(16, 8), (48, 4)], ids=["patch16-b8", "headline-patch48-b4"])
+def test_split_precision_discriminator_matches_free_running_fp64_oracle(patch, nb):
+    """engine_d_split.py: logits, every parameter gradient, d/dx and the BatchNorm running statistics against the
+    FREE-RUNNING fp64 oracle (the 16-bit schedule can only be gated against the forward-pinned oracle: its own
+    free-running errors are printed beside)."""
+    from oracle import pesr_oracle as O
+    from pesr_b200.model import Discriminator
+    opt = {'patch_size': patch, 'spectral_norm': False}
+    sd = O.init_discriminator(opt, 0)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(nb, 3, 4 * patch, 4 * patch, generator=g) * 255
+    R = torch.randn(nb, 1, generator=g)
+    leaf = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+            for k, v in sd.items()}
+    xo = x.double().clone().requires_grad_(True)
+    stats = []
+    yo = O.discriminator_forward(leaf, xo, stats_out=stats)
+    names = [k for k in leaf if leaf[k].is_floating_point() and leaf[k].requires_grad]
+    og = torch.autograd.grad((yo * R.double()).sum(), [leaf[k] for k in names] + [xo])
+    ograds = dict(zip(names, og[:-1]))
+    res = {}
+    for name, kw in (("split", dict(split_precision=True)), ("fp16", {})):
+        D = Discriminator(opt, **kw)
+        D.load_state_dict(sd)
+        D = D.cuda().train()
+        xc = x.cuda().requires_grad_(True)
+        y = D(xc)
+        (y * R.cuda()).sum().backward()
+        errs = sorted((rel_l2(p.grad.cpu(), ograds[k]), k) for k, p in D.named_parameters())
+        res[name] = (rel_l2(y.detach().cpu(), yo.detach()), errs[len(errs) // 2][0], errs[-1][0], rel_l2(xc.grad.cpu(), og[-1]))
+        print(f"D patch {patch} nb {nb} [{name}] vs free-running fp64 oracle: logits {res[name][0]:.2e}, param-grad rel-L2 "
+              f"median {res[name][1]:.2e} max {res[name][2]:.2e} ({errs[-1][1]}), d/dx {res[name][3]:.2e}")
+        if name == "split":
+            st = D.state_dict()
+            for i in (0, 3, 7):
+                mean, var, n = stats[i]
+                assert rel_l2(st[f'features.{i}.1.running_mean'].cpu(), 0.1 * mean) < 1e-5
+                assert rel_l2(st[f'features.{i}.1.running_var'].cpu(), 0.9 + 0.1 * var * n / (n - 1)) < 1e-5
+                assert int(st[f'features.{i}.1.num_batches_tracked']) == 1
+            # the G phase (train.py:234-238): frozen parameters, input gradient only, D(sr) / D(hr) as one batched pair
+            for p in D.parameters():
+                p.requires_grad = False
+                p.grad = None
+            xa = x.cuda().requires_grad_(True)
+            ya, yb = D.forward_pair(xa, x.flip(0).cuda())
+            (ya * R.cuda()).sum().backward()
+            assert all(p.grad is None for p in D.parameters())
+            assert rel_l2(ya.detach().cpu(), yo.detach()) < 1e-4 and rel_l2(xa.grad.cpu(), og[-1]) < 1e-3
+    lg, med, worst, dx = res["split"]
+    assert lg < 1e-4                        # measured ~1e-6: 22-bit operands, fp32 activations, fp64 statistics
+    assert med < 1e-3 and dx < 1e-3         # the north_star's gradient tolerance, free-running
+    assert worst < 5e-3
+    assert med < 0.2 * res["fp16"][1]
+
+
+def test_split_precision_vgg_matches_free_running_fp64_oracle():
+    from oracle import pesr_oracle as O
+    from pesr_b200 import losses
+    from pesr_b200.model import VGG
+    sd = O.init_vgg(2)
+    g = torch.Generator().manual_seed(3)
+    sr = torch.rand(2, 3, 64, 64, generator=g) * 255
+    hr = torch.rand(2, 3, 64, 64, generator=g) * 255
+    so = sr.double().clone().requires_grad_(True)
+    of_sr, of_hr = O.vgg_forward({k: v.double() for k, v in sd.items()}, so, hr.double())
+    ol = O.mse_loss(of_sr, of_hr)
+    og, = torch.autograd.grad(ol, so)
+    res = {}
+    for name, kw in (("split", dict(split_precision=True)), ("fp16", {})):
+        V = VGG(pretrained=False, **kw)
+        V.load_state_dict(sd)
+        V = V.cuda()
+        src = sr.cuda().requires_grad_(True)
+        f_sr, f_hr = V(src, hr.cuda())
+        assert f_sr.shape == (2, 512, 4, 4) and f_sr.requires_grad and not f_hr.requires_grad
+        loss = losses.mse_loss(f_sr, f_hr)
+        loss.backward()
+        res[name] = (rel_l2(f_sr.detach().cpu(), of_sr.detach()), rel_l2(f_hr.cpu(), of_hr),
+                     abs(float(loss) - float(ol)) / float(ol), rel_l2(src.grad.cpu(), og))
+        print(f"VGG [{name}] vs free-running fp64 oracle: f_sr {res[name][0]:.2e} f_hr {res[name][1]:.2e} "
+              f"loss {res[name][2]:.2e} d(loss)/d(sr) {res[name][3]:.2e}")
+        with torch.no_grad():
+            g_sr, g_hr = V(sr.cuda(), hr.cuda())
+            assert rel_l2(g_sr.cpu(), f_sr.detach().cpu()) < 1e-6
+    f1, f2, le, dsr = res["split"]
+    assert f1 < 1e-4 and f2 < 1e-4 and le < 1e-4
+    assert dsr < 1e-3
+    assert dsr < 0.2 * res["fp16"][3]
+
+
+def test_split_precision_gan_step_matches_free_running_fp64_oracle():
+    """train.py:202-259 with all three networks on the split-precision schedules: the five losses, every Generator and
+    Discriminator gradient and D's Adam step against the FREE-RUNNING fp64 oracle (no pinning, no quantisation)."""
+    from oracle import pesr_oracle as O
+    from pesr_b200 import steps
+    from pesr_b200.model import VGG, Discriminator, Generator
+    from pesr_b200.optim import Adam
+    opt = {'depth': 2, 'num_channels': 64, 'res_scale': 0.1, 'patch_size': 12, 'spectral_norm': False}
+    nb, patch, lrate = 4, 12, 5e-5
+    g_sd, d_sd, v_sd = O.init_generator(opt, 0), O.init_discriminator(opt, 1), O.init_vgg(2)
+    gen = torch.Generator().manual_seed(3)
+    lr = torch.rand(nb, 3, patch, patch, generator=gen) * 255
+    hr = torch.rand(nb, 3, patch * 4, patch * 4, generator=gen) * 255
+    free = O.gan_step(g_sd, d_sd, v_sd, lr, hr, opt, lr_rate=lrate, dtype=torch.float64)
+    keys = ['l1', 'vgg', 'g_loss', 'tv', 'd_loss']
+    res = {}
+    for name, kw in (("split", dict(split_precision=True)), ("fp16", {})):
+        G, D, V = Generator(opt, **kw), Discriminator(opt, **kw), VGG(pretrained=False, **kw)
+        G.load_state_dict(g_sd), D.load_state_dict(d_sd), V.load_state_dict(v_sd)
+        G, D, V = G.cuda(), D.cuda(), V.cuda()
+        optG, optD = Adam(G.parameters(), lr=lrate), Adam(D.parameters(), lr=lrate)
+        cfg = dict(steps.DEFAULT_GAN_CFG)
+        cfg['target_real'] = torch.ones(nb, 1, device="cuda")
+        cfg['target_fake'] = torch.zeros(nb, 1, device="cuda")
+        got = steps.gan_step(G, D, V, optG, optD, lr.cuda(), hr.cuda(), cfg).cpu()
+        d_grads = {k: p.grad.cpu() for k, p in D.named_parameters()}       # left by the D phase (train.py:213-216)
+        rl = [abs(float(got[i]) - float(free[k])) / max(abs(float(free[k])), 1e-30) for i, k in enumerate(keys)]
+        ge = sorted(rel_l2(p.grad.cpu(), free['g_grads'][k]) for k, p in G.named_parameters())
+        de = sorted(rel_l2(d_grads[k], free['d_grads'][k]) for k in d_grads)
+        res[name] = (max(rl[1:]), ge[len(ge) // 2], ge[-1], de[len(de) // 2], de[-1])
+        print(f"GAN step [{name}] vs free-running fp64 oracle: losses {['%.1e' % v for v in rl]}; G grads rel-L2 median "
+              f"{res[name][1]:.2e} max {res[name][2]:.2e}; D grads median {res[name][3]:.2e} max {res[name][4]:.2e}")
+    le, gmed, gmax, dmed, dmax = res["split"]
+    assert le < 1e-4
+    assert gmed < 1e-3 and dmed < 1e-3          # the north_star's tolerance for gradients, free-running, whole step
+    assert gmax < 5e-3 and dmax < 5e-3
+    assert gmed < 0.2 * res["fp16"][1] and dmed < 0.2 * res["fp16"][3]

@@ -421,7 +421,7 @@ def run_b200(args):
         line["graph_note"] = graph_note
     if world > 1:
         line["ddp"] = {"nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"), "reserved_sms": os.environ.get("PESR_RESERVE_SMS", "4"),
-                       "bucket_mb": os.environ.get("PESR_DDP_BUCKET_MB", "16"),
+                       "bucket_mb": os.environ.get("PESR_DDP_BUCKET_MB", "8"),
                        "fc1_factor_gather": os.environ.get("PESR_NO_FC1_GATHER") != "1",
                        "exposed_wait_ms_per_step": ddp_exposed}
     line.update(extras)

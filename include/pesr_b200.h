@@ -271,6 +271,22 @@ int pesr_maxpool2_f32_fwd(const float* x, int32_t nb, int32_t h, int32_t w, int3
 int pesr_maxpool2_f32_bwd(const float* x, const float* dy, int32_t nb, int32_t h, int32_t w, int32_t c, int32_t relu_mask,
                           float* dx, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Gradient all-reduce (average) over NVLink / NVSwitch peer memory: the reduction nn.DataParallel performs on GPU 0
+ * (train.py:114-118), as a two-shot kernel on `ctas` CTAs over a range of a SYMMETRIC fp32 buffer (the same allocation
+ * mapped into every process of the node).  peer_ptrs[world]: this process's addresses of every rank's buffer (host
+ * array); multicast_ptr != 0: NVSwitch multicast address of the buffer (multimem.ld_reduce / multimem.st are used and
+ * peer_ptrs may be NULL).  Element range [offset_elems, offset_elems + count) (multiples of 4) ends up holding
+ * scale * sum over ranks on every rank, bit-identical.  pad_ptrs[world]: every rank's signal pad (>= 1280 zero-initialised
+ * bytes of symmetric memory); the kernel itself makes the ranks meet before and after the reduction, with `epoch` (a
+ * counter the caller increments per call, identical on all ranks) as the flag value.  pad_ptrs NULL: the caller orders
+ * the ranks.  One launch, one thread-block cluster of `ctas` (<= 8) CTAs.
+ * ------------------------------------------------------------------------------------------------ */
+#define PESR_MAX_PEERS 16
+int pesr_allreduce_p2p(const uint64_t* peer_ptrs, const uint64_t* pad_ptrs, int32_t world, int32_t rank,
+                       uint64_t multicast_ptr, int64_t offset_elems, int64_t count, float scale, int32_t ctas,
+                       uint32_t epoch, void* stream);
+
 /* MeanShift as a stand-alone op (model/basic.py:9-17): out[n][o][p] = sum_i w9[o*3+i] * x[n][i][p] + b3[o] on
  * [nb][3][hw] fp32 tensors (b3 may be NULL). */
 int pesr_mean_shift(const float* x, int32_t nb, int64_t hw, const float* w9, const float* b3, float* out, void* stream);

@@ -111,6 +111,8 @@ SIGNATURES = {
     "pesr_u8hwc_to_f32nchw_batch": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "pesr_col2im3_tiled": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "pesr_mean_shift": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "pesr_allreduce_p2p": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _i32, _i32, C.c_uint64, _i64, _i64, _f32,
+                                     _i32, C.c_uint32, _vp]),
     "pesr_split16": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _f32, _vp, _i32, _vp, _vp, _vp]),
     "pesr_colmoments32": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "pesr_affine_split": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),

@@ -68,6 +68,7 @@ class DiscriminatorEngine:
         self.grad_hook = None
         self.grad_hook_finish = None
         self.grad_hook_flush = None    # launches the all-reduce of the gradient ranges handed over so far (tail bucket)
+        self.flat_alloc = None         # allocator of the flat gradient buffer (FlatGrads.alloc)
         self.param_list = None
         self.defer_finish = False  # True: the data-parallel wrapper waits for the all-reduce itself (DataParallel.finish)
         self.last_flat = None
@@ -111,7 +112,7 @@ class DiscriminatorEngine:
         self.c0_key = None
         self.scale_ws = torch.zeros(4, device=device, dtype=torch.float32)
         self.bn_ws = torch.zeros(2 * 512, device=device, dtype=torch.float64)
-        self.flat_grads = FlatGrads(self.param_list)
+        self.flat_grads = FlatGrads(self.param_list, alloc=self.flat_alloc)
         self.offsets, self.flat_numel = self.flat_grads.offsets, self.flat_grads.numel
 
     def invalidate_packs(self):

@@ -137,8 +137,10 @@ class FlatGrads:
     optimiser step (gradient accumulation, two separate D calls) gets a fresh buffer, as autograd may still hold views
     of the first one in its input buffers."""
 
-    def __init__(self, param_list):
+    def __init__(self, param_list, alloc=None):
         self.params = param_list
+        self.alloc = alloc        # optional allocator of the persistent buffer: alloc(numel, device) (parallel.DataParallel
+        #                           places it in symmetric memory for the NVLink peer-memory all-reduce)
         self.offsets, off = {}, 0
         for p in param_list:
             self.offsets[p] = off
@@ -150,7 +152,8 @@ class FlatGrads:
     def get(self, device):
         version = self.params[0]._version
         if self.buf is None or self.buf.device != device:
-            self.buf = torch.empty(self.numel, device=device, dtype=torch.float32)
+            self.buf = self.alloc(self.numel, device) if self.alloc is not None else \
+                torch.empty(self.numel, device=device, dtype=torch.float32)
             self.handed_at = None
         if self.handed_at == version:
             return torch.empty(self.numel, device=device, dtype=torch.float32)
@@ -239,6 +242,7 @@ class GeneratorEngine:
         self.grad_hook = None      # callable(lo, hi, flat) -> None
         self.grad_hook_finish = None
         self.grad_hook_flush = None    # launches the all-reduce of the gradient ranges handed over so far (tail bucket)
+        self.flat_alloc = None         # allocator of the flat gradient buffer (FlatGrads.alloc)
         self.param_list = None
         self.last_flat = None
         self.defer_finish = False  # True: the data-parallel wrapper waits for the all-reduce itself (DataParallel.finish)
@@ -290,7 +294,7 @@ class GeneratorEngine:
         self.bias_up0 = torch.empty(4 * C_, device=device, dtype=torch.float32)
         self.bias_up2 = torch.empty(4 * C_, device=device, dtype=torch.float32)
         # flat gradient layout: parameter order, each tensor starting on a 16-byte boundary
-        self.flat_grads = FlatGrads(self.param_list)
+        self.flat_grads = FlatGrads(self.param_list, alloc=self.flat_alloc)
         self.offsets, self.flat_numel = self.flat_grads.offsets, self.flat_grads.numel
 
     # ------------------------------------------------------------------ plans

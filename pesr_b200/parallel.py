@@ -55,6 +55,53 @@ def nccl_env_defaults():
     os.environ.setdefault("NCCL_MIN_CTAS", "1")
 
 
+_P2P = os.environ.get("PESR_DDP_NCCL_ONLY") != "1"       # A/B knob: reduce through NCCL instead of the peer-memory kernel
+_SYMM_NCCL = os.environ.get("PESR_DDP_SYMM_NCCL") == "1"  # A/B knob: symmetric buffer, but reduced by NCCL
+_P2P_CTAS = int(os.environ.get("PESR_DDP_CTAS", "0"))    # CTAs of the peer-memory all-reduce (0: the reserved SMs)
+
+
+class _SymmetricFlat:
+    """The flat gradient buffer of one network in symmetric memory (torch.distributed._symmetric_memory: one allocation per
+    rank, every rank's allocation mapped into every process, NVSwitch multicast address when the fabric has one) and the
+    hand-written all-reduce over it (csrc/comm_ops.cu)."""
+
+    def __init__(self, numel, device, group, world, rank):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+        self.tensor = symm_mem.empty(numel, dtype=torch.float32, device=device)
+        name = group.group_name if group is not None else dist.group.WORLD.group_name
+        self.hdl = symm_mem.rendezvous(self.tensor, name)
+        self.world, self.rank = world, rank
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.ptrs = (C.c_uint64 * world)(*ptrs)
+        self.pads = None
+        if int(self.hdl.signal_pad_size) >= 1280 and os.environ.get("PESR_DDP_TORCH_BARRIER") != "1":
+            self.pads = (C.c_uint64 * world)(*[int(p) for p in self.hdl.signal_pad_ptrs])
+        self.epoch = 0
+        mc = int(self.hdl.multicast_ptr or 0)         # 0 when the fabric has no multicast (then: peer loads / stores)
+        self.multicast = mc if os.environ.get("PESR_DDP_NO_MULTIMEM") != "1" else 0
+        self.ctas = _P2P_CTAS or max(1, int(os.environ.get("PESR_RESERVE_SMS", "4")))
+
+    def all_reduce_avg(self, lo, hi, stream):
+        """Average [lo, hi) of the buffer over the ranks, in place, on `stream` (the current stream)."""
+        from ._lib import check, lib
+        self.epoch = (self.epoch + 1) & 0x7FFFFFFF
+        if self.pads is None:
+            self.hdl.barrier(channel=0)      # every rank's backward has produced the range
+        check(lib.pesr_allreduce_p2p(self.ptrs, self.pads, self.world, self.rank, self.multicast, lo, hi - lo,
+                                     1.0 / self.world, self.ctas, self.epoch, stream.cuda_stream), "pesr_allreduce_p2p")
+        if self.pads is None:
+            self.hdl.barrier(channel=0)      # every owner has stored its slice everywhere
+
+
+def _new_comm_stream():
+    """High priority: when an SM frees up, the block scheduler places NCCL's pending CTAs before the next convolution's."""
+    if os.environ.get("PESR_DDP_LOW_PRIORITY") == "1":       # A/B knob
+        return torch.cuda.Stream()
+    return torch.cuda.Stream(priority=-1)
+
+
 class DataParallel(torch.nn.Module):
     """Wraps a pesr_b200 network; exposes ``.module`` like nn.DataParallel (train.py:303,309)."""
 
@@ -64,13 +111,15 @@ class DataParallel(torch.nn.Module):
         self.pg = process_group
         self.world_size = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         if bucket_mb is None:
-            bucket_mb = float(os.environ.get("PESR_DDP_BUCKET_MB", "16"))
+            bucket_mb = float(os.environ.get("PESR_DDP_BUCKET_MB", "8"))
         self.bucket_elems = int(bucket_mb * (1 << 20) // 4)
         self.label = type(module).__name__
         self._pending = None      # (lo, hi, flat) accumulated, not yet reduced
         self._works = []
         self._comm_stream = None
         self._engine = None
+        self._symm = None         # _SymmetricFlat once the engine has asked for its flat buffer
+        self._symm_failed = None
         if self.world_size > 1:
             self._broadcast_parameters()
             eng = getattr(module, "engine", None)
@@ -84,6 +133,10 @@ class DataParallel(torch.nn.Module):
                 # overlap the all-reduce instead of waiting for it inside backward
                 e.defer_finish = defer_finish
                 self._engine = e
+                if _P2P and torch.cuda.is_available() and hasattr(e, "flat_alloc"):
+                    e.flat_alloc = self._alloc_flat
+                    if getattr(e, "flat_grads", None) is not None:      # engine already built: re-home its buffer
+                        e.flat_grads.alloc, e.flat_grads.buf = self._alloc_flat, None
                 if hasattr(e, "fc1_gather") and _FC1_GATHER:
                     e.fc1_gather = self._gather_rows
                     e.grad_hook_skip = self._skip_range
@@ -109,6 +162,21 @@ class DataParallel(torch.nn.Module):
         if self._pending[1] - self._pending[0] >= self.bucket_elems:
             self._flush()
 
+    def _alloc_flat(self, numel, device):
+        """FlatGrads.alloc: the persistent gradient buffer lives in symmetric memory (a collective call: every rank reaches
+        its first backward of this network at the same point of the step).  Falls back to an ordinary tensor + NCCL."""
+        if self._symm is None and self._symm_failed is None:
+            try:
+                rank = dist.get_rank(self.pg)
+                self._symm = _SymmetricFlat(numel, device, self.pg, self.world_size, rank)
+            except Exception as e:        # no symmetric memory on this system: NCCL all-reduce
+                self._symm_failed = f"{type(e).__name__}: {str(e)[:200]}"
+                print(f"[pesr_b200.parallel] symmetric memory unavailable ({self._symm_failed}); using NCCL all-reduce",
+                      flush=True)
+        if self._symm is not None and self._symm.tensor.numel() == numel:
+            return self._symm.tensor
+        return torch.empty(numel, device=device, dtype=torch.float32)
+
     def _skip_range(self, lo, hi):
         """[lo, hi) of the flat buffer is filled by the engine with an already averaged gradient: reduce what is pending
         above it and leave the range alone."""
@@ -118,7 +186,7 @@ class DataParallel(torch.nn.Module):
         """all-gather the two factors of the Linear weight gradient on the communication stream.  Returns
         (dz1 of all ranks [world*rows][1024], flat7 of all ranks, event, world)."""
         if self._comm_stream is None:
-            self._comm_stream = torch.cuda.Stream()
+            self._comm_stream = _new_comm_stream()
         w = self.world_size
         dz1, flat7 = dz1.contiguous(), flat7.contiguous()
         dz_all = torch.empty(w * dz1.shape[0], dz1.shape[1], device=dz1.device, dtype=dz1.dtype)
@@ -144,12 +212,15 @@ class DataParallel(torch.nn.Module):
             return
         if flat.is_cuda:
             if self._comm_stream is None:
-                self._comm_stream = torch.cuda.Stream()
+                self._comm_stream = _new_comm_stream()
             ev = torch.cuda.Event()
             ev.record()
             self._comm_stream.wait_event(ev)
             with torch.cuda.stream(self._comm_stream):
-                dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.AVG, group=self.pg)
+                if self._symm is not None and flat.data_ptr() == self._symm.tensor.data_ptr() and not _SYMM_NCCL:
+                    self._symm.all_reduce_avg(lo, hi, self._comm_stream)
+                else:
+                    dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.AVG, group=self.pg)
                 done = torch.cuda.Event()
                 done.record()
             self._works.append(done)

@@ -87,7 +87,8 @@ def _reference(dev):
     return [t.cpu() for t in d_mean], [t.cpu() for t in g_mean], float(d_loss)
 
 
-def _worker(rank, port, out_path):
+def _worker(rank, port, out_path, env):
+    os.environ.update(env)
     import torch.distributed as dist
     from pesr_b200 import steps
     from pesr_b200.optim import Adam
@@ -105,7 +106,9 @@ def _worker(rank, port, out_path):
         lr, hr = _shards()
         out = steps.gan_step(Gw, Dw, V, optG, optD, lr[rank].to(dev), hr[rank].to(dev), _cfg(dev), ddp_g=Gw, ddp_d=Dw)
         torch.cuda.synchronize()
-        res = dict(d=[p.grad.cpu() for p in D.parameters()], g=[p.grad.cpu() for p in G.parameters()], losses=out.cpu())
+        res = dict(d=[p.grad.cpu() for p in D.parameters()], g=[p.grad.cpu() for p in G.parameters()], losses=out.cpu(),
+                   path=("peer-memory kernel" + (" (multimem)" if Gw._symm.multicast else " (peer loads / stores)"))
+                   if Gw._symm is not None else f"NCCL ({Gw._symm_failed})")
         if rank == 0:
             res['ref'] = _reference(dev)
         torch.save(res, f"{out_path}.{rank}")
@@ -114,12 +117,15 @@ def _worker(rank, port, out_path):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_two_rank_gan_step_gradients_are_the_shard_mean(tmp_path):
+@pytest.mark.parametrize("env", [{}, {"PESR_DDP_NO_MULTIMEM": "1"}, {"PESR_DDP_NCCL_ONLY": "1", "PESR_NO_FC1_GATHER": "1"}],
+                         ids=["peer-memory-all-reduce", "peer-loads-stores", "nccl-all-reduce"])
+def test_two_rank_gan_step_gradients_are_the_shard_mean(tmp_path, env):
     import torch.multiprocessing as mp
     from conftest import rel_l2
     out_path = str(tmp_path / "res")
-    mp.spawn(_worker, args=(_free_port(), out_path), nprocs=2, join=True)
+    mp.spawn(_worker, args=(_free_port(), out_path, env), nprocs=2, join=True)
     r0, r1 = torch.load(out_path + ".0"), torch.load(out_path + ".1")
+    print("gradient reduction path:", r0['path'])
     d_ref, g_ref, d_loss_ref = r0['ref']
     # both ranks hold the same reduced gradients
     for a, b in zip(r0['d'] + r0['g'], r1['d'] + r1['g']):

@@ -1,0 +1,23 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run2() {  # name, env...
+  name=$1; shift
+  env "$@" PESR_DDP_TRACE=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) bench.py --gpus 2 --steps 40 --warmup 3 > gpurun_out/r2r_$name.json 2> gpurun_out/r2r_$name.err; echo "$name exit=$?"
+  python - <<PY
+import json
+try:
+    d=json.loads([l for l in open('gpurun_out/r2r_$name.json') if l.startswith('{')][-1])
+    print('$name: N=2 ms/step', round(d['ms_per_step'],3), 'sustained', round(d['sustained']['ms_per_step'],3), 'host', round(d['host_enqueue_ms_per_step'],2), {k: round(v,3) for k,v in d['ddp']['exposed_wait_ms_per_step'].items()})
+except Exception as e: print('$name failed', e)
+PY
+  grep -v "OMP_NUM\|^\*\*\*" gpurun_out/r2r_$name.err | tail -3
+}
+{
+run2 b8_hi
+run2 b4_hi PESR_DDP_BUCKET_MB=4
+run2 b16_hi PESR_DDP_BUCKET_MB=16
+run2 b8_lo PESR_DDP_LOW_PRIORITY=1
+run2 b8_hi_r6 PESR_RESERVE_SMS=4 NCCL_MAX_CTAS=6
+timeout 300 python tools/phase_times.py gan 20 | head -3
+} > gpurun_out/r2r.log 2>&1
+cat gpurun_out/r2r.log | cut -c1-400

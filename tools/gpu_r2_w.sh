@@ -1,0 +1,21 @@
+#!/bin/bash
+mkdir -p gpurun_out
+N=${1:-2}
+run() {  # name, env...
+  name=$1; shift
+  env "$@" PESR_DDP_TRACE=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) bench.py --gpus $N --steps 40 --warmup 3 > gpurun_out/r2w_${N}_$name.json 2> gpurun_out/r2w_${N}_$name.err; echo "$name exit=$?"
+  python - <<PY
+import json
+try:
+    d=json.loads([l for l in open('gpurun_out/r2w_${N}_$name.json') if l.startswith('{')][-1])
+    print('$name: N=$N ms/step', round(d['ms_per_step'],3), 'value', round(d['value'],1), 'sustained', round(d['sustained']['ms_per_step'],3), 'host', round(d['host_enqueue_ms_per_step'],2), {k: round(v,3) for k,v in d['ddp']['exposed_wait_ms_per_step'].items()})
+except Exception as e: print('$name failed', e)
+PY
+  grep -v "OMP_NUM\|^\*\*\*" gpurun_out/r2w_${N}_$name.err | tail -5 | cut -c1-300
+}
+{
+if [ "$N" = 2 ]; then timeout 600 python -m pytest tests/test_parallel_gpu.py -q -m gpu -s -p no:cacheprovider 2>&1 | grep -v "^$" | tail -12; fi
+run p2p
+if [ "$N" = 2 ]; then run p2p_nomm PESR_DDP_NO_MULTIMEM=1; run nccl PESR_DDP_NCCL_ONLY=1; fi
+} > gpurun_out/r2w_$N.log 2>&1
+cat gpurun_out/r2w_$N.log | cut -c1-400

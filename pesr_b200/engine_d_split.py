@@ -16,6 +16,11 @@ from .engine_split import HL, SplitOps, SplitWeight
 from .ops import ACT_LRELU
 
 
+import os
+
+_WSCALE = float(os.environ.get("PESR_SPLIT_WSCALE", "256"))     # power of two applied to the conv weight operands (engine_split)
+
+
 class _SplitLinearWeight:
     """hi / lo 16-bit copies of a Linear weight [out][in], refreshed when the parameter changes."""
 
@@ -60,10 +65,11 @@ class SplitDiscriminatorEngine(SplitOps):
             return
         self.sentinel, self.device = sentinel, device
         w0 = d.features[0][0].weight
-        pk = {"c0_f": SplitWeight(w0, 4, pad_to=64), "c0_d": SplitWeight(w0, 6, pad_to=32)}
+        ws = _WSCALE
+        pk = {"c0_f": SplitWeight(w0, 4, pad_to=64, scale=ws), "c0_d": SplitWeight(w0, 6, pad_to=32, scale=ws)}
         for i in range(1, 8):
             w = d.features[i][0].weight
-            pk[f"c{i}_f"], pk[f"c{i}_d"] = SplitWeight(w, 0), SplitWeight(w, 1)
+            pk[f"c{i}_f"], pk[f"c{i}_d"] = SplitWeight(w, 0, scale=ws), SplitWeight(w, 1, scale=ws)
         self.packed = pk
         self.fc1, self.fc2 = _SplitLinearWeight(d.classifier[0].weight), _SplitLinearWeight(d.classifier[2].weight)
         self.wg = torch.empty(3 * max(9 * 512 * 512 * 4, 148 * 128 * 64), device=device, dtype=torch.float32)
@@ -113,12 +119,12 @@ class SplitDiscriminatorEngine(SplitOps):
             hh, ww = dims[i]
             y = e32(nt * hh * ww, co)
             if i == 0:
-                self._conv3(cur, "c0_f", nt, hh, ww, 64, co, y, taps=[(0, 0)])
+                self._conv3(cur, "c0_f", nt, hh, ww, 64, co, y, taps=[(0, 0)], alpha=1.0 / _WSCALE)
             elif s == 1:
-                self._conv3(cur, f"c{i}_f", nt, hh, ww, ci, co, y)
+                self._conv3(cur, f"c{i}_f", nt, hh, ww, ci, co, y, alpha=1.0 / _WSCALE)
             else:
                 hi_, wi_ = dims[i - 1]
-                self._conv3(cur, f"c{i}_f", nt, hh, ww, ci, co, y, taps=taps2, tap_src=srcs2, tap_widx=widx2,
+                self._conv3(cur, f"c{i}_f", nt, hh, ww, ci, co, y, alpha=1.0 / _WSCALE, taps=taps2, tap_src=srcs2, tap_widx=widx2,
                             srcs_fn=lambda t, hi_=hi_, wi_=wi_, ci=ci: _parity_planes(t, nt, hi_, wi_, ci))
             bn = d.features[i][1]
             npix = nb * hh * ww
@@ -228,13 +234,14 @@ class SplitDiscriminatorEngine(SplitOps):
         ops.linear_dgrad(dz1, w1h, nbb, kfc, 1024, dflat)
         ops.linear_dgrad(dz1, w1l, nbb, kfc, 1024, dflat_b)
         dflat += dflat_b
-        # every 16-bit gradient operand below carries `scale` (a power of two chosen from max|dflat|)
+        # every 16-bit gradient operand below carries `scale`, a power of two chosen from max|gradient| and RENEWED at
+        # every layer: the lo halves are 2^-11 of the hi halves, so a tensor whose values sit far below the fp16 normal
+        # range would silently lose them (gradients shrink and grow by the BatchNorm factors gamma * rstd layer by layer)
         ops.amax_scale(dflat, self.scale_ws, target=16.0)
-        scale = self.scale_ws[1:2]
+        scale = self.scale_ws[1:2].clone()
         h7, w7 = dims[7]
         dA = (dflat * scale).view(nbb, 512, h7 * w7).permute(0, 2, 1).reshape(nbb * h7 * w7, 512).contiguous()
         taps2, srcs2, _ = _s2_taps()
-        inv_scale = (1.0 / scale.double())
         for i in range(7, -1, -1):
             ci, co, s = D_LAYERS[i]
             hh, ww = dims[i]
@@ -263,6 +270,7 @@ class SplitDiscriminatorEngine(SplitOps):
                 kc = (-gr * s1 / npix + gr * rstd * mean * dgamma / npix).float()
                 ops.affine_split(dZ[rows], npix, co, b32=y[rows], ka=ka, kb=kb, kc=kc, hi=dY.hi[rows], lo=dY.lo[rows])
             if need_param_grads:
+                inv_scale = 1.0 / scale.double()
                 grads[bn.weight].copy_(dgam * inv_scale)
                 grads[bn.bias].copy_(dbet * inv_scale)
                 if i == 0:
@@ -280,7 +288,7 @@ class SplitDiscriminatorEngine(SplitOps):
             hi_, wi_ = dims[i - 1]
             dA = e32(nbb * hi_ * wi_, ci)
             if s == 1:
-                self._conv3(dY, f"c{i}_d", nbb, hi_, wi_, co, ci, dA)
+                self._conv3(dY, f"c{i}_d", nbb, hi_, wi_, co, ci, dA, alpha=1.0 / _WSCALE)
             else:
                 # backward-data of a stride-2 conv: four parity classes of the input grid in one launch (engine_d.py)
                 all_taps, all_widx, classes = [], [], []
@@ -291,12 +299,17 @@ class SplitDiscriminatorEngine(SplitOps):
                         all_taps += [(oy, ox) for (_dy, oy) in ys for (_dx, ox) in xs_]
                         all_widx += [8 - (dy * 3 + dx) for (dy, _oy) in ys for (dx, _ox) in xs_]
                         classes.append((len(ys) * len(xs_), ph, pw))
-                self._conv3(dY, f"c{i}_d", nbb, hi_ // 2, wi_ // 2, co, ci, dA, taps=all_taps, tap_widx=all_widx,
+                self._conv3(dY, f"c{i}_d", nbb, hi_ // 2, wi_ // 2, co, ci, dA, alpha=1.0 / _WSCALE, taps=all_taps, tap_widx=all_widx,
                             srcs_fn=lambda t, hh=hh, ww=ww, co=co: [ops.nhwc_src(t, nbb, hh, ww, co)],
                             out_h=hi_, out_w=wi_, out_sy=2, out_sx=2, aux_mode=1, classes=classes)
+            # renew the range scale for the next layer (a NEW tensor: kernels already enqueued keep reading the old one)
+            ops.amax_scale(dA, self.scale_ws, target=16.0)
+            f = self.scale_ws[1:2]
+            dA.mul_(f)
+            scale = scale * f
         dxs = [None] * G
         if any(need_in[:gsel]):
-            Zd = self._conv3(dY, "c0_d", nbb, h, w, 64, 32, e32(nbb * h * w, 32), taps=[(0, 0)])
+            Zd = self._conv3(dY, "c0_d", nbb, h, w, 64, 32, e32(nbb * h * w, 32), taps=[(0, 0)], alpha=1.0 / _WSCALE)
             dx = torch.empty(nbb, 3, h, w, device=dev, dtype=torch.float32)
             ops.col2im3(Zd, 32, nbb, h, w, dx, mul=1.0, div_dev=scale, sgn=-1)
             for g in range(gsel):

@@ -24,7 +24,18 @@ from .engine_g import FlatGrads, _shuffle_perm, _unshuffle_perm
 from .engine_split import HL as _HL
 from .engine_split import SplitOps
 from .engine_split import SplitWeight as _SplitWeight
+from .engine_split import _shuffle2, _unshuffle2
 from .ops import ACT_RELU
+
+
+import os
+
+# The incoming gradient is scaled (by a power of two) so that its largest element sits at _GRAD_TARGET.  The hi + lo pair
+# carries 22 bits only for elements above ~1e-4 of the fp16 normal range: with the 16-bit schedule's target of 16 a gradient
+# image with a wide dynamic range (d(GAN loss)/d(sr) through a Discriminator right after its first Adam step: 7.8e-3
+# relative error of the Generator gradients) loses its small elements.  2^12 leaves 16x headroom for growth through the
+# Generator's backward (measured growth: < 2x) and 8 more bits below.
+_GRAD_TARGET = float(os.environ.get("PESR_SPLIT_GRAD_TARGET", "4096"))
 
 
 class SplitGeneratorEngine(SplitOps):
@@ -152,7 +163,7 @@ class SplitGeneratorEngine(SplitOps):
         grads[g.add_mean.weight].view(-1).copy_(sums[0:9])
         grads[g.add_mean.bias].copy_(sums[9:12])
         torch.mv(am_wt, sums[9:12], out=grads[up4.bias])
-        ops.amax_scale(dsr, ws, target=16.0)
+        ops.amax_scale(dsr, ws, target=_GRAD_TARGET)
         dcol = _HL(16 * P, 64, dev)
         ops.im2col3(dsr, dcol.hi, affine_a=am_wt, mul_dev=scale, sgn=-1)
         ops.im2col3(dsr, dcol.lo, affine_a=am_wt, mul_dev=scale, sgn=-1, low_part=True)

@@ -16,7 +16,11 @@ from ._lib import check, lib
 class SplitWeight:
     """hi / lo 16-bit GEMM operands of one fp32 parameter in layout `mode`, re-packed when the parameter changes."""
 
-    def __init__(self, param, mode, pad_to=0):
+    def __init__(self, param, mode, pad_to=0, scale=1.0):
+        # scale (a power of two): the operand pair holds param * scale.  Small weights (|w| ~ 0.03) have lo halves in the
+        # fp16 SUBNORMAL range (19 significant bits in all); scaled by 256 both halves are normal numbers (22 bits) and the
+        # caller folds 1 / scale into the convolution's alpha.
+        self.scale = float(scale)
         co, ci, k = param.shape[0], param.shape[1], param.shape[2]
         shape = ops.packed_shape(co, ci, k, mode, pad_to)
         self.param, self.mode, self.pad_to = param, mode, pad_to
@@ -29,6 +33,8 @@ class SplitWeight:
         key = (p.data_ptr(), p._version)
         if key != self.key:
             w = p.detach()
+            if self.scale != 1.0:
+                w = w * self.scale
             ops.pack_weights(w, self.mode, self.hi, self.pad_to)
             ops.pack_weights(w - w.half().float(), self.mode, self.lo, self.pad_to)
             self.key = key

@@ -89,15 +89,16 @@ def _uniform_target(t):
     if not torch.is_tensor(t):
         return float(t)
     key = (t.data_ptr(), t._version, t.numel())
-    v = _TARGET_CACHE.get(key)
-    if v is None:
+    hit = _TARGET_CACHE.get(key)
+    if hit is None:
         lo, hi = float(t.min()), float(t.max())
         if lo != hi:
             raise ValueError("pesr_b200 GAN losses take a constant target tensor (all zeros or all ones)")
         if len(_TARGET_CACHE) > 64:
             _TARGET_CACHE.clear()
-        v = _TARGET_CACHE[key] = lo
-    return v
+        # the entry keeps the tensor alive: a freed tensor's address could otherwise come back holding another value
+        hit = _TARGET_CACHE[key] = (lo, t)
+    return hit[0]
 
 
 def rsgan_bce(pred_a, pred_b, target=1.0):

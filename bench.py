@@ -547,9 +547,27 @@ def side_measurements(args, dev, G, optim_G, dev_lr, dev_hr):
                                                 "ms_per_step": ms, "tflops_algorithmic": step_gflop("pretrain") / ms,
                                                 "tensor_passes_per_conv": 3, "launch": "eager",
                                                 "note": "pesr_b200/engine_g_split.py; tests/test_split_precision_gpu.py"}
+        if args.workload == "gan":
+            # the whole GAN step with all three networks on the split-precision schedules (engine_d_split / engine_v_split)
+            from pesr_b200.model import VGG, Discriminator
+            Ds = Discriminator(OPT, split_precision=True).to(dev)
+            Vs = VGG(pretrained=False, split_precision=True).to(dev)
+            oD = Adam(Ds.parameters(), lr=5e-5)
+            cfg_s = dict(steps.DEFAULT_GAN_CFG)
+            cfg_s['target_real'] = torch.ones(BATCH, 1, device=dev)
+            cfg_s['target_fake'] = torch.zeros(BATCH, 1, device=dev)
+            ms = timed(lambda i: steps.gan_step(Gs, Ds, Vs, oS, oD, dev_lr[i % len(dev_lr)], dev_hr[i % len(dev_hr)], cfg_s), 4, warm=2)
+            out["split_precision_gan_step"] = {"metric": "GAN train samples/s, split-precision G + D + VGG", "value": BATCH / (ms * 1e-3),
+                                               "ms_per_step": ms, "tflops_algorithmic": step_gflop("gan") / ms,
+                                               "tensor_passes_per_conv": 3, "launch": "eager",
+                                               "note": "pesr_b200/engine_{g,d,v}_split.py; gradients vs the free-running fp64 oracle: "
+                                                       "tests/test_split_precision_gpu.py"}
+            del Ds, Vs, oD
         del Gs, oS
+        torch.cuda.empty_cache()
     except Exception as e:
-        out["split_precision_pretrain_step"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        out["split_precision_pretrain_step"] = out.get("split_precision_pretrain_step") or {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        out["split_precision_error"] = f"{type(e).__name__}: {str(e)[:200]}"
     G.eval()
     flop_px = 100505088
     inf = {}

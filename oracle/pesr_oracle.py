@@ -346,7 +346,7 @@ def pretrain_step(g_sd, lr_img, hr_img, opt, dtype=torch.float32, qdtype=None):
 
 def gan_step(g_sd, d_sd, v_sd, lr_img, hr_img, opt, lr_rate=5e-5, alpha_l1=0.0, alpha_vgg=50.0, alpha_gan=1.0,
              alpha_tv=1e-6, gamma=1.0, dtype=torch.float32, qdtype=None, focal_detach=False, gan_type='RSGAN',
-             focal=True, pins=None):
+             focal=True, pins=None, gp_u=None):
     """train.py:202-259 (defaults of train.py:64-76: RSGAN + focal loss; gan_type='SGAN' and focal=False select the
     other branches of train.py:210-213 / :244-253), with one real Adam step on D between the two phases as in
     train.py:229.  Returns a dict of losses, gradients and `sr`.
@@ -372,6 +372,14 @@ def gan_step(g_sd, d_sd, v_sd, lr_img, hr_img, opt, lr_rate=5e-5, alpha_l1=0.0, 
                   F.binary_cross_entropy_with_logits(pred_fake, torch.zeros_like(pred_fake)))
     else:
         d_loss = F.binary_cross_entropy_with_logits(pred_real - pred_fake, ones)   # train.py:213
+    if gp_u is not None:                                                       # gradient penalty, train.py:216-226
+        x_both = (hr_img * gp_u.to(dtype) + sr.detach() * (1 - gp_u.to(dtype))).detach().requires_grad_(True)
+        pred_both = discriminator_forward(d, x_both, qdtype=None)
+        grad = torch.autograd.grad(outputs=pred_both, inputs=x_both, grad_outputs=torch.ones_like(pred_both),
+                                   retain_graph=True, create_graph=True, only_inputs=True)[0]
+        out['gp'] = 10 * ((grad.norm(2, 1).norm(2, 1).norm(2, 1) - 1) ** 2).mean()
+        d_loss = d_loss + out['gp']
+        out['gp'] = out['gp'].detach()
     d_grads = torch.autograd.grad(d_loss, [d[k] for k in d_train])
     out['d_loss'] = d_loss.detach()
     out['d_grads'] = dict(zip(d_train, d_grads))

@@ -71,7 +71,30 @@ def gan_step(G, D, vgg, optim_G, optim_D, lr, hr, cfg, ddp_g=None, ddp_d=None):
         total_D_loss = bce(pred_real, t_real) + bce(pred_fake, t_fake)
     else:
         total_D_loss = losses.rsgan_bce(pred_real, pred_fake, t_real)
-    total_D_loss.backward()
+    if cfg.get('GP'):
+        # train.py:216-226 (`--GP true`, off by default): the penalty needs a second derivative through D, which the kernel
+        # schedule does not implement; pesr_b200/gp.py evaluates it with ATen on the same parameters.  Its parameter
+        # gradients join the schedule's before anything is reduced across ranks.
+        from .gp import gradient_penalty
+        d_mod = getattr(D, "module", D)
+        eng = d_mod.engine()
+        params = list(d_mod.parameters())
+        hook, eng.grad_hook = eng.grad_hook, None
+        try:
+            gp = gradient_penalty(d_mod, hr, sr, u=cfg.get('gp_u'))
+            gp_grads = torch.autograd.grad(gp, params, allow_unused=True)
+            total_D_loss.backward()
+        finally:
+            eng.grad_hook = hook
+        with torch.no_grad():
+            for p, g in zip(params, gp_grads):
+                if g is not None:
+                    p.grad.add_(g)
+        total_D_loss = total_D_loss.detach() + gp.detach()
+        if ddp_d is not None:
+            ddp_d.allreduce_grads()
+    else:
+        total_D_loss.backward()
     # The Generator-phase terms that do not involve D (train.py:240-247) are issued BEFORE waiting for D's gradient
     # all-reduce (DataParallel(defer_finish=True): backward returns with the last buckets still in flight and
     # ddp_d.finish() below is the wait): VGG's forward, L1 and TV depend on sr / hr only, so they keep the SMs busy

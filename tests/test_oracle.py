@@ -204,3 +204,46 @@ def test_rounding_noise_floor_and_forward_pinning():
     pinned = sorted(rel_l2(g32[k], gp[k]) for k in gp)
     print(f"forward-pinned: logits {rel_l2(y32, yp):.2e}, grads median {pinned[len(pinned) // 2]:.2e} max {pinned[-1]:.2e}")
     assert rel_l2(y32, yp) < 1e-5 and pinned[-1] < 1e-4 and rel_l2(dx32, dxp) < 1e-4
+
+
+def test_gradient_penalty_branch_matches_the_oracle():
+    """pesr_b200/gp.py (train.py:216-226, `--GP true`): the penalty and its parameter gradients -- a second derivative
+    through conv / train-mode BatchNorm / LeakyReLU / Linear, evaluated with ATen on the Discriminator's own
+    parameters -- against the fp64 oracle (O.gan_step(gp_u=...) restates the reference lines), and the BatchNorm
+    running statistics the extra train-mode call leaves behind."""
+    import torch.nn.functional as F
+    from pesr_b200.gp import discriminator_aten, gradient_penalty
+    from pesr_b200.model import Discriminator
+    opt = {'patch_size': 8, 'spectral_norm': False}
+    sd = O.init_discriminator(opt, 3)
+    D = Discriminator(opt)
+    D.load_state_dict(sd)
+    D.train()
+    g = torch.Generator().manual_seed(5)
+    nb = 3
+    hr = torch.rand(nb, 3, 32, 32, generator=g) * 255
+    sr = torch.rand(nb, 3, 32, 32, generator=g) * 255
+    u = torch.rand(nb, 1, 1, 1, generator=g)
+    # the ATen restatement is the module's function (what the kernel schedule computes on the GPU)
+    leaf = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+            for k, v in sd.items()}
+    assert rel_l2(discriminator_aten(D, hr).detach(), O.discriminator_forward(leaf, hr.double()).detach()) < 1e-5
+    D.load_state_dict(sd)            # undo the running-statistics update of the call above
+    gp = gradient_penalty(D, hr, sr, u=u)
+    names = [k for k, _ in D.named_parameters()]
+    grads = torch.autograd.grad(gp, list(D.parameters()), allow_unused=True)
+    x_both = (hr.double() * u.double() + sr.double() * (1 - u.double())).requires_grad_(True)
+    pred = O.discriminator_forward(leaf, x_both)
+    gx = torch.autograd.grad(pred, x_both, torch.ones_like(pred), create_graph=True)[0]
+    ogp = 10 * ((gx.norm(2, 1).norm(2, 1).norm(2, 1) - 1) ** 2).mean()
+    og = torch.autograd.grad(ogp, [leaf[k] for k in names], allow_unused=True)
+    assert abs(float(gp) - float(ogp)) < 1e-4 * abs(float(ogp))
+    errs = []
+    for k, a, b in zip(names, grads, og):
+        if b is None or float(b.abs().max()) == 0.0:
+            assert a is None or float(a.abs().max()) < 1e-6, k        # classifier.2.bias: the penalty does not see it
+            continue
+        errs.append(rel_l2(a, b))
+    assert max(errs) < 2e-3 and sorted(errs)[len(errs) // 2] < 2e-4, errs      # fp32 double backward vs fp64
+    assert int(D.features[0][1].num_batches_tracked) == 1
+    assert float((D.features[3][1].running_mean - sd['features.3.1.running_mean']).abs().max()) > 0

@@ -221,3 +221,42 @@ def test_split_precision_gan_step_matches_free_running_fp64_oracle():
     assert gmax < 5e-3 and dmax < 5e-3
     assert badfrac < 1e-4
     assert dmed < 0.2 * res["fp16"][3]
+
+
+def test_gan_step_with_gradient_penalty_matches_oracle():
+    """`--GP true` (train.py:216-226): the Discriminator phase with the gradient penalty (pesr_b200/gp.py, ATen double
+    backward on the module's parameters) added to the kernel schedule's gradients, against the fp64 oracle: the D loss
+    (RSGAN + penalty), every D parameter gradient and the update optim_D.step() applies."""
+    from oracle import pesr_oracle as O
+    from pesr_b200 import steps
+    from pesr_b200.model import VGG, Discriminator, Generator
+    from pesr_b200.optim import Adam
+    opt = {'depth': 2, 'num_channels': 64, 'res_scale': 0.1, 'patch_size': 12, 'spectral_norm': False}
+    nb, patch, lrate = 4, 12, 5e-5
+    g_sd, d_sd, v_sd = O.init_generator(opt, 0), O.init_discriminator(opt, 1), O.init_vgg(2)
+    gen = torch.Generator().manual_seed(3)
+    lr = torch.rand(nb, 3, patch, patch, generator=gen) * 255
+    hr = torch.rand(nb, 3, patch * 4, patch * 4, generator=gen) * 255
+    u = torch.rand(nb, 1, 1, 1, generator=gen)
+    free = O.gan_step(g_sd, d_sd, v_sd, lr, hr, opt, lr_rate=lrate, dtype=torch.float64, gp_u=u.double())
+    G, D, V = Generator(opt, split_precision=True), Discriminator(opt, split_precision=True), VGG(pretrained=False, split_precision=True)
+    G.load_state_dict(g_sd), D.load_state_dict(d_sd), V.load_state_dict(v_sd)
+    G, D, V = G.cuda(), D.cuda(), V.cuda()
+    optG, optD = Adam(G.parameters(), lr=lrate), Adam(D.parameters(), lr=lrate)
+    cfg = dict(steps.DEFAULT_GAN_CFG, GP=True, gp_u=u.cuda())
+    cfg['target_real'] = torch.ones(nb, 1, device="cuda")
+    cfg['target_fake'] = torch.zeros(nb, 1, device="cuda")
+    got = steps.gan_step(G, D, V, optG, optD, lr.cuda(), hr.cuda(), cfg).cpu()
+    e_loss = abs(float(got[4]) - float(free['d_loss'])) / abs(float(free['d_loss']))
+    de = sorted((rel_l2(p.grad.cpu(), free['d_grads'][k]), k) for k, p in D.named_parameters())
+    bad = sum(int(((p.detach().cpu().double() - free['d_params_after'][k].double()).abs() > 0.05 * lrate).sum())
+              for k, p in D.named_parameters())
+    total = sum(p.numel() for p in D.parameters())
+    print(f"GAN step with gradient penalty: D loss {float(got[4]):.6f} (penalty {float(free['gp']):.4f} of it) rel {e_loss:.1e}; D grads rel-L2 "
+          f"median {de[len(de) // 2][0]:.2e} max {de[-1][0]:.2e} ({de[-1][1]}); Adam update differs on {bad} of {total} weights")
+    assert float(free['gp']) > 0.1 * float(free['d_loss'])          # the penalty is a real share of the loss here
+    assert e_loss < 1e-4
+    assert de[len(de) // 2][0] < 1e-3 and de[-1][0] < 5e-3
+    assert bad / total < 1e-3
+    # three train-mode calls of D in the D phase (hr, sr, the mix) and two in the G phase
+    assert int(D.features[0][1].num_batches_tracked) == 5

@@ -120,10 +120,9 @@ def save_full_state(path, epoch, best_psnr, G, optim_G, D=None, optim_D=None):
 
 def main():
     args = parser.parse_args()
-    if args.GP:
-        raise NotImplementedError('--GP true (gradient penalty, train.py:216-226) differentiates D\'s backward pass a second '
-                                  'time (create_graph=True through conv / train-mode BatchNorm); the B200 schedules '
-                                  'implement first-order backward only. It is off by default in the reference.')
+    if args.GP and args.cuda_graph:
+        raise SystemExit('--GP true (gradient penalty, train.py:216-226) runs its double backward through ATen autograd '
+                         '(pesr_b200/gp.py) and is not captured: use it without --cuda_graph')
     if args.num_channels % 64 != 0:
         raise SystemExit('--num_channels must be a multiple of 64 (tensor-core K block)')
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -156,7 +155,7 @@ def main():
         cfg = dict(alpha_l1=args.alpha_l1, alpha_vgg=args.alpha_vgg, alpha_gan=args.alpha_gan, alpha_tv=args.alpha_tv,
                    fl_gamma=args.fl_gamma, gan_type=args.gan_type, focal_loss=args.focal_loss,
                    target_real=torch.ones(args.batch_size, 1, device=device),
-                   target_fake=torch.zeros(args.batch_size, 1, device=device))
+                   target_fake=torch.zeros(args.batch_size, 1, device=device), GP=args.GP)
     check_point = os.path.join(args.check_point, args.phase)
     if rank == 0:
         os.makedirs(check_point, exist_ok=True)

@@ -496,7 +496,15 @@ def hbm_kernels(dev, peak_gbs):
     run("FC1 forward (conv_igemm split-K, 151 MB of fp16 weights)", 2 * k * o, lambda i: ops.conv_igemm(descs[i]), 2)
     dy = torch.randn(BATCH, o, device=dev)
     dws = [torch.empty(o, k, device=dev) for _ in range(2)]
-    run("linear_wgrad_kernel FC1 (302 MB fp32 gradient written)", 4 * k * o, lambda i: ops.linear_wgrad(dy, x16, BATCH, k, o, dws[i]), 2)
+    run("linear_wgrad_kernel FC1, CUDA cores (302 MB fp32 gradient written; round-1 path, PESR_FC1_WGRAD_SKINNY=1)", 4 * k * o,
+        lambda i: ops.linear_wgrad(dy, x16, BATCH, k, o, dws[i]), 2)
+    from pesr_b200.engine_d import DiscriminatorEngine
+    eng_fc = DiscriminatorEngine(None)
+    dy32 = torch.randn(2 * BATCH, o, device=dev) * 1e-4
+    x32r = torch.randn(2 * BATCH, k, device=dev, dtype=f16)
+    run("FC1 weight gradient on the tensor cores (conv_wgrad_kernel, 32 rows as hi + lo pairs; 302 MB written)", 4 * k * o,
+        lambda i: eng_fc._fc1_wgrad(dy32, x32r, k, dws[i]), 2, note="includes the amax / split / operand copies (4 small launches)")
+    del eng_fc
     del w16, dws, part
     # x8 self-ensemble blend + uint8 store at 1356 x 2040 (E6): 9 fp32 reads + 1 byte written per element
     H, W = 1356, 2040

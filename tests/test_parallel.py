@@ -23,6 +23,9 @@ def _free_port():
 class _FakeEngine:
     grad_hook = None
     grad_hook_finish = None
+    grad_hook_flush = None
+    grad_hook_skip = None
+    fc1_gather = None          # parallel.DataParallel installs the factor all-gather / skip hooks when this attribute exists
 
 
 class _FakeNet(torch.nn.Module):
@@ -57,6 +60,21 @@ def _worker(rank, world, port, n, cuts, bucket_mb, out):
         net.engine().grad_hook_finish()
         expect = torch.arange(n, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
         ok = torch.allclose(flat, expect)
+        # a range the engine fills with an already averaged gradient (the Discriminator's Linear weight, formed from the
+        # all-gathered factors): everything around it is reduced, the range itself is left alone; the tail bucket is
+        # launched by the end-of-backward flush and only waited for in finish()
+        flat2 = torch.arange(n, dtype=torch.float32) * (rank + 1)
+        eng = net.engine()
+        eng.grad_hook(800, n, flat2)
+        eng.grad_hook_skip(300, 800)
+        eng.grad_hook(100, 300, flat2)
+        eng.grad_hook(0, 100, flat2)
+        eng.grad_hook_flush()
+        ok = ok and ddp._pending is None
+        eng.grad_hook_finish()
+        expect2 = expect.clone()
+        expect2[300:800] = torch.arange(300, 800, dtype=torch.float32) * (rank + 1)
+        ok = ok and torch.allclose(flat2, expect2)
         # fallback path for modules without a flat-gradient schedule
         net.w.grad = torch.full((7,), float(rank))
         ddp.allreduce_grads()

@@ -1,4 +1,4 @@
-"""Data parallelism: one process per GPU + NCCL gradient all-reduce over NVLink, replacing the
+"""Data parallelism: one process per GPU, gradients averaged over NVLink / NVSwitch, replacing the
 reference's single-process nn.DataParallel (train.py:114-118).
 
 Semantics kept from nn.DataParallel: every replica sees an equal shard of the batch, BatchNorm
@@ -8,8 +8,15 @@ become the average of the per-rank gradients; the TV term, a batch SUM in the re
 
 Overlap: the Generator / Discriminator schedules emit their parameter gradients into one flat fp32
 buffer that completes from its end towards its start; each completed range is handed to
-``_on_range``, which launches ncclAllReduce(AVG) for every full bucket on a side stream while the
-remaining backward kernels keep the SMs busy.  The last (smallest) bucket is the only exposed one.
+``_on_range``, which launches the all-reduce of every full bucket on a high-priority side stream while the
+remaining backward kernels keep the SMs busy; the tail bucket is launched at the end of backward and
+``finish()`` (called right before optimizer.step()) is the only wait.
+
+The reduction itself is the hand-written two-shot kernel of csrc/comm_ops.cu over a symmetric-memory copy of
+the flat buffer (multimem.ld_reduce / multimem.st through the NVSwitch, or peer loads / stores), run on the SMs
+the persistent tensor-core kernels leave free (PESR_OPT_RESERVE_SMS); NCCL carries the parameter broadcast,
+the all-gather of the Linear(73728 -> 1024) gradient factors, and is the fallback when symmetric memory is
+not available.
 """
 import os
 

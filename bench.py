@@ -215,7 +215,6 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
         from pesr_b200.parallel import nccl_env_defaults
         nccl_env_defaults()       # NCCL_MAX_CTAS = the SMs the persistent kernels leave free (pesr_b200/parallel.py)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

@@ -178,8 +178,9 @@ class DataParallel(torch.nn.Module):
                 self._symm = _SymmetricFlat(numel, device, self.pg, self.world_size, rank)
             except Exception as e:        # no symmetric memory on this system: NCCL all-reduce
                 self._symm_failed = f"{type(e).__name__}: {str(e)[:200]}"
+                import sys
                 print(f"[pesr_b200.parallel] symmetric memory unavailable ({self._symm_failed}); using NCCL all-reduce",
-                      flush=True)
+                      file=sys.stderr, flush=True)
         if self._symm is not None and self._symm.tensor.numel() == numel:
             return self._symm.tensor
         return torch.empty(numel, device=device, dtype=torch.float32)

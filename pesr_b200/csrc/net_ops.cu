@@ -122,6 +122,15 @@ bn_reduce_vec_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, l
   const long long step = (long long)gridDim.x * rpp;
   long long p = (long long)blockIdx.x * rpp + r;
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  if (mode == 0) {
+    for (; p + 7 * step < npix; p += 8 * step) {      // statistics pass: one operand, eight loads in flight
+      uint4 u[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) u[q] = x[(p + q * step) * tpr + v];
+#pragma unroll
+      for (int q = 0; q < 8; q++) accum(u[q], zero4);
+    }
+  }
   for (; p + 3 * step < npix; p += 4 * step) {
     uint4 u[4], w[4];
 #pragma unroll
@@ -210,9 +219,8 @@ __global__ void bn_lrelu_fwd_kernel(const uint4* __restrict__ y, long long nvec,
   }
   __syncthreads();
   const int cv = c >> 3;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+  auto apply = [&](long long i, const uint4& u) {
     const int c0 = (int)(i % cv) * 8;
-    const uint4 u = y[i];
     const uint32_t in[4] = {u.x, u.y, u.z, u.w};
     uint32_t out[4];
 #pragma unroll
@@ -226,7 +234,19 @@ __global__ void bn_lrelu_fwd_kernel(const uint4* __restrict__ y, long long nvec,
       out[j] = pack2(v0, v1, bf);
     }
     a[i] = make_uint4(out[0], out[1], out[2], out[3]);
+  };
+  // four independent 16-byte loads in flight per thread (one per thread kept ~4.8 MB in flight on the whole GPU, short of
+  // what HBM3e needs: 0.63 of the copy bandwidth)
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < nvec; i += 4 * stride) {
+    uint4 u[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) u[q] = y[i + q * stride];
+#pragma unroll
+    for (int q = 0; q < 4; q++) apply(i + q * stride, u[q]);
   }
+  for (; i < nvec; i += stride) apply(i, y[i]);
 }
 
 // dy = gamma * rstd * (dz - s1/n - xhat * s2/n) = ka*dz + kb*y + kc per channel and group; block (0, 0) also emits
@@ -263,9 +283,8 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* _
     kc[i] = (float)(g * r * (m * r * k2 - k1));
   }
   __syncthreads();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+  auto apply = [&](long long i, const uint4& ug, const uint4& uy) {
     const int c0 = (int)(i % cv) * 8;
-    const uint4 ug = dz[i], uy = y[i];
     const uint32_t g_in[4] = {ug.x, ug.y, ug.z, ug.w}, y_in[4] = {uy.x, uy.y, uy.z, uy.w};
     uint32_t out[4];
 #pragma unroll
@@ -275,7 +294,16 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* _
       out[j] = pack2(ka[cc] * g.x + kb[cc] * yy.x + kc[cc], ka[cc + 1] * g.y + kb[cc + 1] * yy.y + kc[cc + 1], bf);
     }
     dy[i] = make_uint4(out[0], out[1], out[2], out[3]);
+  };
+  // two vector pairs (four 16-byte loads) in flight per thread, see bn_lrelu_fwd_kernel
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < nvec; i += 2 * stride) {
+    const uint4 g0 = dz[i], g1 = dz[i + stride], y0 = y[i], y1 = y[i + stride];
+    apply(i, g0, y0);
+    apply(i + stride, g1, y1);
   }
+  if (i < nvec) apply(i, dz[i], y[i]);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -171,6 +171,7 @@ def profile_read(kind):
 
 
 OPT_PAIR_MODE, OPT_SUB_STAGES, OPT_PDL, OPT_STAGED_EPILOGUE, OPT_SPECIALISED_EPILOGUE = 0, 1, 2, 3, 4
+OPT_RESERVE_SMS, OPT_RESIDENT_WEIGHTS = 5, 6
 
 
 def set_option(option, value):

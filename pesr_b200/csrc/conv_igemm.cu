@@ -69,6 +69,12 @@ struct ConvK {
   // small-N layers): sub_mode 1 = nsub consecutive 64-channel chunks of one tap, 2 = the three vertical taps of one
   // kernel column out of a (tile_h + 2)-row halo box
   int sub_mode, nsub, a_sub_off, b_sub_off, a_bytes, steps_per_tile;
+  // sub_mode 2 with RESIDENT weights (wres_bytes > 0): the layer's whole packed weight tensor (<= ~150 KB: the N = 64 /
+  // 128 layers of VGG and the Discriminator) is loaded into shared memory once per CTA, in the order the halo stages
+  // consume it, and every pipeline stage carries the activation box only.  Those layers re-fetched 74 KB of weights for
+  // every 128-pixel tile - more L2 -> SM traffic per tile than the activations, at 115 B per MMA cycle - and ran at a
+  // third of the tensor rate.
+  int wres_bytes;
   unsigned long long* dbg;   // optional timeline of block 0 (bring-up): [64] clock64 stamps + [63] = globaltimer ns
   long long split_stride32;
   // several sub-problems ("classes") of one pixel grid in ONE launch: class c owns taps [cls_tap0[c], cls_tap0[c+1]) and
@@ -118,12 +124,14 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
   const int b_rows = kPair ? p.block_n / 2 : p.block_n;                      // weight rows staged by this CTA
 
   uint8_t* epi_base = smem + (size_t)p.stages * p.stage_bytes;            // staging tiles of the staged epilogue
-  uint8_t* tail = epi_base + (kStaged ? kEpiBytes : kEpi == 7 ? kBnEpiBytes : 0);
+  uint8_t* wres = epi_base;                                               // resident weights (never with a staged epilogue)
+  uint8_t* tail = epi_base + (kStaged ? kEpiBytes : kEpi == 7 ? kBnEpiBytes : 0) + p.wres_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* wres_bar = reinterpret_cast<uint64_t*>(tail + 192);
   float* bias_s = reinterpret_cast<float*>(tail + 256);  // [2][256]
 
   if (threadIdx.x == 0) {
@@ -137,6 +145,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], kPair ? 8 : 128);   // pair: one arrival per epilogue warp of both CTAs
     }
+    mbar_init(wres_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -223,7 +232,16 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       // PDL prologue: the weights do not depend on the preceding kernel, so the first ring of weight boxes is in
       // flight while that kernel drains
       int npre = 0;
-      if (p.pdl_early_b) {
+      const bool resident = MODE == 2 && p.wres_bytes > 0;
+      auto load_resident = [&]() {     // every (channel block, dx) weight box of the layer, in stage order
+        mbar_expect_tx_w(wres_bar, (uint32_t)p.wres_bytes);
+        for (int s = 0; s < p.steps_per_tile; s++) {
+          const int cb = s / 3, t = s - cb * 3;
+          tma_load_3d_w(wres + (size_t)s * 3 * p.b_sub_off, &maps.b, wres_bar, cb * kKBlock, t * p.cout, 0);
+        }
+      };
+      if (resident && p.pdl_early_b) load_resident();
+      if (p.pdl_early_b && !resident) {
         int split, m_tile, n_tile, cls, s0, s1, t, cb;
         decode(worker, split, m_tile, n_tile, cls);
         step_range(split, cls, s0, s1);
@@ -238,6 +256,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
       }
       griddep_wait();
       griddep_launch();
+      if (resident && !p.pdl_early_b) load_resident();
       for (int tile = worker; tile < p.num_tiles; tile += nworkers) {
         int split, m_tile, n_tile, cls, s0, s1, t, cb;
         decode(tile, split, m_tile, n_tile, cls);
@@ -263,8 +282,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
             mbar_wait_w(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
             uint64_t* fb = &full_bar[stage];
-            const bool with_b = npre == 0;     // else: the weights of this step were issued in the prologue
-            if (with_b) expect(fb); else npre--;
+            const bool with_b = npre == 0 && !resident;     // else: the weights of this step were issued in the prologue
+            if (with_b || resident) expect(fb); else npre--;
             if (MODE == 2) {
               tma_load_4d_w(sa, ma, fb, cb * kKBlock, ww + t, hh, img);
               if (with_b) tma_load_3d_w(sa + p.a_bytes, &maps.b, fb, cb * kKBlock, t * p.cout + brow, 0);
@@ -297,6 +316,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
     // ===================== MMA issuer (leader CTA only in pair mode) =====================
     if (leader) {
       const uint32_t idesc = make_idesc(kPair ? 256 : kTileM, p.block_n, p.dtype, 0, p.b_mn_major);
+      // the accumulator address through a shuffle: the compiler then knows it is warp-uniform and keeps it in a uniform
+      // register instead of converting it (R2UR under the elect predicate) in front of every tcgen05.mma
+      const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -311,21 +333,36 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
         const int steps_per_tile = p.sub_mode == 2 ? p.steps_per_tile : total_kb / p.nsub;
         if (kPair) mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1); else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
+        const uint32_t d_tmem = tmem_base_u + (uint32_t)(acc * kAccStride);
         if (dbg && lane == 0) dbg[8 + (tile == worker ? 0 : 4)] = clock64();    // MMA warp: accumulator free
+        // UMMA shared-memory descriptors: everything but the 14-bit address field (bits 0..13, in 16-byte units) is the same
+        // for every K-major operand tile, and the tiles are 1024-byte aligned, so the descriptor of sub-block j, k-slice k
+        // is desc_k | (base >> 4) + j * sub + 2 * k: one add / one or per operand instead of a shift-mask-or chain per
+        // instruction.  The narrow layers (N = 64: 32 tensor cycles per instruction) are bound by this loop's issue rate.
+        const uint64_t desc_k = make_smem_desc(0, 16, 1024);
         if (!kPair && p.sub_mode) {
+          const uint32_t a_sub16 = (uint32_t)p.a_sub_off >> 4, b_sub16 = (uint32_t)p.b_sub_off >> 4;
+          const bool resident = p.wres_bytes > 0;
+          if (resident && tile == worker) {       // the layer's weights, loaded once per CTA
+            mbar_wait_w(wres_bar, 0);
+            tc_fence_after();
+          }
+          const uint32_t wres16 = smem_u32(wres) >> 4;
+          uint32_t accum = 0;
           for (int st = 0; st < steps_per_tile; st++) {
             mbar_wait_w(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
-            const uint32_t b_addr = a_addr + p.a_bytes;
+            uint32_t a16 = a_addr >> 4;
+            uint32_t b16 = resident ? wres16 + (uint32_t)st * 3u * b_sub16 : (a_addr + (uint32_t)p.a_bytes) >> 4;
             for (int j = 0; j < p.nsub; j++) {
 #pragma unroll
               for (int k = 0; k < kKBlock / 16; k++) {
-                const uint64_t da = make_smem_desc(a_addr + j * p.a_sub_off + k * 32, 16, 1024);
-                const uint64_t db = make_smem_desc(b_addr + j * p.b_sub_off + k * 32, 16, 1024);
-                umma_f16_w(d_tmem, da, db, idesc, (st > 0 || j > 0 || k > 0) ? 1u : 0u);
+                umma_f16_w(d_tmem, desc_k | (uint64_t)(a16 + 2 * k), desc_k | (uint64_t)(b16 + 2 * k), idesc, accum);
+                accum = 1;
               }
+              a16 += a_sub16;
+              b16 += b_sub16;
             }
             umma_commit_w(&empty_bar[stage]);
             if (st == steps_per_tile - 1) umma_commit_w(&tmem_full[acc]);
@@ -342,11 +379,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
           {
             const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
             const uint32_t b_addr = a_addr + kABytes;
+            const uint32_t a16 = a_addr >> 4, b16 = b_addr >> 4;
 #pragma unroll
             for (int k = 0; k < kKBlock / 16; k++) {
-              const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
-              const uint64_t db = p.b_mn_major ? make_smem_desc(b_addr + k * 2048, 8192, 1024)
-                                               : make_smem_desc(b_addr + k * 32, 16, 1024);
+              const uint64_t da = desc_k | (uint64_t)(a16 + 2 * k);
+              const uint64_t db = p.b_mn_major ? make_smem_desc(b_addr + k * 2048, 8192, 1024) : (desc_k | (uint64_t)(b16 + 2 * k));
               if (kPair) umma2_f16_w(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
               else       umma_f16_w(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
@@ -778,6 +815,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__
 static int g_sub_mode_enabled = 1;
 static int g_staged_enabled = 1;
 static int g_light_enabled = 1;
+static int g_wres_enabled = -1;   // resident weights for the narrow 3x3 layers: -1 from the environment (PESR_NO_WRES=1 disables)
 static unsigned long long* g_dbg_buf = nullptr;
 static int g_pair_mode = -1;  // -1: from the environment (PESR_NO_PAIR=1 disables), 0: never, 1: whenever legal
 
@@ -794,6 +832,7 @@ extern "C" int pesr_set_option(int option, int value) {
     case PESR_OPT_STAGED_EPILOGUE: g_staged_enabled = value; return 0;
     case PESR_OPT_SPECIALISED_EPILOGUE: g_light_enabled = value; return 0;
     case PESR_OPT_RESERVE_SMS: set_reserved_sms(value); return 0;
+    case PESR_OPT_RESIDENT_WEIGHTS: g_wres_enabled = value ? 1 : 0; return 0;
   }
   set_error("pesr_set_option: unknown option %d", option);
   return PESR_E_ARG;
@@ -814,6 +853,10 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
   if (g_pair_mode < 0) {
     const char* e = getenv("PESR_NO_PAIR");
     g_pair_mode = (e && e[0] == '1') ? 0 : 1;
+  }
+  if (g_wres_enabled < 0) {
+    const char* e = getenv("PESR_NO_WRES");
+    g_wres_enabled = (e && e[0] == '1') ? 0 : 1;
   }
   if (dd.block_n == 256 && dd.tile_h > 0 && dd.tile_w > 0 && g_sub_mode_enabled && dd.ksplit <= 1 && !dd.b_mn_major) {
     const int tn0 = dd.tile_n > 0 ? dd.tile_n : 1;
@@ -867,6 +910,10 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
   if (g_pair_mode < 0) {
     const char* e = getenv("PESR_NO_PAIR");
     g_pair_mode = (e && e[0] == '1') ? 0 : 1;
+  }
+  if (g_wres_enabled < 0) {
+    const char* e = getenv("PESR_NO_WRES");
+    g_wres_enabled = (e && e[0] == '1') ? 0 : 1;
   }
   const int img_groups = (d->nb + tile_n - 1) / tile_n;
   const int m_tiles_host = img_groups * ((d->h + d->tile_h - 1) / d->tile_h) * ((d->w + d->tile_w - 1) / d->tile_w);
@@ -1004,7 +1051,18 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
   }
   k.bn_sums = d->bn_sums;
   const int epi_smem = staged ? kEpiBytes : epi == 7 ? kBnEpiBytes : 0;
-  const int smem_budget = conv_smem_budget() - 4096 - epi_smem;
+  int smem_budget = conv_smem_budget() - 4096 - epi_smem;
+  // resident weights (ConvK::wres_bytes): one column tile, the whole packed tensor plus >= 3 activation stages fit, and
+  // every CTA has at least two tiles to spread the one-off weight load over
+  k.wres_bytes = 0;
+  if (sub_mode == 2 && g_wres_enabled && k.n_tiles == 1 && epi_smem == 0) {
+    const long long wbytes = 9ll * d->cout * d->cin * 2;
+    if (wbytes + 3ll * k.a_bytes <= smem_budget && k.num_tiles >= 2 * num_sms() && k.a_bytes % 1024 == 0) {
+      k.wres_bytes = (int)wbytes;
+      k.stage_bytes = k.a_bytes;
+      smem_budget -= k.wres_bytes;
+    }
+  }
   k.stages = smem_budget / k.stage_bytes;
   if (k.stages > kMaxStages) k.stages = kMaxStages;
   for (int t = 0; t < PESR_MAX_TAPS; t++) {
@@ -1026,7 +1084,7 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
   k.aux_mode = d->aux_mode;
 
   // >= 120 KB of dynamic smem also guarantees one CTA per SM, so the 512-column TMEM allocation never contends.
-  size_t smem = (size_t)k.stages * k.stage_bytes + epi_smem + 1024 /*align*/ + 256 /*barriers*/ +
+  size_t smem = (size_t)k.stages * k.stage_bytes + epi_smem + k.wres_bytes + 1024 /*align*/ + 256 /*barriers*/ +
                 2 * 256 * sizeof(float);
   if (smem < 120 * 1024) smem = 120 * 1024;
   // kernel variant: CTA pair x epilogue specialisation (see the template comment)

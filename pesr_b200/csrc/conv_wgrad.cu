@@ -157,6 +157,10 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
     }
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc(kPair ? 256 : 128, p.block_n, p.dtype, 1, 1);
+    // warp-uniform copies (through a shuffle the compiler knows it): the accumulator address and the constant part of the
+    // operand descriptors stay in uniform registers instead of being converted in front of every tcgen05.mma
+    const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint64_t desc_mn = make_smem_desc(0, p.lbo, p.sbo);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -167,7 +171,7 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
       patch_range(split, p0, p1);
       if (kPair) mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1); else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kWgAccStride);
+      const uint32_t d_tmem = tmem_base_u + (uint32_t)(acc * kWgAccStride);
       for (int pt = p0; pt < p1; pt++) {
         mbar_wait_w(&full_bar[stage], phase);
         tc_fence_after();
@@ -176,10 +180,11 @@ conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
         {
           const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
           const uint32_t b_addr = a_addr + p.a_boxes * kWgBoxBytes;
+          const uint32_t a16 = a_addr >> 4, b16 = b_addr >> 4;      // 1024-byte aligned tiles: the address field just adds
 #pragma unroll
           for (int k = 0; k < kWgKBlock / 16; k++) {
-            const uint64_t da = make_smem_desc(a_addr + k * 2048, p.lbo, p.sbo);
-            const uint64_t db = make_smem_desc(b_addr + k * 2048, p.lbo, p.sbo);
+            const uint64_t da = desc_mn | (uint64_t)(a16 + k * 128);
+            const uint64_t db = desc_mn | (uint64_t)(b16 + k * 128);
             if (kPair) umma2_f16_w(d_tmem, da, db, idesc, (pt > p0 || k > 0) ? 1u : 0u);
             else       umma_f16_w(d_tmem, da, db, idesc, (pt > p0 || k > 0) ? 1u : 0u);
           }

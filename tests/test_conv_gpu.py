@@ -260,3 +260,45 @@ def test_multi_pack_writes_both_layouts_from_one_read(co, ci, mode):
         ops.pack_weights(w.detach(), mode + 1, ref_b)
         assert torch.equal(f.buf, ref_f) and torch.equal(b.buf, ref_b)
         assert b.key == (w.data_ptr(), w._version)
+
+
+@pytest.mark.parametrize("nb,cin,cout,h,w", [(5, 64, 64, 96, 96), (3, 64, 128, 128, 96), (3, 128, 64, 96, 128),
+                                             (7, 64, 64, 100, 72)])
+@pytest.mark.parametrize("resident", [True, False], ids=["weights-resident", "weights-per-stage"])
+def test_narrow_layers_with_resident_weights(nb, cin, cout, h, w, resident):
+    """The N = 64 / 128 layers of VGG and the Discriminator (>= 2 tiles per SM, one column tile) keep their whole packed
+    weight tensor in shared memory (ConvK::wres_bytes): the light (bias + ReLU) and the mask (backward-data) epilogues
+    against torch, and bit-equal to the per-stage weight path."""
+    from pesr_b200 import _lib, ops
+    dtype = torch.float16
+    g = torch.Generator(device="cuda").manual_seed(nb * 31 + cin + h)
+    x = torch.randn(nb, cin, h, w, device="cuda", generator=g)
+    wt = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (3 * cin ** 0.5)
+    b = torch.randn(cout, device="cuda", generator=g)
+    m = torch.randn(nb, cout, h, w, device="cuda", generator=g)
+    ref = F.conv2d(x.half().float(), wt.half().float(), b, padding=1)
+    wp = torch.empty(ops.packed_shape(cout, cin, 3, 0), device="cuda", dtype=dtype)
+    ops.pack_weights(wt, 0, wp)
+    x16, m16 = _nhwc16(x, dtype), _nhwc16(m, dtype)
+    outs = []
+    for res in ((True, False) if resident else (False,)):
+        _lib.set_option(_lib.OPT_RESIDENT_WEIGHTS, 1 if res else 0)
+        try:
+            o_relu = torch.empty(nb, h, w, cout, device="cuda", dtype=dtype)
+            o_mask = torch.empty(nb, h, w, cout, device="cuda", dtype=dtype)
+            ops.conv_igemm(ops.make_conv_desc(dtype=0, nb=nb, h=h, w=w, cin=cin, cout=cout, srcs=[ops.nhwc_src(x16, nb, h, w, cin)],
+                                              wpacked=wp, bias=b, act=ops.ACT_RELU, out16=o_relu, ld_out16=cout))
+            ops.conv_igemm(ops.make_conv_desc(dtype=0, nb=nb, h=h, w=w, cin=cin, cout=cout, srcs=[ops.nhwc_src(x16, nb, h, w, cin)],
+                                              wpacked=wp, bias=b, mask16=m16, ld_mask16=cout, mask_mode=2, out16=o_mask, ld_out16=cout))
+            # a second launch reuses the plan (and follows another conv in the stream: PDL prologue with early weights)
+            o_again = torch.empty_like(o_relu)
+            ops.conv_igemm(ops.make_conv_desc(dtype=0, nb=nb, h=h, w=w, cin=cin, cout=cout, srcs=[ops.nhwc_src(x16, nb, h, w, cin)],
+                                              wpacked=wp, bias=b, act=ops.ACT_RELU, out16=o_again, ld_out16=cout))
+        finally:
+            _lib.set_option(_lib.OPT_RESIDENT_WEIGHTS, 1)
+        assert rel_l2(_nchw32(o_relu, nb, cout, h, w), ref.relu()) < 3e-4
+        assert rel_l2(_nchw32(o_mask, nb, cout, h, w), ref * torch.where(m.half().float() > 0, 1.0, 0.2)) < 3e-4
+        assert torch.equal(o_again, o_relu)
+        outs.append((o_relu, o_mask))
+    if len(outs) == 2:
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])

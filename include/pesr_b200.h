@@ -140,7 +140,7 @@ int pesr_conv_igemm(const pesr_conv_desc* d, void* stream);
                                        NCCL's all-reduce CTAs occupy: with a full-machine static tile schedule ONE SM taken by a
                                        concurrent kernel sends a CTA to a second wave (profiles/r02_sm_hog_probe.txt). */
 #define PESR_OPT_RESIDENT_WEIGHTS 6  /* narrow 3x3 layers keep their whole packed weight tensor in shared memory (pesr_conv_igemm):
-                                       0 off, 1 on (default; PESR_NO_WRES=1 in the environment disables) */
+                                       0 off, 1 where it wins: 128-wide column tiles (default; PESR_NO_WRES=1 disables), 2 wherever legal */
 int pesr_set_option(int option, int value);
 
 /* ------------------------------------------------------------------------------------------------

@@ -832,7 +832,7 @@ extern "C" int pesr_set_option(int option, int value) {
     case PESR_OPT_STAGED_EPILOGUE: g_staged_enabled = value; return 0;
     case PESR_OPT_SPECIALISED_EPILOGUE: g_light_enabled = value; return 0;
     case PESR_OPT_RESERVE_SMS: set_reserved_sms(value); return 0;
-    case PESR_OPT_RESIDENT_WEIGHTS: g_wres_enabled = value ? 1 : 0; return 0;
+    case PESR_OPT_RESIDENT_WEIGHTS: g_wres_enabled = value < 0 ? 0 : value > 2 ? 2 : value; return 0;
   }
   set_error("pesr_set_option: unknown option %d", option);
   return PESR_E_ARG;
@@ -1053,9 +1053,11 @@ extern "C" int pesr_conv_igemm(const pesr_conv_desc* d_in, void* stream_) {
   const int epi_smem = staged ? kEpiBytes : epi == 7 ? kBnEpiBytes : 0;
   int smem_budget = conv_smem_budget() - 4096 - epi_smem;
   // resident weights (ConvK::wres_bytes): one column tile, the whole packed tensor plus >= 3 activation stages fit, and
-  // every CTA has at least two tiles to spread the one-off weight load over
+  // every CTA has at least two tiles to spread the one-off weight load over.  Measured in a chain (tools/perf_narrow.py):
+  // 64 -> 128 @96x96x32 49.5 -> 43.5 us, 128 -> 64 unchanged, 64 -> 64 @192x192x32 118.5 -> 121.8 us (that layer is not
+  // feed-bound and only pays the prologue), so the mode is taken for N = 128 tiles (g_wres_enabled == 2: wherever legal).
   k.wres_bytes = 0;
-  if (sub_mode == 2 && g_wres_enabled && k.n_tiles == 1 && epi_smem == 0) {
+  if (sub_mode == 2 && g_wres_enabled && (d->block_n >= 128 || g_wres_enabled >= 2) && k.n_tiles == 1 && epi_smem == 0) {
     const long long wbytes = 9ll * d->cout * d->cin * 2;
     if (wbytes + 3ll * k.a_bytes <= smem_budget && k.num_tiles >= 2 * num_sms() && k.a_bytes % 1024 == 0) {
       k.wres_bytes = (int)wbytes;

@@ -282,7 +282,7 @@ def test_narrow_layers_with_resident_weights(nb, cin, cout, h, w, resident):
     x16, m16 = _nhwc16(x, dtype), _nhwc16(m, dtype)
     outs = []
     for res in ((True, False) if resident else (False,)):
-        _lib.set_option(_lib.OPT_RESIDENT_WEIGHTS, 1 if res else 0)
+        _lib.set_option(_lib.OPT_RESIDENT_WEIGHTS, 2 if res else 0)          # 2: wherever legal (the default takes it for N = 128)
         try:
             o_relu = torch.empty(nb, h, w, cout, device="cuda", dtype=dtype)
             o_mask = torch.empty(nb, h, w, cout, device="cuda", dtype=dtype)

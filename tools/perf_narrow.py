@@ -9,10 +9,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pesr_b200 import _lib, ops  # noqa: E402
 
 
+ONE = len(sys.argv) > 1 and sys.argv[1] == "one"      # two launches per variant only (for ncu)
+
+
 def chain(fn, n=20):
-    for _ in range(3):
+    for _ in range(2 if ONE else 3):
         fn()
     torch.cuda.synchronize()
+    if ONE:
+        return float("nan")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n):

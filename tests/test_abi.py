@@ -88,3 +88,21 @@ def test_pick_tile_covers_128_pixels_and_prefers_unpadded_tiles():
     assert ops.pick_tile(12, 12, 16, 512) == (8, 4, 4)           # 44% padding as 16x8 -> eight images per tile
     assert ops.pick_tile(24, 24, 16, 64) == (1, 16, 8)           # narrow layers keep one image per tile
     assert ops.pick_tile(339, 510, 1, 256) == (1, 8, 16)
+
+
+def test_library_sass_is_tcgen05_and_has_no_legacy_mma():
+    """tools/sass_opcodes.py over the built library: the tensor-core kernels issue UTCHMMA (tcgen05.mma, also as .2CTA
+    pairs) fed by UTMALDG (TMA) with LDTM epilogues, the gradient all-reduce uses LDGMC (multimem.ld_reduce), and no
+    HMMA (mma.sync / wmma) exists anywhere."""
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which("cuobjdump") is None:
+        import pytest
+        pytest.skip("cuobjdump not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sass_opcodes.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    for op in ("UTCHMMA=", "UTCHMMA.2CTA=", "UTMALDG.", "LDTM", "LDGMC.E.ADD.F32"):
+        assert op in r.stdout, op
+    assert "HMMA instructions anywhere: 0" in r.stdout

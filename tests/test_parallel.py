@@ -98,3 +98,34 @@ def test_bucketed_allreduce_gloo_world2(bucket_mb, cuts):
         p.join(120)
         assert p.exitcode == 0
     assert all(out.get(r) for r in range(world)), dict(out)
+
+
+def test_nccl_env_defaults_and_flat_buffer_allocator(monkeypatch):
+    """parallel.nccl_env_defaults: NCCL is confined to the SMs the persistent kernels leave free unless the user said
+    otherwise; engine_g.FlatGrads takes its persistent buffer from the allocator DataParallel installs (symmetric memory on
+    the GPU) and keeps handing out fresh buffers while the previous hand-out is unconsumed."""
+    sys.path.insert(0, ROOT)
+    from pesr_b200 import parallel
+    from pesr_b200.engine_g import FlatGrads
+    for k in ("NCCL_MAX_CTAS", "NCCL_MIN_CTAS", "PESR_RESERVE_SMS"):
+        monkeypatch.delenv(k, raising=False)
+    parallel.nccl_env_defaults()
+    assert os.environ["NCCL_MAX_CTAS"] == "4" and os.environ["NCCL_MIN_CTAS"] == "1"
+    monkeypatch.setenv("NCCL_MAX_CTAS", "16")
+    parallel.nccl_env_defaults()
+    assert os.environ["NCCL_MAX_CTAS"] == "16"            # an explicit setting wins
+    params = [torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(3, 3))]
+    calls = []
+
+    def alloc(numel, device):
+        calls.append(numel)
+        return torch.zeros(numel, device=device)
+    fg = FlatGrads(params, alloc=alloc)
+    assert fg.offsets[params[1]] == 8 and fg.numel == 20      # every tensor starts on a 16-byte boundary
+    a = fg.get(torch.device("cpu"))
+    assert calls == [20] and a.numel() == 20
+    b = fg.get(torch.device("cpu"))                            # no optimiser step in between: a fresh buffer, not `a`
+    assert b.data_ptr() != a.data_ptr() and calls == [20]
+    with torch.no_grad():
+        params[0].add_(1.0)                                     # what an optimiser step does to the version counter
+    assert fg.get(torch.device("cpu")).data_ptr() == a.data_ptr()
